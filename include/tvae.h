@@ -1,0 +1,194 @@
+/* libtvae_b200 — C ABI of the B200-native TEMPO-VAE hot path (sm_100a).
+ *
+ * The reference (cfpark00/TEMPO-VAE) has no FFI layer: its hot path is eager PyTorch
+ * (src/model.py, src/model_with_l2.py, src/train_utils.py:149-183). Each entry point below therefore cites the
+ * reference call site(s) whose arithmetic it replaces. INTEGRATION.md shows the ctypes binding a maintainer adds.
+ *
+ * Conventions
+ *  - every function returns 0 on success, < 0 on error; tvae_last_error() returns a thread-local message;
+ *  - the caller owns all device memory (incl. workspaces); the library never allocates device memory, never
+ *    synchronises and never changes the current device; work is enqueued on `stream`;
+ *  - activations are NHWC ("channels last"): element (n, h, w, c) of a tensor with channel pitch `pitch` lives at
+ *    ((n*H + h)*W + w)*pitch + c. bf16 tensors need pitch % 8 == 0, fp32 tensors pitch % 4 == 0, bases 16-B aligned;
+ *  - parameters keep the reference's own layouts (Conv2d OIHW fp32, ConvTranspose2d [Cin][Cout][kH][kW] fp32).
+ */
+#ifndef TVAE_H_
+#define TVAE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TVAE_ABI_VERSION 1
+
+typedef struct CUstream_st* tvae_stream_t; /* == cudaStream_t */
+
+const char* tvae_last_error(void);
+int32_t tvae_abi_version(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Convolution forward / data-gradient as an implicit GEMM on tcgen05 tensor cores.
+ * Replaces nn.Conv2d / nn.ConvTranspose2d forward (src/model.py:21-42; call sites :107-118,181,205,208-210,
+ * 240-247,270-278,358,402,502,544,609-614; src/model_with_l2.py:23,30) and autograd's input-gradient for them.
+ *   kind 0: RxR (R in {1,3}) stride-1 "same" convolution over x[N,H,W,C]; flip=1 negates the tap offsets (dgrad).
+ *           w packed [rows >= Cout][R*R*c_pad] (tvae_pack_weight).
+ *   kind 1: 2x2 stride-2 convolution, x[N,H,W,C] -> [N,H/2,W/2,Cout]; w packed [rows >= Cout][4*c_pad].
+ *   kind 2: 2x2 stride-2 transposed convolution, x[N,H,W,C] -> [N,2H,2W,Cout]; w packed [4*Cout][c_pad].
+ * Epilogue: + bias[Cout] (optional) + residual (optional, fp32, indexed like the output), then written as fp32
+ * and/or bf16 (either pointer may be NULL, not both).
+ */
+typedef struct {
+  const void* x;        /* bf16 NHWC */
+  int32_t N, H, W, C, x_pitch;
+  int32_t kind, R, flip;
+  const void* w;        /* bf16 packed, K-major */
+  int32_t w_rows, k_pitch, c_pad;
+  int32_t Cout;
+  const float* bias;
+  const float* residual;
+  int32_t res_pitch;
+  float* out_f32;
+  int32_t out_f32_pitch;
+  void* out_bf16;
+  int32_t out_bf16_pitch;
+  int32_t bn;           /* N tile, 0 = auto */
+} tvae_conv_args;
+int32_t tvae_conv_gemm(const tvae_conv_args* args, tvae_stream_t stream);
+
+/* Weight gradient: grad[m][n][tap] (=|+=) sum_pixels P[pixel][m] * Q[pixel (+) tap][n].
+ * Replaces autograd's weight-gradient of the same call sites.
+ *   kind 0: Q on the same [N,H,W] grid, RxR taps with zero padding   (Conv2d: P = dY, Q = x)
+ *   kind 1: Q on the 2x finer grid [N,2H,2W], tap (ty,tx) = pixel (2h+ty, 2w+tx)
+ *           (2x2 s2 Conv2d: P = dY, Q = x;  2x2 s2 ConvTranspose2d: P = x, Q = dY)
+ * workspace: tvae_wgrad_workspace_bytes(Cm, Cn, ntaps, splits) bytes of fp32 scratch (split-K partials).
+ */
+typedef struct {
+  const void* p;        /* bf16 NHWC [N,H,W,Cm] */
+  int32_t p_pitch, Cm;
+  const void* q;        /* bf16 NHWC */
+  int32_t q_pitch, Cn;
+  int32_t N, H, W;      /* grid of P */
+  int32_t kind, R;
+  int32_t splits;       /* >= 1; tvae_wgrad_splits() suggests a value */
+  float* workspace;
+  float* grad;          /* fp32 [Cm][Cn][taps] */
+  int32_t accumulate;   /* 0: overwrite grad, 1: add into it */
+} tvae_wgrad_args;
+int32_t tvae_wgrad_gemm(const tvae_wgrad_args* args, tvae_stream_t stream);
+int64_t tvae_wgrad_workspace_bytes(int32_t Cm, int32_t Cn, int32_t ntaps, int32_t splits);
+int32_t tvae_wgrad_splits(int32_t Cm, int32_t Cn, int32_t ntaps, int64_t pixels);
+
+/* out[(tr*Crow + cr)][tk*c_pad + c] = bf16(w[cr*s_row + c*s_col + (tr+tk)*s_tap]), zero for c in [C, c_pad).
+ * One of TR, TK is 1. Row pitch of `out` is TK*c_pad. */
+int32_t tvae_pack_weight(const float* w, void* out_bf16, int32_t Crow, int32_t TR, int32_t TK, int32_t C,
+                         int32_t c_pad, int64_t s_row, int64_t s_col, int64_t s_tap, tvae_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Layout conversion at the API boundary (the reference's tensors are NCHW fp32; src/train_utils.py:154).
+ */
+int32_t tvae_nchw_f32_to_nhwc_bf16(const float* x, void* out_bf16, int32_t N, int32_t C, int32_t HW,
+                                   int32_t out_pitch, tvae_stream_t stream);
+int32_t tvae_nhwc_f32_to_nchw_f32(const float* x, float* out, int32_t N, int32_t C, int32_t HW, int32_t in_pitch,
+                                  tvae_stream_t stream);
+int32_t tvae_nhwc_bf16_to_nchw_f32(const void* x_bf16, float* out, int32_t N, int32_t C, int32_t HW,
+                                   int32_t in_pitch, tvae_stream_t stream);
+int32_t tvae_f32_to_bf16(const float* x, void* out_bf16, int64_t n, tvae_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * GroupNorm (+ exact-erf GELU). Replaces nn.GroupNorm + nn.GELU (src/model.py:105,179,202,333-339,400,542;
+ * src/model_with_l2.py:24-25) and their backward.
+ *  x fp32 NHWC [N,HW,C] (pitch C); stats[N][G][2] = (mean, rstd); act: 0 = identity, 1 = GELU.
+ */
+int32_t tvae_gn_stats(const float* x, int32_t N, int32_t HW, int32_t C, int32_t G, float eps, float* stats,
+                      tvae_stream_t stream);
+int32_t tvae_gn_act_fwd(const float* x, const float* stats, const float* gamma, const float* beta, int32_t N,
+                        int32_t HW, int32_t C, int32_t G, int32_t act, void* out_bf16, tvae_stream_t stream);
+/* da: bf16 gradient wrt the activation output; gres (optional bf16) is added to dx (residual branch).
+ * dgamma/dbeta are overwritten. workspace: tvae_gn_bwd_workspace_bytes(N, C, G). */
+int64_t tvae_gn_bwd_workspace_bytes(int32_t N, int32_t C, int32_t G);
+int32_t tvae_gn_act_bwd(const float* x, const float* stats, const float* gamma, const float* beta, const void* da_bf16,
+                        const void* gres_bf16, int32_t N, int32_t HW, int32_t C, int32_t G, int32_t act,
+                        void* dx_bf16, float* dgamma, float* dbeta, float* workspace, tvae_stream_t stream);
+
+/* Column sums: out[c] = sum_rows x[row][c] (bias gradients). x bf16 [rows][pitch]; workspace rows_blocks*C floats:
+ * tvae_colsum_workspace_bytes(rows, C). */
+int64_t tvae_colsum_workspace_bytes(int64_t rows, int32_t C);
+int32_t tvae_colsum_bf16(const void* x_bf16, int64_t rows, int32_t C, int32_t pitch, float* out, float* workspace,
+                         tvae_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Mid-block self-attention core. Replaces the einsum/softmax/einsum of AttnBlock.forward (src/model.py:128-139)
+ * and its backward. Heads are channel-interleaved exactly as the reference's reshape(b, c_, n_heads, hw):
+ * head h owns channels {d*n_heads + h}. q,k,v: fp32 [B*T][pitch] at column offsets (fused qkv GEMM output).
+ * out: bf16 [B*T][C]; lse: fp32 [B][heads][T] (saved for backward). scale = (C/heads)^-0.5.
+ */
+int32_t tvae_attn_fwd(const float* q, const float* k, const float* v, int32_t pitch, int32_t B, int32_t T,
+                      int32_t C, int32_t heads, void* out_bf16, float* out_f32, float* lse, tvae_stream_t stream);
+/* d_out fp32 [B*T][C]; o fp32 [B*T][C] (forward output); dqkv: bf16 [B*T][3C] = (dq | dk | dv);
+ * workspace: B*heads*T floats. */
+int32_t tvae_attn_bwd(const float* q, const float* k, const float* v, int32_t pitch, const float* o,
+                      const float* d_out, const float* lse, int32_t B, int32_t T, int32_t C, int32_t heads,
+                      void* dqkv_bf16, float* workspace, tvae_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Reparameterisation + KL. Replaces DiagonalGaussianDistribution.__init__/sample/kl (src/model.py:47-75).
+ * moments fp32 NHWC [B*HW][2Z] = (mean | logvar); logvar is clamped to [-30, 20].
+ * eps: NCHW fp32 [B][Z][HW] supplied by the caller (the reference draws it on the CPU, src/model.py:61-65),
+ * or NULL to draw it with the Philox4x32-10 counter RNG keyed (seed, sample_offset + b, element).
+ * z_bf16: NHWC [B*HW][z_pitch] (operand of post_quant_conv); z_nchw / eps_out (optional) fp32 NCHW;
+ * kl[B] = 0.5 * sum(mean^2 + var - 1 - logvar) per sample.
+ */
+int32_t tvae_reparam_fwd(const float* moments, const float* eps, uint64_t seed, uint64_t sample_offset, int32_t B,
+                         int32_t HW, int32_t Z, void* z_bf16, int32_t z_pitch, float* z_nchw, float* eps_out,
+                         float* kl, tvae_stream_t stream);
+/* d_moments (bf16 NHWC [B*HW][2Z]) = d/d(moments) of  sum_i <dz_i, z_i> + kl_scale * sum_b kl[b],
+ * for up to two samples z_i = mean + std*eps_i (dz_i: fp32 NHWC [B*HW][Z], eps_i: fp32 NCHW; pair 2 optional). */
+int32_t tvae_reparam_bwd(const float* moments, const float* dz1, const float* eps1, const float* dz2,
+                         const float* eps2, float kl_scale, int32_t B, int32_t HW, int32_t Z, void* dmoments_bf16,
+                         tvae_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Reconstruction NLL. Replaces F.l1_loss / F.mse_loss + the logvar scaling (src/model.py:656-663).
+ *  x: bf16 NHWC [P][x_pitch]; xhat: fp32 NHWC [P][xh_pitch]; C valid channels; loss_type 0 = l1, 1 = l2.
+ *  sums[3] (fp64) = { sum rec, sum (x - xhat)^2, unused }; written by the kernel (no pre-zeroing needed).
+ *  dxhat (optional bf16 [P][dx_pitch], pad lanes zeroed) = d(rec)/d(xhat) * grad_scale, where the caller passes
+ *  grad_scale = exp(-logvar) / B (read from the device scalar `logvar`): dxhat = sign(xhat - x)*s or 2(xhat-x)*s.
+ *  workspace: tvae_nll_workspace_bytes().
+ */
+int64_t tvae_nll_workspace_bytes(void);
+int32_t tvae_nll_fwd(const void* x_bf16, int32_t x_pitch, const float* xhat, int32_t xh_pitch, int64_t P, int32_t C,
+                     int32_t loss_type, const float* logvar, int32_t batch, void* dxhat_bf16, int32_t dx_pitch,
+                     double* sums, double* workspace, tvae_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * L2-product head loss. Replaces AvgPool2d(4) + isnan mask + masked-mean MSE (src/model_with_l2.py:151-168).
+ *  pred: fp32 NHWC [B*hw][pred_pitch] (channel p = product p); target: fp32 [B][H][W] per product (NaN = invalid),
+ *  H = 4*h, W = 4*w. out[p] = {sum sq err, valid count} (fp64 [nprod][2]); dpred (bf16 NHWC [B*hw][dp_pitch]) =
+ *  weight[p] * 2 (pred - tgt) / count[p] on valid pixels, 0 elsewhere (computed by the _bwd call after the counts
+ *  are known).
+ */
+int32_t tvae_l2head_loss_fwd(const float* pred, int32_t pred_pitch, const float* const* targets, int32_t nprod,
+                             int32_t B, int32_t h, int32_t w, double* out, tvae_stream_t stream);
+int32_t tvae_l2head_loss_bwd(const float* pred, int32_t pred_pitch, const float* const* targets, int32_t nprod,
+                             int32_t B, int32_t h, int32_t w, const double* sums, const float* weights,
+                             float grad_scale, void* dpred_bf16, int32_t dp_pitch, tvae_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Optimiser. Replaces clip_grad_norm_(max_norm) + torch.optim.AdamW.step (src/train_utils.py:175-177;
+ * src/model.py:756-758). Flat fp32 buffers of n elements.
+ *  tvae_sumsq: out[0] (fp64) = sum g^2 (deterministic two-stage); workspace tvae_sumsq_workspace_bytes(n).
+ *  tvae_adamw: clip coefficient min(1, max_norm / (sqrt(sumsq) + 1e-6)) is computed on the device from `sumsq`
+ *  (NULL = no clipping); decoupled weight decay; bias correction from `step` (1-based, after increment).
+ */
+int64_t tvae_sumsq_workspace_bytes(int64_t n);
+int32_t tvae_sumsq(const float* g, int64_t n, double* out, double* workspace, tvae_stream_t stream);
+int32_t tvae_adamw(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                   float beta1, float beta2, float eps, float weight_decay, int64_t step, const double* sumsq,
+                   float max_norm, float grad_scale, tvae_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TVAE_H_ */

@@ -1,0 +1,380 @@
+// Implicit-GEMM convolution on tcgen05 tensor cores (sm_100a).
+//
+//   D[pixel, cout] = sum_{tap, cin} A[pixel + shift(tap), cin] * Wp[cout, tap, cin]  (+ bias, + residual)
+//
+// * A (activations, NHWC bf16) is never im2col'ed: every K-block is ONE 4-D TMA box
+//   {64 ch, bw, bh, bn} of the activation tensor at the tap-shifted coordinate; out-of-image taps are
+//   produced by TMA's out-of-bounds zero fill, so the 3x3 halo costs nothing. Stride-2 2x2 convs use one
+//   strided tensor-map view per tap. The box lands in shared memory as 128 rows x 128 B with the 128-byte
+//   swizzle, which is exactly the canonical K-major UMMA operand layout.
+// * B (packed weights [rows][taps * c_pad] bf16, K-major) is a 2-D TMA box {64, BN}.
+// * One elected thread issues tcgen05.mma (M=128, N=BN<=256, K=16) into a double-buffered fp32 TMEM
+//   accumulator (2 x 256 columns); a 4-warp epilogue drains it with tcgen05.ld while the next tile's MMAs run.
+// * Persistent: grid = #SMs, static round-robin over (m_tile, n_tile) with n fastest so the CTAs that share
+//   an A tile run at the same time and hit L2.
+//
+// Replaces the nn.Conv2d / nn.ConvTranspose2d call sites of the reference:
+//   src/model.py:21-42 (get_conv), :240-247 (2x2 s2 down), :270-278 (2x2 s2 transposed up),
+//   and their autograd dgrad (same kernel, transposed/flipped weight pack).
+#include "common.cuh"
+#include "tvae_internal.h"
+
+namespace tvae {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int A_STAGE_BYTES = BM * BK * 2;       // 16 KB
+constexpr int B_STAGE_BYTES = 256 * BK * 2;      // 32 KB (BN <= 256)
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int STAGES = 4;
+constexpr int NTHREADS = 192;                    // warp0: TMA, warp1: MMA + TMEM alloc, warps 2-5: epilogue
+constexpr int TMEM_COLS = 512;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+
+struct ConvMaps {
+  CUtensorMap a[4];
+  CUtensorMap b;
+};
+
+struct ConvParams {
+  int m_tiles, n_tiles, bn;
+  int num_kb, cblks, ntaps, last_k16;
+  int tiles_w, tiles_h, bw, bh, bnimg;
+  int dh[9], dw[9], amap[9];
+  // epilogue
+  int m_total, n_valid;
+  float* out_f32;
+  int ld_f32;
+  __nv_bfloat16* out_bf16;
+  int ld_bf16;
+  const float* bias;
+  const float* res;
+  int ld_res;
+  int up_mode, up_H, up_W, cout_per_tap;
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ ConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
+  uint8_t* smem = smem_raw + pad;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < 4; ++i) tma_prefetch_desc(&maps.a[i]);
+    tma_prefetch_desc(&maps.b);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int total_tiles = p.m_tiles * p.n_tiles;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx_bytes = A_STAGE_BYTES + (uint32_t)p.bn * (BK * 2);
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int mt = t / p.n_tiles, nt = t % p.n_tiles;
+        const int w0 = (mt % p.tiles_w) * p.bw;
+        const int h0 = ((mt / p.tiles_w) % p.tiles_h) * p.bh;
+        const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.bnimg;
+        const int brow = nt * p.bn;
+        int kb = 0;
+        for (int tap = 0; tap < p.ntaps; ++tap) {
+          const CUtensorMap* am = &maps.a[p.amap[tap]];
+          const int hh = h0 + p.dh[tap], ww = w0 + p.dw[tap];
+          for (int cb = 0; cb < p.cblks; ++cb, ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1, 1);
+            uint8_t* sa = smem + stage * STAGE_BYTES;
+            mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+            tma_load_4d(am, &full_bar[stage], sa, cb * BK, ww, hh, n0);
+            tma_load_2d(&maps.b, &full_bar[stage], sa + A_STAGE_BYTES, kb * BK, brow);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(BM, p.bn, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        mbar_wait(&tempty_bar[as], aphase ^ 1, 2);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)as * 256u;
+        int kb = 0;
+        for (int tap = 0; tap < p.ntaps; ++tap) {
+          for (int cb = 0; cb < p.cblks; ++cb, ++kb) {
+            mbar_wait(&full_bar[stage], phase, 3);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+            const uint64_t da = make_smem_desc_sw128(sa, 16, 1024);
+            const uint64_t db = make_smem_desc_sw128(sa + A_STAGE_BYTES, 16, 1024);
+            const int nk = (cb == p.cblks - 1) ? p.last_k16 : 4;
+            for (int k = 0; k < nk; ++k) {
+              // +32 B per K=16 step inside the 128-B swizzle row (descriptor address is in 16-B units)
+              umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            }
+            umma_commit(&empty_bar[stage]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+        umma_commit(&tfull_bar[as]);
+        as ^= 1;
+        if (as == 0) aphase ^= 1;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (4 warps, 128 rows)
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int mt = t / p.n_tiles, nt = t % p.n_tiles;
+      mbar_wait(&tfull_bar[as], aphase, 4);
+      tc_fence_after();
+      const long long pix = (long long)mt * BM + row;
+      const bool row_ok = pix < p.m_total;
+      int col0 = nt * p.bn;   // column in the (tap, cout) / cout space
+      long long opix = pix;
+      if (p.up_mode) {
+        const int tap = col0 / p.cout_per_tap;
+        col0 -= tap * p.cout_per_tap;
+        const int hw = p.up_H * p.up_W;
+        const int n = (int)(pix / hw);
+        const int rem = (int)(pix - (long long)n * hw);
+        const int h = rem / p.up_W, w = rem - h * p.up_W;
+        opix = ((long long)n * (2 * p.up_H) + (2 * h + (tap >> 1))) * (2 * p.up_W) + (2 * w + (tap & 1));
+      }
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * 256u;
+      for (int c = 0; c < p.bn; c += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr + (uint32_t)c, r);
+        tmem_ld_wait();
+        const int col = col0 + c;
+        if (row_ok && col < p.n_valid) {
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+          const bool full = (col + 16 <= p.n_valid);
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (full || col + j < p.n_valid) v[j] += __ldg(p.bias + col + j);
+          }
+          if (p.res) {
+            const float* rp = p.res + opix * p.ld_res + col;
+            if (full) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) {
+                const float4 x = *reinterpret_cast<const float4*>(rp + j);
+                v[j] += x.x; v[j + 1] += x.y; v[j + 2] += x.z; v[j + 3] += x.w;
+              }
+            } else {
+              for (int j = 0; j < 16; ++j)
+                if (col + j < p.n_valid) v[j] += rp[j];
+            }
+          }
+          if (p.out_f32) {
+            float* op = p.out_f32 + opix * p.ld_f32 + col;
+            if (full) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4)
+                *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+              for (int j = 0; j < 16; ++j)
+                if (col + j < p.n_valid) op[j] = v[j];
+            }
+          }
+          if (p.out_bf16) {
+            __nv_bfloat16* op = p.out_bf16 + opix * p.ld_bf16 + col;
+            if (full) {
+              uint4 a, b;
+              a.x = pack_bf16(v[0], v[1]); a.y = pack_bf16(v[2], v[3]);
+              a.z = pack_bf16(v[4], v[5]); a.w = pack_bf16(v[6], v[7]);
+              b.x = pack_bf16(v[8], v[9]); b.y = pack_bf16(v[10], v[11]);
+              b.z = pack_bf16(v[12], v[13]); b.w = pack_bf16(v[14], v[15]);
+              *reinterpret_cast<uint4*>(op) = a;
+              *reinterpret_cast<uint4*>(op + 8) = b;
+            } else {
+              for (int j = 0; j < 16; ++j)
+                if (col + j < p.n_valid) op[j] = __float2bfloat16(v[j]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      as ^= 1;
+      if (as == 0) aphase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+int pick_bn(int cout) {
+  if (cout <= 256) return (cout + 15) / 16 * 16;
+  const int nt = (cout + 255) / 256;
+  const int per = (cout + nt - 1) / nt;
+  return (per + 15) / 16 * 16;
+}
+
+}  // namespace
+
+}  // namespace tvae
+
+using namespace tvae;
+
+extern "C" int32_t tvae_conv_gemm(const tvae_conv_args* a, cudaStream_t stream) {
+  TVAE_CHECK(a != nullptr, "tvae_conv_gemm: null args");
+  TVAE_CHECK(a->x && a->w, "tvae_conv_gemm: null x/w");
+  TVAE_CHECK(a->out_f32 || a->out_bf16, "tvae_conv_gemm: no output");
+  TVAE_CHECK(a->kind >= 0 && a->kind <= 2, "tvae_conv_gemm: bad kind %d", a->kind);
+  TVAE_CHECK(a->x_pitch % 8 == 0 && a->k_pitch % 8 == 0, "tvae_conv_gemm: pitches must be multiples of 8 elements");
+  TVAE_CHECK((reinterpret_cast<uintptr_t>(a->x) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->w) & 15) == 0,
+             "tvae_conv_gemm: x/w must be 16-byte aligned");
+  TVAE_CHECK(a->c_pad % 64 == 0 && a->c_pad >= a->C, "tvae_conv_gemm: c_pad must be a multiple of 64 and >= C");
+
+  ConvMaps maps;
+  ConvParams p;
+  memset(&p, 0, sizeof(p));
+
+  // geometry of the A-operand pixel grid (== output grid for kind 0/1, == input grid for kind 2)
+  int gH = a->H, gW = a->W;
+  if (a->kind == 1) {
+    TVAE_CHECK(a->H % 2 == 0 && a->W % 2 == 0, "2x2 stride-2 conv needs even H, W");
+    gH = a->H / 2; gW = a->W / 2;
+  }
+  TVAE_CHECK(pixel_box(gH, gW, BM, &p.bw, &p.bh, &p.bnimg),
+             "tvae_conv_gemm: unsupported spatial size %dx%d (W must be a power of two < 128 or a multiple of 128)",
+             gH, gW);
+  p.tiles_w = gW / p.bw;
+  p.tiles_h = gH / p.bh;
+  const long long m_total = (long long)a->N * gH * gW;
+  TVAE_CHECK(m_total < (1ll << 31), "tvae_conv_gemm: too many pixels");
+  p.m_total = (int)m_total;
+  p.m_tiles = (int)((m_total + BM - 1) / BM);
+
+  p.cblks = a->c_pad / BK;
+  const int c_rem = a->C - (p.cblks - 1) * BK;             // valid channels in the last block
+  TVAE_CHECK(c_rem > 0, "tvae_conv_gemm: c_pad too large for C");
+  p.last_k16 = (c_rem + 15) / 16;
+
+  const uint64_t pitchB = (uint64_t)a->x_pitch * 2;
+  if (a->kind == 0) {
+    TVAE_CHECK(a->R == 1 || a->R == 3, "tvae_conv_gemm: R must be 1 or 3");
+    p.ntaps = a->R * a->R;
+    for (int t = 0; t < p.ntaps; ++t) {
+      int dh = t / a->R - a->R / 2, dw = t % a->R - a->R / 2;
+      if (a->flip) { dh = -dh; dw = -dw; }
+      p.dh[t] = dh; p.dw[t] = dw; p.amap[t] = 0;
+    }
+    uint64_t dims[4] = {(uint64_t)a->C, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->N};
+    uint64_t strides[3] = {pitchB, pitchB * a->W, pitchB * a->W * a->H};
+    uint32_t box[4] = {BK, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bnimg};
+    for (int i = 0; i < 4; ++i)
+      if (make_tmap_bf16(&maps.a[i], a->x, 4, dims, strides, box)) return -3;
+  } else if (a->kind == 1) {
+    p.ntaps = 4;
+    for (int t = 0; t < 4; ++t) {
+      p.dh[t] = 0; p.dw[t] = 0; p.amap[t] = t;
+      const int ty = t >> 1, tx = t & 1;
+      const uint8_t* base = reinterpret_cast<const uint8_t*>(a->x) + ((size_t)ty * a->W + tx) * pitchB;
+      uint64_t dims[4] = {(uint64_t)a->C, (uint64_t)gW, (uint64_t)gH, (uint64_t)a->N};
+      uint64_t strides[3] = {2 * pitchB, 2 * pitchB * a->W, pitchB * a->W * a->H};
+      uint32_t box[4] = {BK, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bnimg};
+      if (make_tmap_bf16(&maps.a[t], base, 4, dims, strides, box)) return -3;
+    }
+  } else {
+    p.ntaps = 1;
+    p.dh[0] = p.dw[0] = 0; p.amap[0] = 0;
+    uint64_t dims[4] = {(uint64_t)a->C, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->N};
+    uint64_t strides[3] = {pitchB, pitchB * a->W, pitchB * a->W * a->H};
+    uint32_t box[4] = {BK, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bnimg};
+    for (int i = 0; i < 4; ++i)
+      if (make_tmap_bf16(&maps.a[i], a->x, 4, dims, strides, box)) return -3;
+  }
+  p.num_kb = p.ntaps * p.cblks;
+  TVAE_CHECK(a->k_pitch >= p.num_kb * BK, "tvae_conv_gemm: k_pitch %d < taps*c_pad %d", a->k_pitch, p.num_kb * BK);
+
+  // N tiling
+  int n_cols;  // total GEMM columns
+  if (a->kind == 2) {
+    TVAE_CHECK(a->Cout % 16 == 0, "transposed conv needs Cout %% 16 == 0");
+    int bn = a->bn;
+    if (bn <= 0) {
+      bn = 16;
+      for (int c = 256; c >= 16; c -= 16)
+        if (a->Cout % c == 0) { bn = c; break; }
+    }
+    TVAE_CHECK(a->Cout % bn == 0, "transposed conv: bn must divide Cout");
+    p.bn = bn;
+    n_cols = 4 * a->Cout;
+    p.up_mode = 1; p.up_H = a->H; p.up_W = a->W; p.cout_per_tap = a->Cout;
+  } else {
+    p.bn = a->bn > 0 ? a->bn : pick_bn(a->Cout);
+    n_cols = a->Cout;
+  }
+  TVAE_CHECK(p.bn % 16 == 0 && p.bn >= 16 && p.bn <= 256, "tvae_conv_gemm: bad bn %d", p.bn);
+  p.n_tiles = (n_cols + p.bn - 1) / p.bn;
+  p.n_valid = a->Cout;
+  TVAE_CHECK(a->w_rows >= n_cols, "tvae_conv_gemm: packed weight has %d rows, need %d", a->w_rows, n_cols);
+  {
+    uint64_t dims[2] = {(uint64_t)a->k_pitch, (uint64_t)a->w_rows};
+    uint64_t strides[1] = {(uint64_t)a->k_pitch * 2};
+    uint32_t box[2] = {BK, (uint32_t)p.bn};
+    if (make_tmap_bf16(&maps.b, a->w, 2, dims, strides, box)) return -3;
+  }
+
+  p.out_f32 = a->out_f32; p.ld_f32 = a->out_f32_pitch;
+  p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(a->out_bf16); p.ld_bf16 = a->out_bf16_pitch;
+  p.bias = a->bias;
+  p.res = a->residual; p.ld_res = a->res_pitch;
+  if (p.out_f32) TVAE_CHECK(p.ld_f32 % 4 == 0 && (reinterpret_cast<uintptr_t>(p.out_f32) & 15) == 0, "out_f32 alignment");
+  if (p.out_bf16) TVAE_CHECK(p.ld_bf16 % 8 == 0 && (reinterpret_cast<uintptr_t>(p.out_bf16) & 15) == 0, "out_bf16 alignment");
+  if (p.res) TVAE_CHECK(p.ld_res % 4 == 0 && (reinterpret_cast<uintptr_t>(p.res) & 15) == 0, "residual alignment");
+
+  TVAE_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  const int total = p.m_tiles * p.n_tiles;
+  int grid = num_sms();
+  if (grid > total) grid = total;
+  conv_gemm_kernel<<<grid, NTHREADS, SMEM_BYTES, stream>>>(maps, p);
+  TVAE_CUDA(cudaGetLastError());
+  return 0;
+}

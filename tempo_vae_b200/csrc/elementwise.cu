@@ -1,0 +1,565 @@
+// HBM-bound kernels of the TEMPO-VAE hot path: layout conversion, weight packing, GroupNorm(+GELU) forward and
+// backward, bias-gradient column sums. All are streaming kernels with 16-byte vector accesses on the NHWC
+// channel dimension; reductions are two-stage and order-fixed (bit-reproducible run to run).
+#include "common.cuh"
+#include "tvae_internal.h"
+
+namespace tvae {
+namespace {
+
+constexpr int EW_THREADS = 256;
+
+inline int ew_grid(long long work_items, int per_block = EW_THREADS, int max_blocks = 148 * 16) {
+  long long g = (work_items + per_block - 1) / per_block;
+  if (g < 1) g = 1;
+  if (g > max_blocks) g = max_blocks;
+  return (int)g;
+}
+
+// ---------------------------------------------------------------------------------------------- pack weights
+__global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Crow, int TR,
+                                   int TK, int C, int c_pad, long long s_row, long long s_col, long long s_tap) {
+  const long long kp = (long long)TK * c_pad;
+  const long long total = (long long)TR * Crow * kp;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / kp;
+    const int kk = (int)(i - row * kp);
+    const int tk = kk / c_pad, c = kk - tk * c_pad;
+    const int tr = (int)(row / Crow), cr = (int)(row - (long long)tr * Crow);
+    float v = 0.f;
+    if (c < C) v = w[cr * s_row + c * s_col + (tr + tk) * s_tap];
+    out[i] = __float2bfloat16(v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- transposes
+// NCHW fp32 -> NHWC bf16 (pad lanes [C, pitch) zeroed). Tile: 64 channels x 64 pixels.
+__global__ void nchw_to_nhwc_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int C, int HW,
+                                         int pitch) {
+  __shared__ float tile[64][65];
+  const int n = blockIdx.z;
+  const int c0 = blockIdx.y * 64, p0 = blockIdx.x * 64;
+  const float* xn = x + (long long)n * C * HW;
+  {
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+#pragma unroll 4
+    for (int i = ty; i < 64; i += 4) {
+      const int c = c0 + i, p = p0 + tx;
+      tile[i][tx] = (c < C && p < HW) ? xn[(long long)c * HW + p] : 0.f;
+    }
+  }
+  __syncthreads();
+  {
+    const int cx = threadIdx.x & 31, py = threadIdx.x >> 5;
+    const int c = c0 + 2 * cx;
+#pragma unroll 4
+    for (int i = py; i < 64; i += 8) {
+      const int p = p0 + i;
+      if (p < HW && c < pitch) {
+        __nv_bfloat16* o = out + ((long long)n * HW + p) * pitch + c;
+        if (c + 1 < pitch) {
+          *reinterpret_cast<uint32_t*>(o) = pack_bf16(tile[2 * cx][i], tile[2 * cx + 1][i]);
+        } else {
+          o[0] = __float2bfloat16(tile[2 * cx][i]);
+        }
+      }
+    }
+  }
+}
+
+// NHWC (fp32 or bf16, pitch) -> NCHW fp32
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T* __restrict__ x, float* __restrict__ out, int C, int HW, int pitch) {
+  __shared__ float tile[64][65];
+  const int n = blockIdx.z;
+  const int c0 = blockIdx.y * 64, p0 = blockIdx.x * 64;
+  {
+    const int cx = threadIdx.x & 63, py = threadIdx.x >> 6;
+#pragma unroll 4
+    for (int i = py; i < 64; i += 4) {
+      const int c = c0 + cx, p = p0 + i;
+      float v = 0.f;
+      if (c < C && p < HW) v = (float)x[((long long)n * HW + p) * pitch + c];
+      tile[i][cx] = v;
+    }
+  }
+  __syncthreads();
+  {
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+    float* on = out + (long long)n * C * HW;
+#pragma unroll 4
+    for (int i = ty; i < 64; i += 4) {
+      const int c = c0 + i, p = p0 + tx;
+      if (c < C && p < HW) on[(long long)c * HW + p] = tile[tx][i];
+    }
+  }
+}
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, long long n) {
+  const long long n4 = n / 4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    uint2 o;
+    o.x = pack_bf16(v.x, v.y);
+    o.y = pack_bf16(v.z, v.w);
+    reinterpret_cast<uint2*>(out)[i] = o;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const long long i = n4 * 4 + threadIdx.x;
+    out[i] = __float2bfloat16(x[i]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- GroupNorm stats
+// one block per (n, g); x fp32 [N][HW][C]
+template <int VEC>
+__global__ void gn_stats_kernel(const float* __restrict__ x, int HW, int C, int G, float eps,
+                                float* __restrict__ stats) {
+  __shared__ double red[32];
+  const int n = blockIdx.x / G, g = blockIdx.x % G;
+  const int gs = C / G;
+  const int U = gs / VEC;
+  const float* base = x + (long long)n * HW * C + (long long)g * gs;
+  const long long total = (long long)HW * U;
+  float s1 = 0.f, s2 = 0.f;
+  double d1 = 0.0, d2 = 0.0;
+  int cnt = 0;
+  for (long long e = threadIdx.x; e < total; e += blockDim.x) {
+    const long long p = e / U;
+    const int u = (int)(e - p * U);
+    const float* ptr = base + p * C + u * VEC;
+    if (VEC == 4) {
+      const float4 v = *reinterpret_cast<const float4*>(ptr);
+      s1 += (v.x + v.y) + (v.z + v.w);
+      s2 += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+    } else {
+      const float v = *ptr;
+      s1 += v;
+      s2 += v * v;
+    }
+    if (++cnt == 64) {  // bound the fp32 run length, continue in fp64
+      d1 += s1; d2 += s2; s1 = s2 = 0.f; cnt = 0;
+    }
+  }
+  d1 += s1; d2 += s2;
+  const double t1 = block_sum(d1, red);
+  const double t2 = block_sum(d2, red);
+  if (threadIdx.x == 0) {
+    const double cntd = (double)HW * gs;
+    const double mean = t1 / cntd;
+    double var = t2 / cntd - mean * mean;
+    if (var < 0) var = 0;
+    stats[2 * blockIdx.x] = (float)mean;
+    stats[2 * blockIdx.x + 1] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- GN apply (+GELU)
+template <int VEC>
+__global__ void gn_act_fwd_kernel(const float* __restrict__ x, const float* __restrict__ stats,
+                                  const float* __restrict__ gamma, const float* __restrict__ beta, long long rows,
+                                  int HW, int C, int G, int act, __nv_bfloat16* __restrict__ out) {
+  const int gs = C / G;
+  const int U = C / VEC;
+  const long long total = rows * U;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / U;
+    const int c = (int)(i - row * U) * VEC;
+    const int n = (int)(row / HW);
+    const int g = c / gs;
+    const float mean = stats[2 * (n * G + g)], rstd = stats[2 * (n * G + g) + 1];
+    const float* xp = x + row * C + c;
+    if (VEC == 8) {
+      const float4 a = *reinterpret_cast<const float4*>(xp);
+      const float4 b = *reinterpret_cast<const float4*>(xp + 4);
+      const float4 g0 = *reinterpret_cast<const float4*>(gamma + c);
+      const float4 g1 = *reinterpret_cast<const float4*>(gamma + c + 4);
+      const float4 b0 = *reinterpret_cast<const float4*>(beta + c);
+      const float4 b1 = *reinterpret_cast<const float4*>(beta + c + 4);
+      float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+      const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float y = (v[j] - mean) * rstd * gm[j] + bt[j];
+        v[j] = act ? gelu_f(y) : y;
+      }
+      uint4 o;
+      o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]);
+      o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
+      *reinterpret_cast<uint4*>(out + row * C + c) = o;
+    } else {
+      float y = (*xp - mean) * rstd * gamma[c] + beta[c];
+      out[row * C + c] = __float2bfloat16(act ? gelu_f(y) : y);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- GN backward
+// Stage A: one block per (n, g). Per-channel sums S1[n][c] = sum dy, S2[n][c] = sum dy * xhat, where
+// dy = da * act'(gamma * xhat + beta); then the group means m1 = mean(dy*gamma), m2 = mean(dy*gamma*xhat).
+template <int VEC>
+__global__ void gn_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ stats,
+                                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                                     const __nv_bfloat16* __restrict__ da, int HW, int C, int G, int act, int N,
+                                     float* __restrict__ ws) {
+  extern __shared__ float sm[];  // [blockDim][2*VEC]
+  __shared__ float red[32];
+  const int n = blockIdx.x / G, g = blockIdx.x % G;
+  const int gs = C / G;
+  const int U = gs / VEC;            // channel units per group (<= blockDim)
+  const int lanes = blockDim.x / U;  // pixel lanes
+  const int u = threadIdx.x % U, lane = threadIdx.x / U;
+  const float mean = stats[2 * blockIdx.x], rstd = stats[2 * blockIdx.x + 1];
+  const int c0 = g * gs + u * VEC;
+  float gm[VEC], bt[VEC], s1[VEC], s2[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    gm[j] = gamma[c0 + j]; bt[j] = beta[c0 + j]; s1[j] = 0.f; s2[j] = 0.f;
+  }
+  if (lane < lanes) {
+    for (int p = lane; p < HW; p += lanes) {
+      const long long off = ((long long)n * HW + p) * C + c0;
+      float xv[VEC], dv[VEC];
+      if (VEC == 8) {
+        const float4 a = *reinterpret_cast<const float4*>(x + off);
+        const float4 b = *reinterpret_cast<const float4*>(x + off + 4);
+        xv[0] = a.x; xv[1] = a.y; xv[2] = a.z; xv[3] = a.w; xv[4] = b.x; xv[5] = b.y; xv[6] = b.z; xv[7] = b.w;
+        const uint4 d = *reinterpret_cast<const uint4*>(da + off);
+        const uint32_t dw[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          dv[2 * j] = bf16_bits_to_f(dw[j] & 0xffffu);
+          dv[2 * j + 1] = bf16_bits_to_f(dw[j] >> 16);
+        }
+      } else {
+        xv[0] = x[off];
+        dv[0] = __bfloat162float(da[off]);
+      }
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        const float xh = (xv[j] - mean) * rstd;
+        float dy = dv[j];
+        if (act) dy *= gelu_grad_f(xh * gm[j] + bt[j]);
+        s1[j] += dy;
+        s2[j] += dy * xh;
+      }
+    }
+  }
+  float* mine = sm + (size_t)threadIdx.x * 2 * VEC;
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) { mine[j] = s1[j]; mine[VEC + j] = s2[j]; }
+  __syncthreads();
+  // fixed-order reduction over pixel lanes
+  float gsum1 = 0.f, gsum2 = 0.f;
+  for (int t = threadIdx.x; t < U * 2 * VEC; t += blockDim.x) {
+    const int uu = t / (2 * VEC), k = t % (2 * VEC);
+    float acc = 0.f;
+    for (int l = 0; l < lanes; ++l) acc += sm[(size_t)(l * U + uu) * 2 * VEC + k];
+    const int c = g * gs + uu * VEC + (k % VEC);
+    // ws layout: [2][N][C] per-channel sums, then [N][G][2] group means
+    ws[((long long)(k / VEC) * N + n) * C + c] = acc;
+    const float gmc = gamma[c];
+    if (k < VEC) gsum1 += acc * gmc; else gsum2 += acc * gmc;
+  }
+  const float t1 = block_sum(gsum1, red);
+  const float t2 = block_sum(gsum2, red);
+  if (threadIdx.x == 0) {
+    const float inv = 1.0f / ((float)HW * (float)gs);
+    float* gm_out = ws + 2ll * N * C + 2ll * blockIdx.x;
+    gm_out[0] = t1 * inv;
+    gm_out[1] = t2 * inv;
+  }
+}
+
+// dgamma[c] = sum_n S2[n][c], dbeta[c] = sum_n S1[n][c]
+__global__ void gn_bwd_param_kernel(const float* __restrict__ ws, int N, int C, float* __restrict__ dgamma,
+                                    float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float a = 0.f, b = 0.f;
+  for (int n = 0; n < N; ++n) {
+    b += ws[(long long)n * C + c];
+    a += ws[((long long)N + n) * C + c];
+  }
+  dgamma[c] = a;
+  dbeta[c] = b;
+}
+
+// Stage B: dx = rstd * (dy*gamma - m1 - xhat*m2) (+ gres)
+template <int VEC>
+__global__ void gn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ stats,
+                                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                                    const __nv_bfloat16* __restrict__ da, const __nv_bfloat16* __restrict__ gres,
+                                    const float* __restrict__ gmeans, long long rows, int HW, int C, int G, int act,
+                                    __nv_bfloat16* __restrict__ dx) {
+  const int gs = C / G;
+  const int U = C / VEC;
+  const long long total = rows * U;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / U;
+    const int c = (int)(i - row * U) * VEC;
+    const int n = (int)(row / HW);
+    const int g = c / gs;
+    const int sg = n * G + g;
+    const float mean = stats[2 * sg], rstd = stats[2 * sg + 1];
+    const float m1 = gmeans[2 * sg], m2 = gmeans[2 * sg + 1];
+    const long long off = row * C + c;
+    float xv[VEC], dv[VEC], rv[VEC];
+    if (VEC == 8) {
+      const float4 a = *reinterpret_cast<const float4*>(x + off);
+      const float4 b = *reinterpret_cast<const float4*>(x + off + 4);
+      xv[0] = a.x; xv[1] = a.y; xv[2] = a.z; xv[3] = a.w; xv[4] = b.x; xv[5] = b.y; xv[6] = b.z; xv[7] = b.w;
+      const uint4 d = *reinterpret_cast<const uint4*>(da + off);
+      const uint32_t dw[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        dv[2 * j] = bf16_bits_to_f(dw[j] & 0xffffu);
+        dv[2 * j + 1] = bf16_bits_to_f(dw[j] >> 16);
+      }
+      if (gres) {
+        const uint4 r = *reinterpret_cast<const uint4*>(gres + off);
+        const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          rv[2 * j] = bf16_bits_to_f(rw[j] & 0xffffu);
+          rv[2 * j + 1] = bf16_bits_to_f(rw[j] >> 16);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) rv[j] = 0.f;
+      }
+    } else {
+      xv[0] = x[off];
+      dv[0] = __bfloat162float(da[off]);
+      rv[0] = gres ? __bfloat162float(gres[off]) : 0.f;
+    }
+    float o[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const float gmj = gamma[c + j];
+      const float xh = (xv[j] - mean) * rstd;
+      float dy = dv[j];
+      if (act) dy *= gelu_grad_f(xh * gmj + beta[c + j]);
+      o[j] = rstd * (dy * gmj - m1 - xh * m2) + rv[j];
+    }
+    if (VEC == 8) {
+      uint4 w;
+      w.x = pack_bf16(o[0], o[1]); w.y = pack_bf16(o[2], o[3]);
+      w.z = pack_bf16(o[4], o[5]); w.w = pack_bf16(o[6], o[7]);
+      *reinterpret_cast<uint4*>(dx + off) = w;
+    } else {
+      dx[off] = __float2bfloat16(o[0]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- column sums
+// block (bx, by): channel-unit tile by, row chunk bx. Threads = UL unit-lanes x RL row-lanes.
+template <int VEC>
+__global__ void colsum_partial_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int C, int pitch, int UL,
+                                      long long rows_per_block, float* __restrict__ ws) {
+  extern __shared__ float sm[];  // [blockDim][VEC]
+  const int RL = blockDim.x / UL;
+  const int ul = threadIdx.x % UL, rl = threadIdx.x / UL;
+  const int c = (blockIdx.y * UL + ul) * VEC;
+  const long long r0 = blockIdx.x * rows_per_block;
+  long long r1 = r0 + rows_per_block;
+  if (r1 > rows) r1 = rows;
+  float acc[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
+  if (c < C && rl < RL) {
+    for (long long r = r0 + rl; r < r1; r += RL) {
+      const __nv_bfloat16* p = x + r * pitch + c;
+      if (VEC == 8) {
+        const uint4 d = *reinterpret_cast<const uint4*>(p);
+        const uint32_t dw[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc[2 * j] += bf16_bits_to_f(dw[j] & 0xffffu);
+          acc[2 * j + 1] += bf16_bits_to_f(dw[j] >> 16);
+        }
+      } else if (VEC == 4) {
+        const uint2 d = *reinterpret_cast<const uint2*>(p);
+        acc[0] += bf16_bits_to_f(d.x & 0xffffu); acc[1] += bf16_bits_to_f(d.x >> 16);
+        acc[2] += bf16_bits_to_f(d.y & 0xffffu); acc[3] += bf16_bits_to_f(d.y >> 16);
+      } else {
+        acc[0] += __bfloat162float(*p);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) sm[(size_t)threadIdx.x * VEC + j] = acc[j];
+  __syncthreads();
+  if (threadIdx.x < UL * VEC) {
+    const int uu = threadIdx.x / VEC, j = threadIdx.x % VEC;
+    const int cc = (blockIdx.y * UL + uu) * VEC + j;
+    if (cc < C) {
+      float s = 0.f;
+      for (int l = 0; l < RL; ++l) s += sm[(size_t)(l * UL + uu) * VEC + j];
+      ws[(long long)blockIdx.x * C + cc] = s;
+    }
+  }
+}
+__global__ void colsum_final_kernel(const float* __restrict__ ws, int nblocks, int C, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s = 0.f;
+  for (int b = 0; b < nblocks; ++b) s += ws[(long long)b * C + c];
+  out[c] = s;
+}
+
+inline int colsum_blocks(long long rows) {
+  long long b = (rows + 255) / 256;
+  if (b > 592) b = 592;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace
+}  // namespace tvae
+
+using namespace tvae;
+
+extern "C" int32_t tvae_pack_weight(const float* w, void* out, int32_t Crow, int32_t TR, int32_t TK, int32_t C,
+                                    int32_t c_pad, int64_t s_row, int64_t s_col, int64_t s_tap, cudaStream_t stream) {
+  TVAE_CHECK(w && out, "tvae_pack_weight: null pointer");
+  TVAE_CHECK(TR == 1 || TK == 1, "tvae_pack_weight: one of TR, TK must be 1");
+  TVAE_CHECK(c_pad >= C, "tvae_pack_weight: c_pad < C");
+  const long long total = (long long)TR * Crow * TK * c_pad;
+  pack_weight_kernel<<<ew_grid(total), EW_THREADS, 0, stream>>>(w, reinterpret_cast<__nv_bfloat16*>(out), Crow, TR, TK,
+                                                               C, c_pad, s_row, s_col, s_tap);
+  TVAE_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int32_t tvae_nchw_f32_to_nhwc_bf16(const float* x, void* out, int32_t N, int32_t C, int32_t HW,
+                                              int32_t pitch, cudaStream_t stream) {
+  TVAE_CHECK(x && out, "tvae_nchw_f32_to_nhwc_bf16: null pointer");
+  TVAE_CHECK(pitch >= C && pitch % 2 == 0, "tvae_nchw_f32_to_nhwc_bf16: bad pitch");
+  dim3 grid((HW + 63) / 64, (pitch + 63) / 64, N);
+  nchw_to_nhwc_bf16_kernel<<<grid, 256, 0, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(out), C, HW, pitch);
+  TVAE_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int32_t tvae_nhwc_f32_to_nchw_f32(const float* x, float* out, int32_t N, int32_t C, int32_t HW,
+                                             int32_t pitch, cudaStream_t stream) {
+  TVAE_CHECK(x && out, "tvae_nhwc_f32_to_nchw_f32: null pointer");
+  dim3 grid((HW + 63) / 64, (C + 63) / 64, N);
+  nhwc_to_nchw_kernel<float><<<grid, 256, 0, stream>>>(x, out, C, HW, pitch);
+  TVAE_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int32_t tvae_nhwc_bf16_to_nchw_f32(const void* x, float* out, int32_t N, int32_t C, int32_t HW,
+                                              int32_t pitch, cudaStream_t stream) {
+  TVAE_CHECK(x && out, "tvae_nhwc_bf16_to_nchw_f32: null pointer");
+  dim3 grid((HW + 63) / 64, (C + 63) / 64, N);
+  nhwc_to_nchw_kernel<__nv_bfloat16>
+      <<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), out, C, HW, pitch);
+  TVAE_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int32_t tvae_f32_to_bf16(const float* x, void* out, int64_t n, cudaStream_t stream) {
+  TVAE_CHECK(x && out, "tvae_f32_to_bf16: null pointer");
+  f32_to_bf16_kernel<<<ew_grid(n / 4 + 1), EW_THREADS, 0, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(out), n);
+  TVAE_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int32_t tvae_gn_stats(const float* x, int32_t N, int32_t HW, int32_t C, int32_t G, float eps, float* stats,
+                                 cudaStream_t stream) {
+  TVAE_CHECK(x && stats, "tvae_gn_stats: null pointer");
+  TVAE_CHECK(G > 0 && C % G == 0, "tvae_gn_stats: C %% G != 0");
+  const int gs = C / G;
+  if (gs % 4 == 0 && C % 4 == 0)
+    gn_stats_kernel<4><<<N * G, 512, 0, stream>>>(x, HW, C, G, eps, stats);
+  else
+    gn_stats_kernel<1><<<N * G, 512, 0, stream>>>(x, HW, C, G, eps, stats);
+  TVAE_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int32_t tvae_gn_act_fwd(const float* x, const float* stats, const float* gamma, const float* beta,
+                                   int32_t N, int32_t HW, int32_t C, int32_t G, int32_t act, void* out,
+                                   cudaStream_t stream) {
+  TVAE_CHECK(x && stats && gamma && beta && out, "tvae_gn_act_fwd: null pointer");
+  TVAE_CHECK(G > 0 && C % G == 0, "tvae_gn_act_fwd: C %% G != 0");
+  const long long rows = (long long)N * HW;
+  const int gs = C / G;
+  if (gs % 8 == 0)
+    gn_act_fwd_kernel<8><<<ew_grid(rows * (C / 8)), EW_THREADS, 0, stream>>>(
+        x, stats, gamma, beta, rows, HW, C, G, act, reinterpret_cast<__nv_bfloat16*>(out));
+  else
+    gn_act_fwd_kernel<1><<<ew_grid(rows * C), EW_THREADS, 0, stream>>>(x, stats, gamma, beta, rows, HW, C, G, act,
+                                                                        reinterpret_cast<__nv_bfloat16*>(out));
+  TVAE_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int64_t tvae_gn_bwd_workspace_bytes(int32_t N, int32_t C, int32_t G) {
+  return (2ll * N * C + 2ll * N * G) * 4;
+}
+
+extern "C" int32_t tvae_gn_act_bwd(const float* x, const float* stats, const float* gamma, const float* beta,
+                                   const void* da, const void* gres, int32_t N, int32_t HW, int32_t C, int32_t G,
+                                   int32_t act, void* dx, float* dgamma, float* dbeta, float* ws,
+                                   cudaStream_t stream) {
+  TVAE_CHECK(x && stats && gamma && beta && da && dx && dgamma && dbeta && ws, "tvae_gn_act_bwd: null pointer");
+  TVAE_CHECK(G > 0 && C % G == 0, "tvae_gn_act_bwd: C %% G != 0");
+  const int gs = C / G;
+  const long long rows = (long long)N * HW;
+  const __nv_bfloat16* dap = reinterpret_cast<const __nv_bfloat16*>(da);
+  const __nv_bfloat16* grp = reinterpret_cast<const __nv_bfloat16*>(gres);
+  __nv_bfloat16* dxp = reinterpret_cast<__nv_bfloat16*>(dx);
+  const float* gmeans = ws + 2ll * N * C;
+  if (gs % 8 == 0 && gs / 8 <= 256) {
+    const int threads = 256;
+    gn_bwd_reduce_kernel<8><<<N * G, threads, threads * 16 * sizeof(float), stream>>>(x, stats, gamma, beta, dap, HW, C,
+                                                                                     G, act, N, ws);
+    TVAE_CUDA(cudaGetLastError());
+    gn_bwd_param_kernel<<<(C + 127) / 128, 128, 0, stream>>>(ws, N, C, dgamma, dbeta);
+    gn_bwd_apply_kernel<8><<<ew_grid(rows * (C / 8)), EW_THREADS, 0, stream>>>(x, stats, gamma, beta, dap, grp, gmeans,
+                                                                              rows, HW, C, G, act, dxp);
+  } else {
+    TVAE_CHECK(gs <= 256, "tvae_gn_act_bwd: group size %d > 256 needs a multiple of 8", gs);
+    const int threads = 256;
+    gn_bwd_reduce_kernel<1><<<N * G, threads, threads * 2 * sizeof(float), stream>>>(x, stats, gamma, beta, dap, HW, C,
+                                                                                    G, act, N, ws);
+    TVAE_CUDA(cudaGetLastError());
+    gn_bwd_param_kernel<<<(C + 127) / 128, 128, 0, stream>>>(ws, N, C, dgamma, dbeta);
+    gn_bwd_apply_kernel<1><<<ew_grid(rows * C), EW_THREADS, 0, stream>>>(x, stats, gamma, beta, dap, grp, gmeans, rows,
+                                                                        HW, C, G, act, dxp);
+  }
+  TVAE_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int64_t tvae_colsum_workspace_bytes(int64_t rows, int32_t C) {
+  return (int64_t)colsum_blocks(rows) * C * 4;
+}
+
+extern "C" int32_t tvae_colsum_bf16(const void* x, int64_t rows, int32_t C, int32_t pitch, float* out, float* ws,
+                                    cudaStream_t stream) {
+  TVAE_CHECK(x && out && ws, "tvae_colsum_bf16: null pointer");
+  const int nb = colsum_blocks(rows);
+  const long long rpb = (rows + nb - 1) / nb;
+  const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x);
+  const int vec = (C % 8 == 0 && pitch % 8 == 0) ? 8 : ((C % 4 == 0 && pitch % 4 == 0) ? 4 : 1);
+  const int U = (C + vec - 1) / vec;
+  int UL = 1;
+  while (UL < U && UL < 256) UL <<= 1;  // power of two <= 256 so it divides the block
+  dim3 grid(nb, (U + UL - 1) / UL);
+  const size_t smem = 256 * vec * sizeof(float);
+  if (vec == 8) colsum_partial_kernel<8><<<grid, 256, smem, stream>>>(xp, rows, C, pitch, UL, rpb, ws);
+  else if (vec == 4) colsum_partial_kernel<4><<<grid, 256, smem, stream>>>(xp, rows, C, pitch, UL, rpb, ws);
+  else colsum_partial_kernel<1><<<grid, 256, smem, stream>>>(xp, rows, C, pitch, UL, rpb, ws);
+  TVAE_CUDA(cudaGetLastError());
+  colsum_final_kernel<<<(C + 127) / 128, 128, 0, stream>>>(ws, nb, C, out);
+  TVAE_CUDA(cudaGetLastError());
+  return 0;
+}

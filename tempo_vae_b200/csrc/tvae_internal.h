@@ -1,0 +1,22 @@
+// Host-side internals shared by the translation units of libtvae_b200.so (not part of the C ABI).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+#include "../../include/tvae.h"
+
+namespace tvae {
+
+void set_error(const char* fmt, ...);
+int num_sms();
+
+// Encode a bf16 tiled tensor map with 128-byte swizzle and zero out-of-bounds fill.
+// dims/box are innermost-first; strides (bytes) are for dims 1..rank-1. Returns 0 on success.
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box);
+
+// Pixel box {bw, bh, bn} that covers `rows` consecutive pixels (raster order) of an [N, H, W] grid.
+bool pixel_box(int H, int W, int rows, int* bw, int* bh, int* bn);
+
+}  // namespace tvae

@@ -1,0 +1,310 @@
+"""Tensor-level wrappers over the C ABI (include/tvae.h).
+
+PyTorch is used here for device memory and streams only; every arithmetic op below is a call into
+libtvae_b200.so on torch's current CUDA stream. Activations are NHWC tensors `[N, H, W, pitch]` (bf16 operands,
+fp32 residual stream); `C` (the number of valid channels, <= pitch) travels next to them.
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib
+from ._lib import ConvArgs, WgradArgs, check, lib
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def round_up(v, m):
+    return (v + m - 1) // m * m
+
+
+def require_cuda(t, name="tensor"):
+    if not t.is_cuda:
+        raise _lib.TvaeError(
+            f"{name} is on {t.device}: the TEMPO-VAE B200 path runs on CUDA only (there is no CPU fallback)")
+
+
+# ----------------------------------------------------------------------------------------------- weight packing
+class PackedWeight:
+    """bf16 K-major GEMM operand [rows][k_pitch] built from a parameter in the reference's layout."""
+
+    __slots__ = ("data", "rows", "k_pitch", "c_pad", "version")
+
+    def __init__(self, data, rows, k_pitch, c_pad):
+        self.data, self.rows, self.k_pitch, self.c_pad = data, rows, k_pitch, c_pad
+        self.version = -1
+
+
+# mode -> how the GEMM operand is cut out of the parameter
+#  "fwd"        Conv2d [Co][Ci][R][S]     -> [Co][tap][Ci_pad]            (forward)
+#  "dgrad"      Conv2d                    -> [Ci][tap][Co_pad]            (stride-1 dgrad, taps flipped by the kernel)
+#  "down_dgrad" Conv2d 2x2 s2             -> [(tap, Ci)][Co_pad]          (dgrad as transposed-conv GEMM)
+#  "up_fwd"     ConvT  [Ci][Co][2][2]     -> [(tap, Co)][Ci_pad]          (forward)
+#  "up_dgrad"   ConvT                     -> [Ci][tap][Co_pad]            (dgrad as 2x2 s2 conv)
+def pack_geometry(shape, mode):
+    a, b, r, s = shape
+    taps = r * s
+    if mode == "fwd":
+        return dict(Crow=a, TR=1, TK=taps, C=b, s_row=b * taps, s_col=taps, s_tap=1)
+    if mode == "dgrad":
+        return dict(Crow=b, TR=1, TK=taps, C=a, s_row=taps, s_col=b * taps, s_tap=1)
+    if mode == "down_dgrad":
+        return dict(Crow=b, TR=taps, TK=1, C=a, s_row=taps, s_col=b * taps, s_tap=1)
+    if mode == "up_fwd":
+        return dict(Crow=b, TR=taps, TK=1, C=a, s_row=taps, s_col=b * taps, s_tap=1)
+    if mode == "up_dgrad":
+        return dict(Crow=a, TR=1, TK=taps, C=b, s_row=b * taps, s_col=taps, s_tap=1)
+    raise ValueError(mode)
+
+
+def pack_weight(w, mode, out=None):
+    require_cuda(w, "weight")
+    g = pack_geometry(tuple(w.shape), mode)
+    c_pad = round_up(g["C"], 64)
+    rows = g["TR"] * g["Crow"]
+    k_pitch = g["TK"] * c_pad
+    if out is None:
+        out = PackedWeight(torch.empty((rows, k_pitch), dtype=torch.bfloat16, device=w.device), rows, k_pitch, c_pad)
+    wc = w.detach()
+    assert wc.is_contiguous() and wc.dtype == torch.float32
+    check(lib.tvae_pack_weight(wc.data_ptr(), out.data.data_ptr(), g["Crow"], g["TR"], g["TK"], g["C"], c_pad,
+                               g["s_row"], g["s_col"], g["s_tap"], _stream()), "tvae_pack_weight")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- conv GEMM
+def conv_gemm(x, C_in, wp, *, kind, R, Cout, flip=False, bias=None, residual=None, want_f32=True, want_bf16=False,
+              bf16_pitch=None, bn=0, out_f32=None, out_bf16=None):
+    """x: bf16 [N,H,W,pitch]. Returns (out_f32 or None, out_bf16 or None) as NHWC tensors."""
+    N, H, W, pitch = x.shape
+    if kind == 1:
+        oH, oW = H // 2, W // 2
+    elif kind == 2:
+        oH, oW = 2 * H, 2 * W
+    else:
+        oH, oW = H, W
+    dev = x.device
+    if want_f32 and out_f32 is None:
+        out_f32 = torch.empty((N, oH, oW, round_up(Cout, 4)), dtype=torch.float32, device=dev)
+    if want_bf16 and out_bf16 is None:
+        bp = bf16_pitch or round_up(Cout, 8)
+        out_bf16 = torch.empty((N, oH, oW, bp), dtype=torch.bfloat16, device=dev)
+    a = ConvArgs()
+    a.x = x.data_ptr(); a.N, a.H, a.W, a.C, a.x_pitch = N, H, W, C_in, pitch
+    a.kind, a.R, a.flip = kind, R, int(flip)
+    a.w = wp.data.data_ptr(); a.w_rows, a.k_pitch, a.c_pad = wp.rows, wp.k_pitch, wp.c_pad
+    a.Cout = Cout
+    a.bias = _ptr(bias)
+    a.residual = _ptr(residual); a.res_pitch = residual.shape[-1] if residual is not None else 0
+    a.out_f32 = _ptr(out_f32); a.out_f32_pitch = out_f32.shape[-1] if out_f32 is not None else 0
+    a.out_bf16 = _ptr(out_bf16); a.out_bf16_pitch = out_bf16.shape[-1] if out_bf16 is not None else 0
+    a.bn = bn
+    check(lib.tvae_conv_gemm(C.byref(a), _stream()), "tvae_conv_gemm")
+    return out_f32, out_bf16
+
+
+_wgrad_ws = {}
+
+
+def _workspace(nbytes, device, key="ws"):
+    """Grow-only scratch buffer per (device, key); stream-ordered reuse on the current stream."""
+    k = (device, key)
+    buf = _wgrad_ws.get(k)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _wgrad_ws[k] = buf
+    return buf
+
+
+def wgrad_gemm(p, Cm, q, Cn, *, kind, R, grad, accumulate=False, splits=0):
+    """grad[m][n][tap] (+)= sum_pixels p[pixel][m] * q[pixel (+) tap][n]; p: bf16 [N,H,W,pitch] (the dense grid)."""
+    N, H, W, pp = p.shape
+    taps = R * R if kind == 0 else 4
+    if splits <= 0:
+        splits = lib.tvae_wgrad_splits(Cm, Cn, taps, N * H * W)
+    nbytes = lib.tvae_wgrad_workspace_bytes(Cm, Cn, taps, splits)
+    ws = _workspace(nbytes, p.device, "wgrad")
+    assert grad.is_contiguous() and grad.dtype == torch.float32 and grad.numel() == Cm * Cn * taps
+    a = WgradArgs()
+    a.p = p.data_ptr(); a.p_pitch = pp; a.Cm = Cm
+    a.q = q.data_ptr(); a.q_pitch = q.shape[-1]; a.Cn = Cn
+    a.N, a.H, a.W = N, H, W
+    a.kind, a.R, a.splits = kind, R, splits
+    a.workspace = ws.data_ptr(); a.grad = grad.data_ptr(); a.accumulate = int(accumulate)
+    check(lib.tvae_wgrad_gemm(C.byref(a), _stream()), "tvae_wgrad_gemm")
+
+
+# ----------------------------------------------------------------------------------------------- layout
+def nchw_to_nhwc_bf16(x, pitch=None):
+    require_cuda(x, "input")
+    N, Cc, H, W = x.shape
+    pitch = pitch or round_up(Cc, 8)
+    x = x.contiguous()
+    if x.dtype != torch.float32:
+        x = x.float()
+    out = torch.empty((N, H, W, pitch), dtype=torch.bfloat16, device=x.device)
+    check(lib.tvae_nchw_f32_to_nhwc_bf16(x.data_ptr(), out.data_ptr(), N, Cc, H * W, pitch, _stream()),
+          "tvae_nchw_f32_to_nhwc_bf16")
+    return out
+
+
+def nhwc_to_nchw_f32(x, Cc):
+    N, H, W, pitch = x.shape
+    out = torch.empty((N, Cc, H, W), dtype=torch.float32, device=x.device)
+    if x.dtype == torch.float32:
+        check(lib.tvae_nhwc_f32_to_nchw_f32(x.data_ptr(), out.data_ptr(), N, Cc, H * W, pitch, _stream()),
+              "tvae_nhwc_f32_to_nchw_f32")
+    else:
+        check(lib.tvae_nhwc_bf16_to_nchw_f32(x.data_ptr(), out.data_ptr(), N, Cc, H * W, pitch, _stream()),
+              "tvae_nhwc_bf16_to_nchw_f32")
+    return out
+
+
+def f32_to_bf16(x):
+    out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    check(lib.tvae_f32_to_bf16(x.data_ptr(), out.data_ptr(), x.numel(), _stream()), "tvae_f32_to_bf16")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- GroupNorm
+def gn_stats(x, Cc, G, eps):
+    N, H, W, pitch = x.shape
+    assert pitch == Cc and x.dtype == torch.float32
+    stats = torch.empty((N, G, 2), dtype=torch.float32, device=x.device)
+    check(lib.tvae_gn_stats(x.data_ptr(), N, H * W, Cc, G, float(eps), stats.data_ptr(), _stream()), "tvae_gn_stats")
+    return stats
+
+
+def gn_act_fwd(x, stats, gamma, beta, G, act):
+    N, H, W, Cc = x.shape
+    out = torch.empty((N, H, W, Cc), dtype=torch.bfloat16, device=x.device)
+    check(lib.tvae_gn_act_fwd(x.data_ptr(), stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), N, H * W, Cc, G,
+                              int(act), out.data_ptr(), _stream()), "tvae_gn_act_fwd")
+    return out
+
+
+def gn_act_bwd(x, stats, gamma, beta, da, gres, G, act, dgamma, dbeta):
+    N, H, W, Cc = x.shape
+    assert da.shape[-1] == Cc and da.dtype == torch.bfloat16
+    dx = torch.empty((N, H, W, Cc), dtype=torch.bfloat16, device=x.device)
+    ws = _workspace(lib.tvae_gn_bwd_workspace_bytes(N, Cc, G), x.device, "gn")
+    check(lib.tvae_gn_act_bwd(x.data_ptr(), stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), da.data_ptr(),
+                              _ptr(gres), N, H * W, Cc, G, int(act), dx.data_ptr(), dgamma.data_ptr(),
+                              dbeta.data_ptr(), ws.data_ptr(), _stream()), "tvae_gn_act_bwd")
+    return dx
+
+
+def colsum_bf16(x, Cc, out):
+    rows = x.numel() // x.shape[-1]
+    ws = _workspace(lib.tvae_colsum_workspace_bytes(rows, Cc), x.device, "colsum")
+    check(lib.tvae_colsum_bf16(x.data_ptr(), rows, Cc, x.shape[-1], out.data_ptr(), ws.data_ptr(), _stream()),
+          "tvae_colsum_bf16")
+
+
+# ----------------------------------------------------------------------------------------------- attention
+def attn_fwd(qkv, Cc, heads, B, T):
+    """qkv: fp32 [B*T (any leading shape), 3C]. Returns (o_bf16, o_f32, lse)."""
+    pitch = qkv.shape[-1]
+    dev = qkv.device
+    o_bf16 = torch.empty((B * T, Cc), dtype=torch.bfloat16, device=dev)
+    o_f32 = torch.empty((B * T, Cc), dtype=torch.float32, device=dev)
+    lse = torch.empty((B, heads, T), dtype=torch.float32, device=dev)
+    base = qkv.data_ptr()
+    check(lib.tvae_attn_fwd(base, base + 4 * Cc, base + 8 * Cc, pitch, B, T, Cc, heads, o_bf16.data_ptr(),
+                            o_f32.data_ptr(), lse.data_ptr(), _stream()), "tvae_attn_fwd")
+    return o_bf16, o_f32, lse
+
+
+def attn_bwd(qkv, o_f32, d_out, lse, Cc, heads, B, T):
+    pitch = qkv.shape[-1]
+    dev = qkv.device
+    dqkv = torch.empty((B * T, 3 * Cc), dtype=torch.bfloat16, device=dev)
+    ws = torch.empty((B * heads * T,), dtype=torch.float32, device=dev)
+    base = qkv.data_ptr()
+    check(lib.tvae_attn_bwd(base, base + 4 * Cc, base + 8 * Cc, pitch, o_f32.data_ptr(), d_out.data_ptr(),
+                            lse.data_ptr(), B, T, Cc, heads, dqkv.data_ptr(), ws.data_ptr(), _stream()),
+          "tvae_attn_bwd")
+    return dqkv
+
+
+# ----------------------------------------------------------------------------------------------- latent / losses
+def reparam_fwd(moments, Z, *, eps=None, seed=0, sample_offset=0, want_z_nchw=False, z_pitch=None):
+    """moments: fp32 [B,h,w,2Z]. Returns (z_bf16 [B,h,w,z_pitch], z_nchw or None, eps_nchw, kl[B])."""
+    B, h, w, _ = moments.shape
+    dev = moments.device
+    z_pitch = z_pitch or round_up(Z, 8)
+    z_bf16 = torch.zeros((B, h, w, z_pitch), dtype=torch.bfloat16, device=dev) if z_pitch != Z else \
+        torch.empty((B, h, w, Z), dtype=torch.bfloat16, device=dev)
+    z_nchw = torch.empty((B, Z, h, w), dtype=torch.float32, device=dev) if want_z_nchw else None
+    kl = torch.empty((B,), dtype=torch.float32, device=dev)
+    if eps is not None:
+        eps = eps.contiguous().float()
+        eps_out = None
+    else:
+        eps_out = torch.empty((B, Z, h, w), dtype=torch.float32, device=dev)
+    check(lib.tvae_reparam_fwd(moments.data_ptr(), _ptr(eps), seed, sample_offset, B, h * w, Z, z_bf16.data_ptr(),
+                               z_pitch, _ptr(z_nchw), _ptr(eps_out), kl.data_ptr(), _stream()), "tvae_reparam_fwd")
+    return z_bf16, z_nchw, (eps if eps is not None else eps_out), kl
+
+
+def reparam_bwd(moments, Z, dz1, eps1, dz2, eps2, kl_scale):
+    B, h, w, _ = moments.shape
+    dm = torch.empty((B, h, w, 2 * Z), dtype=torch.bfloat16, device=moments.device)
+    check(lib.tvae_reparam_bwd(moments.data_ptr(), _ptr(dz1), _ptr(eps1), _ptr(dz2), _ptr(eps2), float(kl_scale), B,
+                               h * w, Z, dm.data_ptr(), _stream()), "tvae_reparam_bwd")
+    return dm
+
+
+def nll_fwd(x_bf16, xhat, Cc, loss_type, logvar, batch, want_grad):
+    """x_bf16 [N,H,W,xp] bf16; xhat [N,H,W,hp] fp32. Returns (sums fp64[3], dxhat bf16 or None)."""
+    P = x_bf16.numel() // x_bf16.shape[-1]
+    dev = xhat.device
+    sums = torch.empty((3,), dtype=torch.float64, device=dev)
+    ws = _workspace(lib.tvae_nll_workspace_bytes(), dev, "nll")
+    dx = None
+    if want_grad:
+        dx = torch.empty(x_bf16.shape[:-1] + (round_up(Cc, 8),), dtype=torch.bfloat16, device=dev)
+    check(lib.tvae_nll_fwd(x_bf16.data_ptr(), x_bf16.shape[-1], xhat.data_ptr(), xhat.shape[-1], P, Cc, loss_type,
+                           _ptr(logvar), batch, _ptr(dx), dx.shape[-1] if dx is not None else 0, sums.data_ptr(),
+                           ws.data_ptr(), _stream()), "tvae_nll_fwd")
+    return sums, dx
+
+
+def _target_array(targets):
+    arr = (C.c_void_p * len(targets))()
+    for i, t in enumerate(targets):
+        arr[i] = _ptr(t)
+    return arr
+
+
+def l2head_loss_fwd(pred, targets, B, h, w):
+    sums = torch.empty((len(targets), 2), dtype=torch.float64, device=pred.device)
+    check(lib.tvae_l2head_loss_fwd(pred.data_ptr(), pred.shape[-1], _target_array(targets), len(targets), B, h, w,
+                                   sums.data_ptr(), _stream()), "tvae_l2head_loss_fwd")
+    return sums
+
+
+def l2head_loss_bwd(pred, targets, B, h, w, sums, weights, grad_scale, dp_pitch=8):
+    dpred = torch.empty((B, h, w, dp_pitch), dtype=torch.bfloat16, device=pred.device)
+    check(lib.tvae_l2head_loss_bwd(pred.data_ptr(), pred.shape[-1], _target_array(targets), len(targets), B, h, w,
+                                   sums.data_ptr(), weights.data_ptr(), float(grad_scale), dpred.data_ptr(), dp_pitch,
+                                   _stream()), "tvae_l2head_loss_bwd")
+    return dpred
+
+
+# ----------------------------------------------------------------------------------------------- optimiser
+def sumsq(g, out):
+    ws = _workspace(lib.tvae_sumsq_workspace_bytes(g.numel()), g.device, "sumsq")
+    check(lib.tvae_sumsq(g.data_ptr(), g.numel(), out.data_ptr(), ws.data_ptr(), _stream()), "tvae_sumsq")
+
+
+def adamw(p, g, m, v, *, lr, beta1, beta2, eps, weight_decay, step, sumsq_buf=None, max_norm=0.0, grad_scale=1.0):
+    check(lib.tvae_adamw(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, beta1, beta2, eps,
+                         weight_decay, step, _ptr(sumsq_buf), max_norm, grad_scale, _stream()), "tvae_adamw")

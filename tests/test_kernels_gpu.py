@@ -1,0 +1,370 @@
+"""Kernel-level parity: every C-ABI entry point against plain PyTorch fp32 ops on the same (bf16-rounded) inputs.
+
+Tolerances are stated per test. GEMM operands are bf16 (exactly representable inputs are fed to both sides), the
+accumulation is fp32 on both sides, so the only difference is summation order: |err| <= 2e-3 * max|ref|.
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _no_tf32():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+
+
+def ops():
+    from tempo_vae_b200 import ops as o
+    return o
+
+
+def bf16_round(t):
+    return t.to(torch.bfloat16).float()
+
+
+def nhwc_bf16(x_nchw, pitch):
+    N, C, H, W = x_nchw.shape
+    out = torch.zeros((N, H, W, pitch), dtype=torch.bfloat16, device=x_nchw.device)
+    out[..., :C] = x_nchw.permute(0, 2, 3, 1).to(torch.bfloat16)
+    return out
+
+
+def rel_err(a, b):
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+CONV_CASES = [
+    # N, H, W, Cin, Cout, R
+    (2, 16, 16, 64, 64, 3),
+    (2, 16, 16, 128, 128, 1),
+    (3, 32, 32, 256, 256, 3),
+    (2, 64, 64, 128, 512, 3),
+    (1, 64, 64, 1028, 512, 3),
+    (1, 64, 64, 512, 1028, 3),
+    (2, 16, 16, 32, 128, 3),
+    (2, 16, 16, 128, 64, 3),
+    (2, 16, 16, 512, 4, 1),
+    (5, 8, 8, 64, 48, 3),
+    (3, 4, 4, 32, 32, 3),
+    (1, 8, 256, 64, 64, 3),
+]
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout,R", CONV_CASES)
+def test_conv_fwd(N, H, W, Cin, Cout, R):
+    o = ops()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = bf16_round(torch.randn((N, Cin, H, W), device="cuda", generator=g))
+    w = bf16_round(torch.randn((Cout, Cin, R, R), device="cuda", generator=g) / math.sqrt(Cin * R * R))
+    b = torch.randn((Cout,), device="cuda", generator=g)
+    res = torch.randn((N, Cout, H, W), device="cuda", generator=g)
+    ref = F.conv2d(x, w, b, padding=R // 2) + res
+    xp = nhwc_bf16(x, o.round_up(Cin, 8))
+    wp = o.pack_weight(w, "fwd")
+    res_nhwc = torch.zeros((N, H, W, o.round_up(Cout, 4)), device="cuda")
+    res_nhwc[..., :Cout] = res.permute(0, 2, 3, 1)
+    of, ob = o.conv_gemm(xp, Cin, wp, kind=0, R=R, Cout=Cout, bias=b, residual=res_nhwc, want_f32=True, want_bf16=True)
+    torch.cuda.synchronize()
+    got = of[..., :Cout].permute(0, 3, 1, 2)
+    assert rel_err(got, ref) < 2e-3
+    gotb = ob[..., :Cout].float().permute(0, 3, 1, 2)
+    assert rel_err(gotb, ref) < 1e-2
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout,R", [(2, 16, 16, 64, 128, 3), (2, 32, 32, 256, 512, 3), (1, 64, 64, 1028, 512, 3),
+                                               (2, 16, 16, 128, 128, 1)])
+def test_conv_dgrad(N, H, W, Cin, Cout, R):
+    o = ops()
+    g = torch.Generator(device="cuda").manual_seed(2)
+    w = bf16_round(torch.randn((Cout, Cin, R, R), device="cuda", generator=g) / math.sqrt(Cout * R * R))
+    dy = bf16_round(torch.randn((N, Cout, H, W), device="cuda", generator=g))
+    ref = torch.nn.grad.conv2d_input((N, Cin, H, W), w, dy, padding=R // 2)
+    dyp = nhwc_bf16(dy, o.round_up(Cout, 8))
+    wp = o.pack_weight(w, "dgrad")
+    of, _ = o.conv_gemm(dyp, Cout, wp, kind=0, R=R, Cout=Cin, flip=True)
+    torch.cuda.synchronize()
+    assert rel_err(of[..., :Cin].permute(0, 3, 1, 2), ref) < 2e-3
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout", [(2, 16, 16, 64, 64), (2, 64, 64, 512, 512), (3, 32, 32, 256, 256), (2, 8, 8, 32, 16)])
+def test_conv_down_and_dgrad(N, H, W, Cin, Cout):
+    o = ops()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = bf16_round(torch.randn((N, Cin, H, W), device="cuda", generator=g))
+    w = bf16_round(torch.randn((Cout, Cin, 2, 2), device="cuda", generator=g) / math.sqrt(Cin * 4))
+    b = torch.randn((Cout,), device="cuda", generator=g)
+    ref = F.conv2d(x, w, b, stride=2)
+    xp = nhwc_bf16(x, o.round_up(Cin, 8))
+    of, _ = o.conv_gemm(xp, Cin, o.pack_weight(w, "fwd"), kind=1, R=2, Cout=Cout, bias=b)
+    torch.cuda.synchronize()
+    assert rel_err(of[..., :Cout].permute(0, 3, 1, 2), ref) < 2e-3
+    # dgrad of the down conv == transposed-conv GEMM with scatter
+    dy = bf16_round(torch.randn((N, Cout, H // 2, W // 2), device="cuda", generator=g))
+    refd = torch.nn.grad.conv2d_input((N, Cin, H, W), w, dy, stride=2)
+    dyp = nhwc_bf16(dy, o.round_up(Cout, 8))
+    od, _ = o.conv_gemm(dyp, Cout, o.pack_weight(w, "down_dgrad"), kind=2, R=2, Cout=Cin)
+    torch.cuda.synchronize()
+    assert rel_err(od[..., :Cin].permute(0, 3, 1, 2), refd) < 2e-3
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout", [(2, 16, 16, 128, 256), (2, 32, 32, 256, 512), (2, 8, 8, 32, 16)])
+def test_convT_up_and_dgrad(N, H, W, Cin, Cout):
+    o = ops()
+    g = torch.Generator(device="cuda").manual_seed(4)
+    x = bf16_round(torch.randn((N, Cin, H, W), device="cuda", generator=g))
+    w = bf16_round(torch.randn((Cin, Cout, 2, 2), device="cuda", generator=g) / math.sqrt(Cin))
+    b = torch.randn((Cout,), device="cuda", generator=g)
+    ref = F.conv_transpose2d(x, w, b, stride=2)
+    xp = nhwc_bf16(x, o.round_up(Cin, 8))
+    of, _ = o.conv_gemm(xp, Cin, o.pack_weight(w, "up_fwd"), kind=2, R=2, Cout=Cout, bias=b)
+    torch.cuda.synchronize()
+    assert rel_err(of[..., :Cout].permute(0, 3, 1, 2), ref) < 2e-3
+    dy = bf16_round(torch.randn((N, Cout, 2 * H, 2 * W), device="cuda", generator=g))
+    refd = F.conv2d(dy, w, stride=2)  # d/dx of conv_transpose2d
+    dyp = nhwc_bf16(dy, o.round_up(Cout, 8))
+    od, _ = o.conv_gemm(dyp, Cout, o.pack_weight(w, "up_dgrad"), kind=1, R=2, Cout=Cin)
+    torch.cuda.synchronize()
+    assert rel_err(od[..., :Cin].permute(0, 3, 1, 2), refd) < 2e-3
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout,R,splits", [
+    (2, 16, 16, 64, 64, 3, 1), (2, 16, 16, 128, 128, 1, 0), (4, 32, 32, 256, 256, 3, 0), (2, 64, 64, 512, 512, 3, 0),
+    (1, 64, 64, 1028, 512, 3, 0), (1, 64, 64, 512, 1028, 3, 3), (2, 16, 16, 128, 64, 3, 2), (2, 16, 16, 512, 4, 1, 0),
+    (6, 4, 4, 32, 32, 3, 0), (2, 16, 16, 32, 128, 3, 40)])
+def test_wgrad(N, H, W, Cin, Cout, R, splits):
+    o = ops()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = bf16_round(torch.randn((N, Cin, H, W), device="cuda", generator=g))
+    dy = bf16_round(torch.randn((N, Cout, H, W), device="cuda", generator=g))
+    ref = torch.nn.grad.conv2d_weight(x, (Cout, Cin, R, R), dy, padding=R // 2)
+    grad = torch.full((Cout, Cin, R, R), float("nan"), device="cuda")
+    o.wgrad_gemm(nhwc_bf16(dy, o.round_up(Cout, 8)), Cout, nhwc_bf16(x, o.round_up(Cin, 8)), Cin, kind=0, R=R,
+                 grad=grad, splits=splits)
+    torch.cuda.synchronize()
+    assert rel_err(grad, ref) < 2e-3
+    o.wgrad_gemm(nhwc_bf16(dy, o.round_up(Cout, 8)), Cout, nhwc_bf16(x, o.round_up(Cin, 8)), Cin, kind=0, R=R,
+                 grad=grad, splits=splits, accumulate=True)
+    torch.cuda.synchronize()
+    assert rel_err(grad, 2 * ref) < 2e-3
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout", [(2, 16, 16, 64, 64), (2, 64, 64, 512, 512), (2, 8, 8, 32, 16)])
+def test_wgrad_strided(N, H, W, Cin, Cout):
+    o = ops()
+    g = torch.Generator(device="cuda").manual_seed(6)
+    # 2x2 s2 Conv2d: P = dY (coarse), Q = x (fine)
+    x = bf16_round(torch.randn((N, Cin, H, W), device="cuda", generator=g))
+    dy = bf16_round(torch.randn((N, Cout, H // 2, W // 2), device="cuda", generator=g))
+    ref = torch.nn.grad.conv2d_weight(x, (Cout, Cin, 2, 2), dy, stride=2)
+    grad = torch.empty((Cout, Cin, 2, 2), device="cuda")
+    o.wgrad_gemm(nhwc_bf16(dy, o.round_up(Cout, 8)), Cout, nhwc_bf16(x, o.round_up(Cin, 8)), Cin, kind=1, R=2, grad=grad)
+    torch.cuda.synchronize()
+    assert rel_err(grad, ref) < 2e-3
+    # ConvTranspose2d [Cin][Cout][2][2]: P = x (coarse), Q = dY (fine)
+    xc = bf16_round(torch.randn((N, Cin, H // 2, W // 2), device="cuda", generator=g))
+    dyf = bf16_round(torch.randn((N, Cout, H, W), device="cuda", generator=g))
+    wt = torch.zeros((Cin, Cout, 2, 2), device="cuda", requires_grad=True)
+    F.conv_transpose2d(xc, wt, stride=2).backward(dyf)
+    gradt = torch.empty((Cin, Cout, 2, 2), device="cuda")
+    o.wgrad_gemm(nhwc_bf16(xc, o.round_up(Cin, 8)), Cin, nhwc_bf16(dyf, o.round_up(Cout, 8)), Cout, kind=1, R=2, grad=gradt)
+    torch.cuda.synchronize()
+    assert rel_err(gradt, wt.grad) < 2e-3
+
+
+def test_layout_roundtrip():
+    o = ops()
+    x = torch.randn((3, 1028, 16, 16), device="cuda")
+    y = o.nchw_to_nhwc_bf16(x, 1032)
+    assert torch.equal(y[..., :1028], x.permute(0, 2, 3, 1).to(torch.bfloat16))
+    assert (y[..., 1028:] == 0).all()
+    z = o.nhwc_to_nchw_f32(y, 1028)
+    assert torch.equal(z, x.to(torch.bfloat16).float())
+    f = torch.randn((3, 16, 16, 1028), device="cuda")
+    assert torch.equal(o.nhwc_to_nchw_f32(f, 1028), f.permute(0, 3, 1, 2))
+    assert torch.equal(o.f32_to_bf16(f), f.to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("N,H,W,C,G,act,eps", [(3, 16, 16, 128, 8, 1, 1e-6), (2, 64, 64, 512, 8, 1, 1e-6), (2, 16, 16, 128, 8, 0, 1e-6),
+                                                (2, 8, 8, 32, 8, 1, 1e-5), (2, 4, 4, 16, 8, 1, 1e-6)])
+def test_groupnorm_gelu_fwd_bwd(N, H, W, C, G, act, eps):
+    o = ops()
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = (torch.randn((N, C, H, W), device="cuda", generator=g) * 1.7 + 0.3).requires_grad_(True)
+    gamma = (torch.randn((C,), device="cuda", generator=g) * 0.5 + 1.0).requires_grad_(True)
+    beta = (torch.randn((C,), device="cuda", generator=g) * 0.2).requires_grad_(True)
+    y = F.group_norm(x, G, gamma, beta, eps)
+    if act:
+        y = F.gelu(y)
+    da = bf16_round(torch.randn((N, C, H, W), device="cuda", generator=g))
+    gres = bf16_round(torch.randn((N, C, H, W), device="cuda", generator=g))
+    y.backward(da)
+    xn = x.detach().permute(0, 2, 3, 1).contiguous()
+    stats = o.gn_stats(xn, C, G, eps)
+    a = o.gn_act_fwd(xn, stats, gamma.detach(), beta.detach(), G, act)
+    torch.cuda.synchronize()
+    ref_stats_mean = x.detach().reshape(N, G, -1).mean(-1)
+    assert torch.allclose(stats[..., 0], ref_stats_mean, atol=1e-5)
+    assert rel_err(a.float().permute(0, 3, 1, 2), y.detach()) < 1e-2  # bf16 output rounding
+    dgamma = torch.empty((C,), device="cuda"); dbeta = torch.empty((C,), device="cuda")
+    dx = o.gn_act_bwd(xn, stats, gamma.detach(), beta.detach(), da.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16),
+                      gres.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16), G, act, dgamma, dbeta)
+    torch.cuda.synchronize()
+    assert rel_err(dx.float().permute(0, 3, 1, 2), x.grad + gres) < 1e-2
+    assert rel_err(dgamma, gamma.grad) < 1e-3
+    assert rel_err(dbeta, beta.grad) < 1e-3
+
+
+@pytest.mark.parametrize("rows,C,pitch", [(4096, 512, 512), (8192, 1028, 1032), (512, 4, 8), (1000, 64, 64)])
+def test_colsum(rows, C, pitch):
+    o = ops()
+    x = torch.randn((rows, pitch), device="cuda").to(torch.bfloat16)
+    out = torch.empty((C,), device="cuda")
+    o.colsum_bf16(x, C, out)
+    torch.cuda.synchronize()
+    assert rel_err(out, x[:, :C].float().sum(0)) < 1e-4
+
+
+@pytest.mark.parametrize("B,T,C,heads", [(3, 256, 128, 4), (2, 64, 16, 4), (1, 1024, 128, 4), (2, 100, 32, 4)])
+def test_attention_fwd_bwd(B, T, C, heads):
+    o = ops()
+    g = torch.Generator(device="cuda").manual_seed(8)
+    qkv = torch.randn((B * T, 3 * C), device="cuda", generator=g).requires_grad_(True)
+    hd = C // heads
+
+    def ref_attn(qkv):
+        q, k, v = qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:]
+        # channel c = d*heads + h  (reference: reshape(b, c_, n_heads, hw))
+        def split(t):
+            return t.reshape(B, T, hd, heads).permute(0, 3, 1, 2)  # [B, heads, T, hd]
+        q, k, v = split(q), split(k), split(v)
+        w = torch.softmax(q @ k.transpose(-1, -2) * hd ** -0.5, dim=-1)
+        out = w @ v  # [B, heads, T, hd]
+        return out.permute(0, 2, 3, 1).reshape(B * T, C)
+
+    ref = ref_attn(qkv)
+    d_out = torch.randn((B * T, C), device="cuda", generator=g)
+    ref.backward(d_out)
+    ob, of, lse = o.attn_fwd(qkv.detach(), C, heads, B, T)
+    torch.cuda.synchronize()
+    assert rel_err(of, ref.detach()) < 1e-4
+    dqkv = o.attn_bwd(qkv.detach(), of, d_out, lse, C, heads, B, T)
+    torch.cuda.synchronize()
+    assert rel_err(dqkv.float(), qkv.grad) < 1e-2  # bf16 output
+
+
+def test_reparam_kl_fwd_bwd():
+    o = ops()
+    B, h, w, Z = 3, 16, 16, 32
+    g = torch.Generator(device="cuda").manual_seed(9)
+    mom = (torch.randn((B, 2 * Z, h, w), device="cuda", generator=g) * 3).requires_grad_(True)
+    with torch.no_grad():
+        mom[0, Z, 0, 0] = 25.0  # exercises the clamp
+        mom[0, Z + 1, 0, 0] = -40.0
+    eps = torch.randn((B, Z, h, w), device="cuda", generator=g)
+    mean, logvar = torch.chunk(mom, 2, dim=1)
+    logvar = torch.clamp(logvar, -30.0, 20.0)
+    z = mean + torch.exp(0.5 * logvar) * eps
+    kl = 0.5 * torch.sum(mean ** 2 + torch.exp(logvar) - 1.0 - logvar, dim=[1, 2, 3])
+    dz = torch.randn((B, Z, h, w), device="cuda", generator=g)
+    kl_scale = 0.37
+    (torch.sum(z * dz) + kl_scale * kl.sum()).backward()
+    mn = mom.detach().permute(0, 2, 3, 1).contiguous()
+    zb, zn, eps_used, klo = o.reparam_fwd(mn, Z, eps=eps, want_z_nchw=True)
+    torch.cuda.synchronize()
+    assert rel_err(zn, z.detach()) < 1e-5
+    assert rel_err(klo, kl.detach()) < 1e-5
+    dm = o.reparam_bwd(mn, Z, dz.permute(0, 2, 3, 1).contiguous(), eps, None, None, kl_scale)
+    torch.cuda.synchronize()
+    assert rel_err(dm.float().permute(0, 3, 1, 2), mom.grad) < 1e-2
+    # Philox mode: N(0,1) moments, reproducible, offset-keyed
+    _, _, e1, _ = o.reparam_fwd(mn, Z, seed=123, sample_offset=0)
+    _, _, e2, _ = o.reparam_fwd(mn, Z, seed=123, sample_offset=0)
+    _, _, e3, _ = o.reparam_fwd(mn[1:], Z, seed=123, sample_offset=1)
+    torch.cuda.synchronize()
+    assert torch.equal(e1, e2) and torch.equal(e1[1:], e3)
+    assert abs(e1.mean().item()) < 0.02 and abs(e1.std().item() - 1.0) < 0.02
+
+
+@pytest.mark.parametrize("loss_type", [0, 1])
+def test_nll(loss_type):
+    o = ops()
+    N, H, W, C = 2, 16, 16, 1028
+    g = torch.Generator(device="cuda").manual_seed(10)
+    x = bf16_round(torch.randn((N, C, H, W), device="cuda", generator=g))
+    xh = torch.randn((N, C, H, W), device="cuda", generator=g).requires_grad_(True)
+    logvar = torch.tensor(0.7, device="cuda", requires_grad=True)
+    rec = (x - xh).abs() if loss_type == 0 else (x - xh) ** 2
+    nll = torch.sum(rec / torch.exp(logvar) + logvar) / N
+    nll.backward()
+    xb = nhwc_bf16(x, 1032)
+    xhn = xh.detach().permute(0, 2, 3, 1).contiguous()
+    sums, dx = o.nll_fwd(xb, xhn, C, loss_type, logvar.detach(), N, True)
+    torch.cuda.synchronize()
+    assert abs(sums[0].item() - rec.sum().item()) / rec.sum().item() < 1e-6
+    assert abs(sums[1].item() - ((x - xh) ** 2).sum().item()) / ((x - xh) ** 2).sum().item() < 1e-6
+    assert rel_err(dx[..., :C].float().permute(0, 3, 1, 2), xh.grad) < 1e-2
+
+
+def test_l2head_loss():
+    o = ops()
+    B, h, w = 3, 16, 16
+    g = torch.Generator(device="cuda").manual_seed(11)
+    pred = torch.randn((B, h, w, 4), device="cuda", generator=g).requires_grad_(True)
+    targets = []
+    for p in range(4):
+        t = torch.randn((B, 4 * h, 4 * w), device="cuda", generator=g)
+        t[torch.rand((B, 4 * h, 4 * w), device="cuda", generator=g) < 0.02] = float("nan")
+        targets.append(t)
+    targets[3][:] = float("nan")  # a product with no valid pixel is skipped
+    weights = torch.tensor([0.1, 0.2, 0.3, 0.4], device="cuda")
+    total = 0.0
+    ref_losses = []
+    for p in range(4):
+        td = F.avg_pool2d(targets[p].unsqueeze(1), 4)
+        pr = pred[..., p].unsqueeze(1)
+        m = ~torch.isnan(td)
+        if m.sum() > 0:
+            l = F.mse_loss(pr[m], td[m])
+            total = total + weights[p] * l
+            ref_losses.append(l.item())
+        else:
+            ref_losses.append(None)
+    total.backward()
+    sums = o.l2head_loss_fwd(pred.detach(), targets, B, h, w)
+    dp = o.l2head_loss_bwd(pred.detach(), targets, B, h, w, sums, weights, 1.0)
+    torch.cuda.synchronize()
+    for p in range(4):
+        if ref_losses[p] is None:
+            assert sums[p, 1].item() == 0
+        else:
+            assert abs(sums[p, 0].item() / sums[p, 1].item() - ref_losses[p]) < 1e-5 * max(1.0, ref_losses[p])
+    assert rel_err(dp[..., :4].float(), pred.grad) < 1e-2
+    assert (dp[..., 4:] == 0).all()
+
+
+def test_adamw_and_clip():
+    o = ops()
+    n = 100003
+    g = torch.Generator(device="cuda").manual_seed(12)
+    p0 = torch.randn((n,), device="cuda", generator=g)
+    p_ref = p0.clone().requires_grad_(True)
+    opt = torch.optim.AdamW([p_ref], lr=1e-3, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.05)
+    p = p0.clone(); m = torch.zeros_like(p); v = torch.zeros_like(p)
+    ss = torch.empty((1,), dtype=torch.float64, device="cuda")
+    for step in range(1, 4):
+        grad = torch.randn((n,), device="cuda", generator=g) * (10.0 if step == 1 else 1e-3)
+        p_ref.grad = grad.clone()
+        torch.nn.utils.clip_grad_norm_([p_ref], 1.0)
+        opt.step()
+        o.sumsq(grad, ss)
+        o.adamw(p, grad, m, v, lr=1e-3, beta1=0.9, beta2=0.95, eps=1e-8, weight_decay=0.05, step=step, sumsq_buf=ss,
+                max_norm=1.0)
+        torch.cuda.synchronize()
+        assert abs(ss.item() - grad.double().pow(2).sum().item()) / ss.item() < 1e-10
+        assert torch.allclose(p, p_ref.detach(), rtol=1e-5, atol=1e-7)
