@@ -99,7 +99,7 @@ int32_t tvae_f32_to_bf16(const float* x, void* out_bf16, int64_t n, tvae_stream_
 /* ------------------------------------------------------------------------------------------------------------
  * GroupNorm (+ exact-erf GELU). Replaces nn.GroupNorm + nn.GELU (src/model.py:105,179,202,333-339,400,542;
  * src/model_with_l2.py:24-25) and their backward.
- *  x fp32 NHWC [N,HW,C] (pitch C); stats[N][G][2] = (mean, rstd); act: 0 = identity, 1 = GELU.
+ *  x fp32 NHWC [N,HW,C] (pitch C); stats[N][G][2] = (mean, rstd); act: 0 = identity, 1 = GELU (exact erf), 2 = ReLU, 3 = SiLU.
  */
 int32_t tvae_gn_stats(const float* x, int32_t N, int32_t HW, int32_t C, int32_t G, float eps, float* stats,
                       tvae_stream_t stream);
@@ -162,6 +162,12 @@ int32_t tvae_nll_fwd(const void* x_bf16, int32_t x_pitch, const float* xhat, int
                      int32_t loss_type, const float* logvar, int32_t batch, void* dxhat_bf16, int32_t dx_pitch,
                      double* sums, double* workspace, tvae_stream_t stream);
 
+/* Scalars of AutoencoderKL.get_loss (src/model.py:660-668) from the reductions above, on the device:
+ *  out[0] = loss = nll + kl, out[1] = nll = (sums[0]*exp(-logvar) + logvar*n_elem)/B,
+ *  out[2] = kl_weight * sum(kl)/B, out[3] = pixel_mse = sums[1]/n_elem, out[4] = d loss / d logvar. */
+int32_t tvae_vae_loss_finalize(const double* sums, const float* kl, int32_t B, const float* logvar, double n_elem,
+                               float kl_weight, float* out, tvae_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * L2-product head loss. Replaces AvgPool2d(4) + isnan mask + masked-mean MSE (src/model_with_l2.py:151-168).
  *  pred: fp32 NHWC [B*hw][pred_pitch] (channel p = product p); target: fp32 [B][H][W] per product (NaN = invalid),
@@ -174,6 +180,11 @@ int32_t tvae_l2head_loss_fwd(const float* pred, int32_t pred_pitch, const float*
 int32_t tvae_l2head_loss_bwd(const float* pred, int32_t pred_pitch, const float* const* targets, int32_t nprod,
                              int32_t B, int32_t h, int32_t w, const double* sums, const float* weights,
                              float grad_scale, void* dpred_bf16, int32_t dp_pitch, tvae_stream_t stream);
+
+/* out[0] = vae_scal[0] + sum_p weights[p] * sums[p][0]/sums[p][1] over products with a valid pixel;
+ * out[1+p] = that product's masked MSE (NaN when it has no valid pixel, i.e. skipped like the reference). */
+int32_t tvae_l2head_finalize(const double* sums, const float* weights, int32_t nprod, const float* vae_scal,
+                             float* out, tvae_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Optimiser. Replaces clip_grad_norm_(max_norm) + torch.optim.AdamW.step (src/train_utils.py:175-177;

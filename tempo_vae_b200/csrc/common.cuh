@@ -224,6 +224,27 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
   return cdf + x * pdf;
 }
 
+// activation codes of the C ABI: 0 identity, 1 GELU (exact erf), 2 ReLU, 3 SiLU  (src/model.py:333-339)
+__device__ __forceinline__ float act_f(float y, int act) {
+  switch (act) {
+    case 1: return gelu_f(y);
+    case 2: return fmaxf(y, 0.f);
+    case 3: return y / (1.0f + __expf(-y));
+    default: return y;
+  }
+}
+__device__ __forceinline__ float act_grad_f(float y, int act) {
+  switch (act) {
+    case 1: return gelu_grad_f(y);
+    case 2: return y > 0.f ? 1.f : 0.f;
+    case 3: {
+      const float s = 1.0f / (1.0f + __expf(-y));
+      return s * (1.0f + y * (1.0f - s));
+    }
+    default: return 1.f;
+  }
+}
+
 __device__ __forceinline__ float bf16_bits_to_f(uint32_t hi16) { return __uint_as_float(hi16 << 16); }
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);

@@ -185,7 +185,7 @@ __global__ void gn_act_fwd_kernel(const float* __restrict__ x, const float* __re
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float y = (v[j] - mean) * rstd * gm[j] + bt[j];
-        v[j] = act ? gelu_f(y) : y;
+        v[j] = act_f(y, act);
       }
       uint4 o;
       o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]);
@@ -193,7 +193,7 @@ __global__ void gn_act_fwd_kernel(const float* __restrict__ x, const float* __re
       *reinterpret_cast<uint4*>(out + row * C + c) = o;
     } else {
       float y = (*xp - mean) * rstd * gamma[c] + beta[c];
-      out[row * C + c] = __float2bfloat16(act ? gelu_f(y) : y);
+      out[row * C + c] = __float2bfloat16(act_f(y, act));
     }
   }
 }
@@ -243,7 +243,7 @@ __global__ void gn_bwd_reduce_kernel(const float* __restrict__ x, const float* _
       for (int j = 0; j < VEC; ++j) {
         const float xh = (xv[j] - mean) * rstd;
         float dy = dv[j];
-        if (act) dy *= gelu_grad_f(xh * gm[j] + bt[j]);
+        if (act) dy *= act_grad_f(xh * gm[j] + bt[j], act);
         s1[j] += dy;
         s2[j] += dy * xh;
       }
@@ -344,7 +344,7 @@ __global__ void gn_bwd_apply_kernel(const float* __restrict__ x, const float* __
       const float gmj = gamma[c + j];
       const float xh = (xv[j] - mean) * rstd;
       float dy = dv[j];
-      if (act) dy *= gelu_grad_f(xh * gmj + beta[c + j]);
+      if (act) dy *= act_grad_f(xh * gmj + beta[c + j], act);
       o[j] = rstd * (dy * gmj - m1 - xh * m2) + rv[j];
     }
     if (VEC == 8) {
@@ -396,8 +396,8 @@ __global__ void colsum_partial_kernel(const __nv_bfloat16* __restrict__ x, long 
 #pragma unroll
   for (int j = 0; j < VEC; ++j) sm[(size_t)threadIdx.x * VEC + j] = acc[j];
   __syncthreads();
-  if (threadIdx.x < UL * VEC) {
-    const int uu = threadIdx.x / VEC, j = threadIdx.x % VEC;
+  for (int t = threadIdx.x; t < UL * VEC; t += blockDim.x) {
+    const int uu = t / VEC, j = t % VEC;
     const int cc = (blockIdx.y * UL + uu) * VEC + j;
     if (cc < C) {
       float s = 0.f;

@@ -167,6 +167,26 @@ __global__ void nll_final_kernel(const double* __restrict__ ws, int nblocks, dou
   if (threadIdx.x == 0) { sums[0] = t1; sums[1] = t2; sums[2] = 0.0; }
 }
 
+// loss / metric scalars of AutoencoderKL.get_loss (src/model.py:660-668), one thread:
+//   out[0] = loss, out[1] = nll_loss, out[2] = kl_loss (already * kl_weight), out[3] = pixel_mse,
+//   out[4] = d(loss)/d(logvar)
+__global__ void vae_loss_finalize_kernel(const double* __restrict__ sums, const float* __restrict__ kl, int B,
+                                         const float* __restrict__ logvar, double n_elem, float kl_weight,
+                                         float* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const double lv = (double)logvar[0];
+  const double inv_var = exp(-lv);
+  double kls = 0.0;
+  for (int b = 0; b < B; ++b) kls += (double)kl[b];
+  const double nll = (sums[0] * inv_var + lv * n_elem) / (double)B;
+  const double klw = (double)kl_weight * kls / (double)B;
+  out[0] = (float)(nll + klw);
+  out[1] = (float)nll;
+  out[2] = (float)klw;
+  out[3] = (float)(sums[1] / n_elem);
+  out[4] = (float)((n_elem - sums[0] * inv_var) / (double)B);
+}
+
 // ---------------------------------------------------------------------------------------------- L2 head loss
 struct L2Targets { const float* t[8]; };
 
@@ -412,6 +432,44 @@ extern "C" int32_t tvae_adamw(float* param, const float* grad, float* exp_avg, f
   int grid = (int)(g4 < 1 ? 1 : (g4 > 148 * 8 ? 148 * 8 : g4));
   adamw_kernel<<<grid, 256, 0, stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay,
                                          (float)bc1, (float)sqrt(bc2), sumsq, max_norm, grad_scale);
+  TVAE_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int32_t tvae_vae_loss_finalize(const double* sums, const float* kl, int32_t B, const float* logvar,
+                                          double n_elem, float kl_weight, float* out, cudaStream_t stream) {
+  TVAE_CHECK(sums && kl && logvar && out, "tvae_vae_loss_finalize: null pointer");
+  vae_loss_finalize_kernel<<<1, 32, 0, stream>>>(sums, kl, B, logvar, n_elem, kl_weight, out);
+  TVAE_CUDA(cudaGetLastError());
+  return 0;
+}
+
+namespace tvae {
+namespace {
+// total = vae_loss + sum_p w_p * mse_p over products with at least one valid pixel (src/model_with_l2.py:161-172)
+__global__ void l2head_finalize_kernel(const double* __restrict__ sums, const float* __restrict__ weights, int nprod,
+                                       const float* __restrict__ vae_scal, float* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double total = (double)vae_scal[0];
+  for (int p = 0; p < nprod; ++p) {
+    const double cnt = sums[2 * p + 1];
+    if (cnt > 0.0) {
+      const double mse = sums[2 * p] / cnt;
+      total += (double)weights[p] * mse;
+      out[1 + p] = (float)mse;
+    } else {
+      out[1 + p] = __int_as_float(0x7fc00000);
+    }
+  }
+  out[0] = (float)total;
+}
+}  // namespace
+}  // namespace tvae
+
+extern "C" int32_t tvae_l2head_finalize(const double* sums, const float* weights, int32_t nprod, const float* vae_scal,
+                                        float* out, cudaStream_t stream) {
+  TVAE_CHECK(sums && weights && vae_scal && out, "tvae_l2head_finalize: null pointer");
+  tvae::l2head_finalize_kernel<<<1, 32, 0, stream>>>(sums, weights, nprod, vae_scal, out);
   TVAE_CUDA(cudaGetLastError());
   return 0;
 }

@@ -10,11 +10,33 @@ import math
 import torch
 
 from . import _lib
-from ._lib import ConvArgs, WgradArgs, check, lib
+from ._lib import ConvArgs, WgradArgs, lib
+from ._lib import check as _check
 
 
 def _stream():
     return torch.cuda.current_stream().cuda_stream
+
+
+def check(rc, what):
+    _check(rc, what)
+    KERNEL_LAUNCHES[0] += _KERNELS_PER_CALL.get(what, 0)
+
+
+# bench.py hooks: PROFILE["conv"|"wgrad"] = {"match": fn(pixels, Cout|Cm, Cin|Cn, kind, R) -> bool, "events": []}
+# brackets the matching launches with CUDA events on the launching stream (per-kernel roofline numbers)
+PROFILE = {}
+
+KERNEL_LAUNCHES = [0]   # kernels of libtvae_b200.so enqueued through this module (bench.py reports the delta)
+
+# kernels launched by one call of each C-ABI entry point
+_KERNELS_PER_CALL = {
+    "tvae_pack_weight": 1, "tvae_conv_gemm": 1, "tvae_wgrad_gemm": 2, "tvae_nchw_f32_to_nhwc_bf16": 1,
+    "tvae_nhwc_f32_to_nchw_f32": 1, "tvae_nhwc_bf16_to_nchw_f32": 1, "tvae_f32_to_bf16": 1, "tvae_gn_stats": 1,
+    "tvae_gn_act_fwd": 1, "tvae_gn_act_bwd": 3, "tvae_colsum_bf16": 2, "tvae_attn_fwd": 1, "tvae_attn_bwd": 2,
+    "tvae_reparam_fwd": 1, "tvae_reparam_bwd": 1, "tvae_nll_fwd": 2, "tvae_vae_loss_finalize": 1,
+    "tvae_l2head_loss_fwd": 1, "tvae_l2head_loss_bwd": 1, "tvae_l2head_finalize": 1, "tvae_sumsq": 2, "tvae_adamw": 1,
+}
 
 
 def _ptr(t):
@@ -23,6 +45,12 @@ def _ptr(t):
 
 def round_up(v, m):
     return (v + m - 1) // m * m
+
+
+def pitch_of(t):
+    """Channel pitch (elements between consecutive pixels) of an NHWC / [rows, C] tensor or channel-slice view."""
+    assert t.stride(-1) == 1, "channels must be the contiguous dimension"
+    return t.stride(-2)
 
 
 def require_cuda(t, name="tensor"):
@@ -83,7 +111,8 @@ def pack_weight(w, mode, out=None):
 def conv_gemm(x, C_in, wp, *, kind, R, Cout, flip=False, bias=None, residual=None, want_f32=True, want_bf16=False,
               bf16_pitch=None, bn=0, out_f32=None, out_bf16=None):
     """x: bf16 [N,H,W,pitch]. Returns (out_f32 or None, out_bf16 or None) as NHWC tensors."""
-    N, H, W, pitch = x.shape
+    N, H, W, _ = x.shape
+    pitch = pitch_of(x)
     if kind == 1:
         oH, oW = H // 2, W // 2
     elif kind == 2:
@@ -102,11 +131,19 @@ def conv_gemm(x, C_in, wp, *, kind, R, Cout, flip=False, bias=None, residual=Non
     a.w = wp.data.data_ptr(); a.w_rows, a.k_pitch, a.c_pad = wp.rows, wp.k_pitch, wp.c_pad
     a.Cout = Cout
     a.bias = _ptr(bias)
-    a.residual = _ptr(residual); a.res_pitch = residual.shape[-1] if residual is not None else 0
-    a.out_f32 = _ptr(out_f32); a.out_f32_pitch = out_f32.shape[-1] if out_f32 is not None else 0
-    a.out_bf16 = _ptr(out_bf16); a.out_bf16_pitch = out_bf16.shape[-1] if out_bf16 is not None else 0
+    a.residual = _ptr(residual); a.res_pitch = pitch_of(residual) if residual is not None else 0
+    a.out_f32 = _ptr(out_f32); a.out_f32_pitch = pitch_of(out_f32) if out_f32 is not None else 0
+    a.out_bf16 = _ptr(out_bf16); a.out_bf16_pitch = pitch_of(out_bf16) if out_bf16 is not None else 0
     a.bn = bn
-    check(lib.tvae_conv_gemm(C.byref(a), _stream()), "tvae_conv_gemm")
+    prof = PROFILE.get("conv")
+    if prof is not None and prof["match"](N * oH * oW if kind != 2 else N * H * W, Cout, C_in, kind, R):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(lib.tvae_conv_gemm(C.byref(a), _stream()), "tvae_conv_gemm")
+        e1.record()
+        prof["events"].append((e0, e1))
+    else:
+        check(lib.tvae_conv_gemm(C.byref(a), _stream()), "tvae_conv_gemm")
     return out_f32, out_bf16
 
 
@@ -125,7 +162,8 @@ def _workspace(nbytes, device, key="ws"):
 
 def wgrad_gemm(p, Cm, q, Cn, *, kind, R, grad, accumulate=False, splits=0):
     """grad[m][n][tap] (+)= sum_pixels p[pixel][m] * q[pixel (+) tap][n]; p: bf16 [N,H,W,pitch] (the dense grid)."""
-    N, H, W, pp = p.shape
+    N, H, W, _ = p.shape
+    pp = pitch_of(p)
     taps = R * R if kind == 0 else 4
     if splits <= 0:
         splits = lib.tvae_wgrad_splits(Cm, Cn, taps, N * H * W)
@@ -134,11 +172,19 @@ def wgrad_gemm(p, Cm, q, Cn, *, kind, R, grad, accumulate=False, splits=0):
     assert grad.is_contiguous() and grad.dtype == torch.float32 and grad.numel() == Cm * Cn * taps
     a = WgradArgs()
     a.p = p.data_ptr(); a.p_pitch = pp; a.Cm = Cm
-    a.q = q.data_ptr(); a.q_pitch = q.shape[-1]; a.Cn = Cn
+    a.q = q.data_ptr(); a.q_pitch = pitch_of(q); a.Cn = Cn
     a.N, a.H, a.W = N, H, W
     a.kind, a.R, a.splits = kind, R, splits
     a.workspace = ws.data_ptr(); a.grad = grad.data_ptr(); a.accumulate = int(accumulate)
-    check(lib.tvae_wgrad_gemm(C.byref(a), _stream()), "tvae_wgrad_gemm")
+    prof = PROFILE.get("wgrad")
+    if prof is not None and prof["match"](N * H * W, Cm, Cn, kind, R):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(lib.tvae_wgrad_gemm(C.byref(a), _stream()), "tvae_wgrad_gemm")
+        e1.record()
+        prof["events"].append((e0, e1))
+    else:
+        check(lib.tvae_wgrad_gemm(C.byref(a), _stream()), "tvae_wgrad_gemm")
 
 
 # ----------------------------------------------------------------------------------------------- layout
@@ -204,7 +250,7 @@ def gn_act_bwd(x, stats, gamma, beta, da, gres, G, act, dgamma, dbeta):
 def colsum_bf16(x, Cc, out):
     rows = x.numel() // x.shape[-1]
     ws = _workspace(lib.tvae_colsum_workspace_bytes(rows, Cc), x.device, "colsum")
-    check(lib.tvae_colsum_bf16(x.data_ptr(), rows, Cc, x.shape[-1], out.data_ptr(), ws.data_ptr(), _stream()),
+    check(lib.tvae_colsum_bf16(x.data_ptr(), rows, Cc, pitch_of(x), out.data_ptr(), ws.data_ptr(), _stream()),
           "tvae_colsum_bf16")
 
 
@@ -277,6 +323,14 @@ def nll_fwd(x_bf16, xhat, Cc, loss_type, logvar, batch, want_grad):
     return sums, dx
 
 
+def vae_loss_finalize(sums, kl, logvar, n_elem, kl_weight):
+    """Returns fp32[5] = (loss, nll_loss, kl_loss, pixel_mse, dloss/dlogvar) on the device."""
+    out = torch.empty((5,), dtype=torch.float32, device=kl.device)
+    check(lib.tvae_vae_loss_finalize(sums.data_ptr(), kl.data_ptr(), kl.numel(), logvar.data_ptr(), float(n_elem),
+                                     float(kl_weight), out.data_ptr(), _stream()), "tvae_vae_loss_finalize")
+    return out
+
+
 def _target_array(targets):
     arr = (C.c_void_p * len(targets))()
     for i, t in enumerate(targets):
@@ -297,6 +351,13 @@ def l2head_loss_bwd(pred, targets, B, h, w, sums, weights, grad_scale, dp_pitch=
                                    sums.data_ptr(), weights.data_ptr(), float(grad_scale), dpred.data_ptr(), dp_pitch,
                                    _stream()), "tvae_l2head_loss_bwd")
     return dpred
+
+
+def l2head_finalize(sums, weights, vae_scal):
+    out = torch.empty((1 + sums.shape[0],), dtype=torch.float32, device=sums.device)
+    check(lib.tvae_l2head_finalize(sums.data_ptr(), weights.data_ptr(), sums.shape[0], vae_scal.data_ptr(),
+                                   out.data_ptr(), _stream()), "tvae_l2head_finalize")
+    return out
 
 
 # ----------------------------------------------------------------------------------------------- optimiser

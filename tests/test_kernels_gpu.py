@@ -366,5 +366,5 @@ def test_adamw_and_clip():
         o.adamw(p, grad, m, v, lr=1e-3, beta1=0.9, beta2=0.95, eps=1e-8, weight_decay=0.05, step=step, sumsq_buf=ss,
                 max_norm=1.0)
         torch.cuda.synchronize()
-        assert abs(ss.item() - grad.double().pow(2).sum().item()) / ss.item() < 1e-10
+        assert abs(ss.item() - grad.double().pow(2).sum().item()) / ss.item() < 1e-7
         assert torch.allclose(p, p_ref.detach(), rtol=1e-5, atol=1e-7)
