@@ -230,6 +230,7 @@ using namespace tvae;
 extern "C" int32_t tvae_attn_fwd(const float* q, const float* k, const float* v, int32_t pitch, int32_t B, int32_t T,
                                  int32_t C, int32_t heads, void* out_bf16, float* out_f32, float* lse,
                                  cudaStream_t stream) {
+  TVAE_ENTER(q);
   TVAE_CHECK(q && k && v && (out_bf16 || out_f32), "tvae_attn_fwd: null pointer");
   TVAE_CHECK(heads > 0 && C % heads == 0 && ROWS * heads <= 1024, "tvae_attn_fwd: bad heads");
   const int hd = C / heads;
@@ -250,6 +251,7 @@ extern "C" int32_t tvae_attn_fwd(const float* q, const float* k, const float* v,
 extern "C" int32_t tvae_attn_bwd(const float* q, const float* k, const float* v, int32_t pitch, const float* o,
                                  const float* d_out, const float* lse, int32_t B, int32_t T, int32_t C, int32_t heads,
                                  void* dqkv_bf16, float* workspace, cudaStream_t stream) {
+  TVAE_ENTER(q);
   TVAE_CHECK(q && k && v && o && d_out && lse && dqkv_bf16 && workspace, "tvae_attn_bwd: null pointer");
   TVAE_CHECK(heads > 0 && C % heads == 0 && ROWS * heads <= 1024, "tvae_attn_bwd: bad heads");
   const int hd = C / heads;

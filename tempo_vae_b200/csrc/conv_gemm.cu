@@ -262,6 +262,7 @@ int pick_bn(int cout) {
 using namespace tvae;
 
 extern "C" int32_t tvae_conv_gemm(const tvae_conv_args* a, cudaStream_t stream) {
+  TVAE_ENTER(a ? a->x : nullptr);
   TVAE_CHECK(a != nullptr, "tvae_conv_gemm: null args");
   TVAE_CHECK(a->x && a->w, "tvae_conv_gemm: null x/w");
   TVAE_CHECK(a->out_f32 || a->out_bf16, "tvae_conv_gemm: no output");

@@ -428,6 +428,7 @@ using namespace tvae;
 
 extern "C" int32_t tvae_pack_weight(const float* w, void* out, int32_t Crow, int32_t TR, int32_t TK, int32_t C,
                                     int32_t c_pad, int64_t s_row, int64_t s_col, int64_t s_tap, cudaStream_t stream) {
+  TVAE_ENTER(w);
   TVAE_CHECK(w && out, "tvae_pack_weight: null pointer");
   TVAE_CHECK(TR == 1 || TK == 1, "tvae_pack_weight: one of TR, TK must be 1");
   TVAE_CHECK(c_pad >= C, "tvae_pack_weight: c_pad < C");
@@ -440,6 +441,7 @@ extern "C" int32_t tvae_pack_weight(const float* w, void* out, int32_t Crow, int
 
 extern "C" int32_t tvae_nchw_f32_to_nhwc_bf16(const float* x, void* out, int32_t N, int32_t C, int32_t HW,
                                               int32_t pitch, cudaStream_t stream) {
+  TVAE_ENTER(x);
   TVAE_CHECK(x && out, "tvae_nchw_f32_to_nhwc_bf16: null pointer");
   TVAE_CHECK(pitch >= C && pitch % 2 == 0, "tvae_nchw_f32_to_nhwc_bf16: bad pitch");
   dim3 grid((HW + 63) / 64, (pitch + 63) / 64, N);
@@ -449,6 +451,7 @@ extern "C" int32_t tvae_nchw_f32_to_nhwc_bf16(const float* x, void* out, int32_t
 }
 extern "C" int32_t tvae_nhwc_f32_to_nchw_f32(const float* x, float* out, int32_t N, int32_t C, int32_t HW,
                                              int32_t pitch, cudaStream_t stream) {
+  TVAE_ENTER(x);
   TVAE_CHECK(x && out, "tvae_nhwc_f32_to_nchw_f32: null pointer");
   dim3 grid((HW + 63) / 64, (C + 63) / 64, N);
   nhwc_to_nchw_kernel<float><<<grid, 256, 0, stream>>>(x, out, C, HW, pitch);
@@ -457,6 +460,7 @@ extern "C" int32_t tvae_nhwc_f32_to_nchw_f32(const float* x, float* out, int32_t
 }
 extern "C" int32_t tvae_nhwc_bf16_to_nchw_f32(const void* x, float* out, int32_t N, int32_t C, int32_t HW,
                                               int32_t pitch, cudaStream_t stream) {
+  TVAE_ENTER(x);
   TVAE_CHECK(x && out, "tvae_nhwc_bf16_to_nchw_f32: null pointer");
   dim3 grid((HW + 63) / 64, (C + 63) / 64, N);
   nhwc_to_nchw_kernel<__nv_bfloat16>
@@ -465,6 +469,7 @@ extern "C" int32_t tvae_nhwc_bf16_to_nchw_f32(const void* x, float* out, int32_t
   return 0;
 }
 extern "C" int32_t tvae_f32_to_bf16(const float* x, void* out, int64_t n, cudaStream_t stream) {
+  TVAE_ENTER(x);
   TVAE_CHECK(x && out, "tvae_f32_to_bf16: null pointer");
   f32_to_bf16_kernel<<<ew_grid(n / 4 + 1), EW_THREADS, 0, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(out), n);
   TVAE_CUDA(cudaGetLastError());
@@ -473,6 +478,7 @@ extern "C" int32_t tvae_f32_to_bf16(const float* x, void* out, int64_t n, cudaSt
 
 extern "C" int32_t tvae_gn_stats(const float* x, int32_t N, int32_t HW, int32_t C, int32_t G, float eps, float* stats,
                                  cudaStream_t stream) {
+  TVAE_ENTER(x);
   TVAE_CHECK(x && stats, "tvae_gn_stats: null pointer");
   TVAE_CHECK(G > 0 && C % G == 0, "tvae_gn_stats: C %% G != 0");
   const int gs = C / G;
@@ -487,6 +493,7 @@ extern "C" int32_t tvae_gn_stats(const float* x, int32_t N, int32_t HW, int32_t 
 extern "C" int32_t tvae_gn_act_fwd(const float* x, const float* stats, const float* gamma, const float* beta,
                                    int32_t N, int32_t HW, int32_t C, int32_t G, int32_t act, void* out,
                                    cudaStream_t stream) {
+  TVAE_ENTER(x);
   TVAE_CHECK(x && stats && gamma && beta && out, "tvae_gn_act_fwd: null pointer");
   TVAE_CHECK(G > 0 && C % G == 0, "tvae_gn_act_fwd: C %% G != 0");
   const long long rows = (long long)N * HW;
@@ -509,6 +516,7 @@ extern "C" int32_t tvae_gn_act_bwd(const float* x, const float* stats, const flo
                                    const void* da, const void* gres, int32_t N, int32_t HW, int32_t C, int32_t G,
                                    int32_t act, void* dx, float* dgamma, float* dbeta, float* ws,
                                    cudaStream_t stream) {
+  TVAE_ENTER(x);
   TVAE_CHECK(x && stats && gamma && beta && da && dx && dgamma && dbeta && ws, "tvae_gn_act_bwd: null pointer");
   TVAE_CHECK(G > 0 && C % G == 0, "tvae_gn_act_bwd: C %% G != 0");
   const int gs = C / G;
@@ -545,6 +553,7 @@ extern "C" int64_t tvae_colsum_workspace_bytes(int64_t rows, int32_t C) {
 
 extern "C" int32_t tvae_colsum_bf16(const void* x, int64_t rows, int32_t C, int32_t pitch, float* out, float* ws,
                                     cudaStream_t stream) {
+  TVAE_ENTER(x);
   TVAE_CHECK(x && out && ws, "tvae_colsum_bf16: null pointer");
   const int nb = colsum_blocks(rows);
   const long long rpb = (rows + nb - 1) / nb;

@@ -28,6 +28,47 @@ int num_sms() {
   return cached[dev];
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Thread/context binding. PyTorch's autograd worker threads set their CUDA device lazily, so an entry point can be
+// called on a thread that has NO current context yet; this library's (statically linked) runtime would then bind
+// device 0. Every entry point therefore calls enter(ptr): if the thread has no current context it binds the primary
+// context of the device that owns `ptr` (a device pointer argument). It never switches an already-bound thread.
+typedef CUresult (*ctx_get_current_fn)(CUcontext*);
+typedef CUresult (*ptr_get_attr_fn)(void*, CUpointer_attribute, CUdeviceptr);
+
+static void* driver_sym(const char* name) {
+  void* sym = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint(name, &sym, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  return sym;
+}
+
+int enter(const void* device_ptr) {
+  static ctx_get_current_fn get_cur = nullptr;
+  static ptr_get_attr_fn get_attr = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    get_cur = reinterpret_cast<ctx_get_current_fn>(driver_sym("cuCtxGetCurrent"));
+    get_attr = reinterpret_cast<ptr_get_attr_fn>(driver_sym("cuPointerGetAttribute"));
+  });
+  if (!get_cur || !get_attr) return 0;  // cannot check: rely on the caller's thread state
+  CUcontext cur = nullptr;
+  if (get_cur(&cur) == CUDA_SUCCESS && cur != nullptr) return 0;
+  int ordinal = -1;
+  if (device_ptr == nullptr ||
+      get_attr(&ordinal, CU_POINTER_ATTRIBUTE_DEVICE_ORDINAL, reinterpret_cast<CUdeviceptr>(device_ptr)) != CUDA_SUCCESS ||
+      ordinal < 0) {
+    set_error("no CUDA context is current on this thread and the device of pointer %p cannot be determined", device_ptr);
+    return -1;
+  }
+  if (cudaSetDevice(ordinal) != cudaSuccess) {
+    set_error("cudaSetDevice(%d) failed while binding a context to the calling thread", ordinal);
+    return -1;
+  }
+  return 0;
+}
+
 typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);

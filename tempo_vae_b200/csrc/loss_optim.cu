@@ -334,6 +334,7 @@ using namespace tvae;
 extern "C" int32_t tvae_reparam_fwd(const float* moments, const float* eps, uint64_t seed, uint64_t sample_offset,
                                     int32_t B, int32_t HW, int32_t Z, void* z_bf16, int32_t z_pitch, float* z_nchw,
                                     float* eps_out, float* kl, cudaStream_t stream) {
+  TVAE_ENTER(moments);
   TVAE_CHECK(moments, "tvae_reparam_fwd: null moments");
   TVAE_CHECK(B > 0 && HW > 0 && Z > 0, "tvae_reparam_fwd: bad shape");
   reparam_fwd_kernel<<<B, 256, 0, stream>>>(moments, eps, seed, sample_offset, HW, Z,
@@ -345,6 +346,7 @@ extern "C" int32_t tvae_reparam_fwd(const float* moments, const float* eps, uint
 extern "C" int32_t tvae_reparam_bwd(const float* moments, const float* dz1, const float* eps1, const float* dz2,
                                     const float* eps2, float kl_scale, int32_t B, int32_t HW, int32_t Z, void* dm,
                                     cudaStream_t stream) {
+  TVAE_ENTER(moments);
   TVAE_CHECK(moments && dm, "tvae_reparam_bwd: null pointer");
   TVAE_CHECK((!dz1 || eps1) && (!dz2 || eps2), "tvae_reparam_bwd: dz without eps");
   const long long total = (long long)B * HW * Z;
@@ -361,6 +363,7 @@ extern "C" int64_t tvae_nll_workspace_bytes(void) { return (int64_t)NLL_BLOCKS *
 extern "C" int32_t tvae_nll_fwd(const void* x, int32_t x_pitch, const float* xhat, int32_t xh_pitch, int64_t P,
                                 int32_t C, int32_t loss_type, const float* logvar, int32_t batch, void* dxhat,
                                 int32_t dx_pitch, double* sums, double* ws, cudaStream_t stream) {
+  TVAE_ENTER(x);
   TVAE_CHECK(x && xhat && sums && ws, "tvae_nll_fwd: null pointer");
   TVAE_CHECK(!dxhat || logvar, "tvae_nll_fwd: dxhat needs logvar");
   TVAE_CHECK(loss_type == 0 || loss_type == 1, "tvae_nll_fwd: loss_type must be 0 (l1) or 1 (l2)");
@@ -381,6 +384,7 @@ extern "C" int32_t tvae_nll_fwd(const void* x, int32_t x_pitch, const float* xha
 
 extern "C" int32_t tvae_l2head_loss_fwd(const float* pred, int32_t pitch, const float* const* targets, int32_t nprod,
                                         int32_t B, int32_t h, int32_t w, double* out, cudaStream_t stream) {
+  TVAE_ENTER(pred);
   TVAE_CHECK(pred && targets && out, "tvae_l2head_loss_fwd: null pointer");
   TVAE_CHECK(nprod >= 1 && nprod <= 8, "tvae_l2head_loss_fwd: nprod must be in [1, 8]");
   L2Targets tg;
@@ -393,6 +397,7 @@ extern "C" int32_t tvae_l2head_loss_fwd(const float* pred, int32_t pitch, const 
 extern "C" int32_t tvae_l2head_loss_bwd(const float* pred, int32_t pitch, const float* const* targets, int32_t nprod,
                                         int32_t B, int32_t h, int32_t w, const double* sums, const float* weights,
                                         float grad_scale, void* dpred, int32_t dp_pitch, cudaStream_t stream) {
+  TVAE_ENTER(pred);
   TVAE_CHECK(pred && targets && sums && weights && dpred, "tvae_l2head_loss_bwd: null pointer");
   TVAE_CHECK(nprod >= 1 && nprod <= 8 && dp_pitch >= nprod, "tvae_l2head_loss_bwd: bad nprod / pitch");
   L2Targets tg;
@@ -409,6 +414,7 @@ extern "C" int32_t tvae_l2head_loss_bwd(const float* pred, int32_t pitch, const 
 extern "C" int64_t tvae_sumsq_workspace_bytes(int64_t n) { (void)n; return (int64_t)SUMSQ_BLOCKS * sizeof(double); }
 
 extern "C" int32_t tvae_sumsq(const float* g, int64_t n, double* out, double* ws, cudaStream_t stream) {
+  TVAE_ENTER(g);
   TVAE_CHECK(g && out && ws, "tvae_sumsq: null pointer");
   TVAE_CHECK((reinterpret_cast<uintptr_t>(g) & 15) == 0, "tvae_sumsq: g must be 16-byte aligned");
   sumsq_partial_kernel<<<SUMSQ_BLOCKS, 256, 0, stream>>>(g, n, ws);
@@ -421,6 +427,7 @@ extern "C" int32_t tvae_sumsq(const float* g, int64_t n, double* out, double* ws
 extern "C" int32_t tvae_adamw(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
                               float beta1, float beta2, float eps, float weight_decay, int64_t step,
                               const double* sumsq, float max_norm, float grad_scale, cudaStream_t stream) {
+  TVAE_ENTER(param);
   TVAE_CHECK(param && grad && exp_avg && exp_avg_sq, "tvae_adamw: null pointer");
   TVAE_CHECK(step >= 1, "tvae_adamw: step is 1-based");
   TVAE_CHECK(((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) |
@@ -438,6 +445,7 @@ extern "C" int32_t tvae_adamw(float* param, const float* grad, float* exp_avg, f
 
 extern "C" int32_t tvae_vae_loss_finalize(const double* sums, const float* kl, int32_t B, const float* logvar,
                                           double n_elem, float kl_weight, float* out, cudaStream_t stream) {
+  TVAE_ENTER(sums);
   TVAE_CHECK(sums && kl && logvar && out, "tvae_vae_loss_finalize: null pointer");
   vae_loss_finalize_kernel<<<1, 32, 0, stream>>>(sums, kl, B, logvar, n_elem, kl_weight, out);
   TVAE_CUDA(cudaGetLastError());
@@ -468,6 +476,7 @@ __global__ void l2head_finalize_kernel(const double* __restrict__ sums, const fl
 
 extern "C" int32_t tvae_l2head_finalize(const double* sums, const float* weights, int32_t nprod, const float* vae_scal,
                                         float* out, cudaStream_t stream) {
+  TVAE_ENTER(sums);
   TVAE_CHECK(sums && weights && vae_scal && out, "tvae_l2head_finalize: null pointer");
   tvae::l2head_finalize_kernel<<<1, 32, 0, stream>>>(sums, weights, nprod, vae_scal, out);
   TVAE_CUDA(cudaGetLastError());

@@ -10,6 +10,12 @@ namespace tvae {
 
 void set_error(const char* fmt, ...);
 int num_sms();
+// bind a CUDA context to the calling thread if it has none (device = owner of device_ptr); 0 on success
+int enter(const void* device_ptr);
+#define TVAE_ENTER(ptr)                      \
+  do {                                       \
+    if (tvae::enter(ptr) != 0) return -4;    \
+  } while (0)
 
 // Encode a bf16 tiled tensor map with 128-byte swizzle and zero out-of-bounds fill.
 // dims/box are innermost-first; strides (bytes) are for dims 1..rank-1. Returns 0 on success.

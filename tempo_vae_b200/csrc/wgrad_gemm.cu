@@ -254,6 +254,7 @@ extern "C" int32_t tvae_wgrad_splits(int32_t cm, int32_t cn, int32_t ntaps, int6
 }
 
 extern "C" int32_t tvae_wgrad_gemm(const tvae_wgrad_args* a, cudaStream_t stream) {
+  TVAE_ENTER(a ? a->p : nullptr);
   TVAE_CHECK(a && a->p && a->q && a->grad && a->workspace, "tvae_wgrad_gemm: null pointer");
   TVAE_CHECK(a->kind >= 0 && a->kind <= 2, "tvae_wgrad_gemm: bad kind");
   TVAE_CHECK(a->p_pitch % 8 == 0 && a->q_pitch % 8 == 0, "tvae_wgrad_gemm: pitches must be multiples of 8");
