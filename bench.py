@@ -197,6 +197,7 @@ def run_ours(args):
     xs = [synthetic_batch(torch, B, shape, dev, seed=1000 * rank + i) for i in range(2)]
     for i in range(args.warmup):
         step_device(xs[i % 2])
+        trainer.step = 1                  # (the reference prints batch statistics while step == 0)
     M = B * 64 * 64
     ops.PROFILE["conv"] = {"match": lambda px, co, ci, kind, R: px == M and co == 512 and ci == 512 and kind == 0 and R == 3,
                            "events": []}
@@ -217,7 +218,7 @@ def run_ours(args):
     conv_ms = [a.elapsed_time(b) for a, b in ops.PROFILE["conv"]["events"]]
     wg_ms = [a.elapsed_time(b) for a, b in ops.PROFILE["wgrad"]["events"]]
     ops.PROFILE.clear()
-    final = {k: float(v) for k, v in last.items()}
+    final = {k: float(v.detach()) for k, v in last.items()}
     value = world * B / (ms / 1e3)
 
     # ---------------------------------------------------------------- end to end (host buffers, public API)
