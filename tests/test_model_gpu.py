@@ -314,3 +314,34 @@ def test_loss_curve_tracks_oracle_over_40_steps(capsys):
     with capsys.disabled():
         print("\n[40-step curve vs oracle] worst relative deviations:", worst)
     assert worst["loss"] < 1e-2 and worst["pixel_mse"] < 2e-2 and worst["kl_loss"] < 5e-2
+
+
+def test_inference_patch_sweep_and_whole_granule_vs_oracle(capsys):
+    """BASELINE config 5 call pattern (patch-batched encode -> posterior mean, sharded round-robin) and the
+    reference's whole-granule call (fully convolutional, global attention / GroupNorm statistics)."""
+    import tempo_vae_b200 as t
+    cfg = orc.TINY_CFG
+    fx = gold("tiny_train.pt")
+    model = build(cfg, fx["state_dict"])
+    C = cfg["shape"][0]
+    g = torch.Generator().manual_seed(21)
+    rad = torch.exp(torch.randn((131, 256, C), generator=g) * 0.5 + 3.0)
+    mean_s, std_s = torch.full((C,), 3.0), torch.full((C,), 0.5)
+    z = t.normalize_radiance(rad, mean_s, std_s)
+    assert float(z.abs().max()) <= 10.0
+    patches = t.granule_to_patches(z)                       # 2 x 4 patches of [C, 64, 64]
+    assert patches.shape == (8, C, 64, 64)
+    lat = torch.cat([t.encode_patches(model, patches, batch_size=3, rank=r, world=2).cpu() for r in range(2)])
+    order = list(range(0, 8, 2)) + list(range(1, 8, 2))
+    with torch.no_grad():
+        ref_mean, _, _ = orc.encode(fx["state_dict"], patches[order], cfg)
+    assert lat.shape == ref_mean.shape == (8, cfg["embed_dim"], 16, 16)
+    e_patch = rel(lat, ref_mean)
+    whole = t.encode_granule_whole(model, z)
+    with torch.no_grad():
+        ref_whole, _, _ = orc.encode(fx["state_dict"], z[:128, :256].permute(2, 0, 1).unsqueeze(0), cfg)
+    assert whole.shape == ref_whole.shape == (1, cfg["embed_dim"], 32, 64)
+    e_whole = rel(whole, ref_whole)
+    with capsys.disabled():
+        print(f"\n[inference] patch-sweep latent rel-L2 {e_patch:.3e}; whole-granule (2048-token attention) {e_whole:.3e}")
+    assert e_patch < 1.5e-2 and e_whole < 1.5e-2
