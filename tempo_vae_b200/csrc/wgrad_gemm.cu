@@ -96,10 +96,14 @@ wgrad_gemm_kernel(const __grid_constant__ WgradMaps maps, const __grid_constant_
         const int kb0 = (int)((long long)p.nblocks * split / p.splits);
         const int kb1 = (int)((long long)p.nblocks * (split + 1) / p.splits);
         const CUtensorMap* qm = &maps.q[p.qmap[tap]];
+        // pixel-block coordinates advance incrementally (no div/mod on the producer's critical path)
+        int iw = kb0 % p.tiles_w, ih = (kb0 / p.tiles_w) % p.tiles_h, in = kb0 / (p.tiles_w * p.tiles_h);
         for (int kb = kb0; kb < kb1; ++kb) {
-          const int w0 = (kb % p.tiles_w) * p.bw;
-          const int h0 = ((kb / p.tiles_w) % p.tiles_h) * p.bh;
-          const int n0 = (kb / (p.tiles_w * p.tiles_h)) * p.bnimg;
+          const int w0 = iw * p.bw, h0 = ih * p.bh, n0 = in * p.bnimg;
+          if (++iw == p.tiles_w) {
+            iw = 0;
+            if (++ih == p.tiles_h) { ih = 0; ++in; }
+          }
           mbar_wait(&empty_bar[stage], phase ^ 1, 11);
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_STAGE_BYTES;
