@@ -498,6 +498,11 @@ extern "C" int32_t tvae_gn_act_fwd(const float* x, const float* stats, const flo
   TVAE_CHECK(G > 0 && C % G == 0, "tvae_gn_act_fwd: C %% G != 0");
   const long long rows = (long long)N * HW;
   const int gs = C / G;
+  if (gn_fast_ok(C, G)) {
+    gn_act_fwd_fast(x, stats, gamma, beta, N, HW, C, G, act, reinterpret_cast<__nv_bfloat16*>(out), stream);
+    TVAE_CUDA(cudaGetLastError());
+    return 0;
+  }
   if (gs % 8 == 0)
     gn_act_fwd_kernel<8><<<ew_grid(rows * (C / 8)), EW_THREADS, 0, stream>>>(
         x, stats, gamma, beta, rows, HW, C, G, act, reinterpret_cast<__nv_bfloat16*>(out));
@@ -525,6 +530,11 @@ extern "C" int32_t tvae_gn_act_bwd(const float* x, const float* stats, const flo
   const __nv_bfloat16* grp = reinterpret_cast<const __nv_bfloat16*>(gres);
   __nv_bfloat16* dxp = reinterpret_cast<__nv_bfloat16*>(dx);
   const float* gmeans = ws + 2ll * N * C;
+  if (gn_fast_ok(C, G)) {
+    gn_act_bwd_fast(x, stats, gamma, beta, dap, grp, N, HW, C, G, act, dxp, dgamma, dbeta, ws, stream);
+    TVAE_CUDA(cudaGetLastError());
+    return 0;
+  }
   if (gs % 8 == 0 && gs / 8 <= 256) {
     const int threads = 256;
     gn_bwd_reduce_kernel<8><<<N * G, threads, threads * 16 * sizeof(float), stream>>>(x, stats, gamma, beta, dap, HW, C,

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <cuda_bf16.h>
 #include <stdint.h>
 #include <string.h>
 #include "../../include/tvae.h"
@@ -24,5 +25,13 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 
 // Pixel box {bw, bh, bn} that covers `rows` consecutive pixels (raster order) of an [N, H, W] grid.
 bool pixel_box(int H, int W, int rows, int* bw, int* bh, int* bn);
+
+// bandwidth-tuned GroupNorm paths (gn_fast.cu)
+bool gn_fast_ok(int C, int G);
+int gn_act_fwd_fast(const float* x, const float* stats, const float* gamma, const float* beta, int N, int HW, int C,
+                    int G, int act, __nv_bfloat16* out, cudaStream_t stream);
+int gn_act_bwd_fast(const float* x, const float* stats, const float* gamma, const float* beta, const __nv_bfloat16* da,
+                    const __nv_bfloat16* gres, int N, int HW, int C, int G, int act, __nv_bfloat16* dx, float* dgamma,
+                    float* dbeta, float* ws, cudaStream_t stream);
 
 }  // namespace tvae
