@@ -208,8 +208,10 @@ def run_ours(args):
     n0 = ops.KERNEL_LAUNCHES[0]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    th0 = time.perf_counter()
     for i in range(args.steps):
         last = step_device(xs[i % 2])
+    host_enqueue_ms = (time.perf_counter() - th0) / args.steps * 1e3     # CPU time to enqueue one step (no sync)
     e1.record()
     barrier()
     launches = ops.KERNEL_LAUNCHES[0] - n0
@@ -224,7 +226,8 @@ def run_ours(args):
     # ---------------------------------------------------------------- end to end (host buffers, public API)
     if args.skip_e2e:
         if rank == 0:
-            print(json.dumps({"profiling_run": True, "value": value, "ms_per_step": ms, "gpu_launches": launches}))
+            print(json.dumps({"profiling_run": True, "value": value, "ms_per_step": ms, "gpu_launches": launches,
+                              "host_enqueue_ms_per_step": host_enqueue_ms}))
         if world > 1:
             dist.destroy_process_group()
         return
@@ -291,6 +294,7 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms, "api": "Trainer.train_step over DevicePrefetcher (pinned host batches)"},
         "gpu_launches": launches,
+        "host_enqueue_ms_per_step": host_enqueue_ms,
         "clocks": clocks,
         "final_metrics": final,
     }

@@ -106,8 +106,8 @@ int32_t tvae_gn_stats(const float* x, int32_t N, int32_t HW, int32_t C, int32_t 
 int32_t tvae_gn_act_fwd(const float* x, const float* stats, const float* gamma, const float* beta, int32_t N,
                         int32_t HW, int32_t C, int32_t G, int32_t act, void* out_bf16, tvae_stream_t stream);
 /* da: bf16 gradient wrt the activation output; gres (optional bf16) is added to dx (residual branch).
- * dgamma/dbeta are overwritten. workspace: tvae_gn_bwd_workspace_bytes(N, C, G). */
-int64_t tvae_gn_bwd_workspace_bytes(int32_t N, int32_t C, int32_t G);
+ * dgamma/dbeta are overwritten. workspace: tvae_gn_bwd_workspace_bytes(N, HW, C, G). */
+int64_t tvae_gn_bwd_workspace_bytes(int32_t N, int32_t HW, int32_t C, int32_t G);
 int32_t tvae_gn_act_bwd(const float* x, const float* stats, const float* gamma, const float* beta, const void* da_bf16,
                         const void* gres_bf16, int32_t N, int32_t HW, int32_t C, int32_t G, int32_t act,
                         void* dx_bf16, float* dgamma, float* dbeta, float* workspace, tvae_stream_t stream);

@@ -513,7 +513,8 @@ extern "C" int32_t tvae_gn_act_fwd(const float* x, const float* stats, const flo
   return 0;
 }
 
-extern "C" int64_t tvae_gn_bwd_workspace_bytes(int32_t N, int32_t C, int32_t G) {
+extern "C" int64_t tvae_gn_bwd_workspace_bytes(int32_t N, int32_t HW, int32_t C, int32_t G) {
+  if (gn_fast_ok(C, G)) return gn_bwd_fast_ws_floats(N, HW, C, G) * 4;
   return (2ll * N * C + 2ll * N * G) * 4;
 }
 

