@@ -54,6 +54,12 @@ typedef struct {
   void* out_bf16;
   int32_t out_bf16_pitch;
   int32_t bn;           /* N tile, 0 = auto */
+  /* Optional fused GroupNorm statistics of the OUTPUT (after bias/residual): per-tile partial sums
+   * stats_part[slot][stats_groups][2] = (sum, sum of squares), slot = 128-pixel tile index (kind 0/1) or
+   * 4*tile + tap (kind 2). Needs Cout/stats_groups to be a multiple of 16 dividing the N tile and images of at least
+   * 128 output pixels; tvae_gn_stats_finalize turns the partials into (mean, rstd). NULL = off. */
+  float* stats_part;
+  int32_t stats_groups;
 } tvae_conv_args;
 int32_t tvae_conv_gemm(const tvae_conv_args* args, tvae_stream_t stream);
 
@@ -103,6 +109,10 @@ int32_t tvae_f32_to_bf16(const float* x, void* out_bf16, int64_t n, tvae_stream_
  */
 int32_t tvae_gn_stats(const float* x, int32_t N, int32_t HW, int32_t C, int32_t G, float eps, float* stats,
                       tvae_stream_t stream);
+/* stats[n][g] = (mean, rstd) from conv-epilogue partials: image n owns slots [n*slots_per_image, (n+1)*slots_per_image);
+ * count = elements per (image, group). */
+int32_t tvae_gn_stats_finalize(const float* stats_part, int32_t slots_per_image, int32_t N, int32_t G, double count,
+                               float eps, float* stats, tvae_stream_t stream);
 int32_t tvae_gn_act_fwd(const float* x, const float* stats, const float* gamma, const float* beta, int32_t N,
                         int32_t HW, int32_t C, int32_t G, int32_t act, void* out_bf16, tvae_stream_t stream);
 /* da: bf16 gradient wrt the activation output; gres (optional bf16) is added to dx (residual branch).

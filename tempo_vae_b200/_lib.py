@@ -30,6 +30,8 @@ class ConvArgs(C.Structure):
         ("out_bf16", C.c_void_p),
         ("out_bf16_pitch", C.c_int32),
         ("bn", C.c_int32),
+        ("stats_part", C.c_void_p),
+        ("stats_groups", C.c_int32),
     ]
 
 
@@ -68,6 +70,7 @@ def _load():
         "tvae_nhwc_bf16_to_nchw_f32": (i32, [vp, vp, i32, i32, i32, i32, vp]),
         "tvae_f32_to_bf16": (i32, [vp, vp, i64, vp]),
         "tvae_gn_stats": (i32, [vp, i32, i32, i32, i32, f32, vp, vp]),
+        "tvae_gn_stats_finalize": (i32, [vp, i32, i32, i32, C.c_double, f32, vp, vp]),
         "tvae_gn_act_fwd": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp]),
         "tvae_gn_bwd_workspace_bytes": (i64, [i32, i32, i32, i32]),
         "tvae_gn_act_bwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp]),

@@ -31,7 +31,7 @@ constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int STAGES = 4;
 constexpr int NTHREADS = 192;                    // warp0: TMA, warp1: MMA + TMEM alloc, warps 2-5: epilogue
 constexpr int TMEM_COLS = 512;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*stats*/;
 
 struct ConvMaps {
   CUtensorMap a[4];
@@ -53,6 +53,9 @@ struct ConvParams {
   const float* res;
   int ld_res;
   int up_mode, up_H, up_W, cout_per_tap;
+  // fused GroupNorm statistics of the output: per-tile partial (sum, sum of squares) per group
+  float* stats_part;   // [slots][G][2], slot = m_tile (x4 + tap for the transposed conv); NULL = off
+  int gs, G;           // group size (multiple of 16, divides BN), number of groups
 };
 
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -66,6 +69,7 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float2* stat_sm = reinterpret_cast<float2*>(smem + STAGES * STAGE_BYTES + 256);   // [2 acc stages][4 warps][16 groups]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -176,6 +180,8 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
         opix = ((long long)n * (2 * p.up_H) + (2 * h + (tap >> 1))) * (2 * p.up_W) + (2 * w + (tap & 1));
       }
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * 256u;
+      const bool do_stats = p.stats_part != nullptr;
+      float st1 = 0.f, st2 = 0.f;
       for (int c = 0; c < p.bn; c += 16) {
         uint32_t r[16];
         tmem_ld16(taddr + (uint32_t)c, r);
@@ -204,6 +210,13 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
                 if (col + j < p.n_valid) v[j] += rp[j];
             }
           }
+          if (do_stats) {   // host guarantees full 16-column chunks (Cout % gs == 0, gs % 16 == 0)
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              st1 += v[j];
+              st2 = fmaf(v[j], v[j], st2);
+            }
+          }
           if (p.out_f32) {
             float* op = p.out_f32 + opix * p.ld_f32 + col;
             if (full) {
@@ -229,6 +242,30 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
               for (int j = 0; j < 16; ++j)
                 if (col + j < p.n_valid) op[j] = __float2bfloat16(v[j]);
             }
+          }
+        }
+        if (do_stats && ((c + 16) % p.gs) == 0) {   // a group's columns are complete: reduce over the warp's 32 rows
+          const float w1 = warp_sum(st1), w2 = warp_sum(st2);
+          if (lane == 0) stat_sm[(as * 4 + q) * 16 + c / p.gs] = make_float2(w1, w2);
+          st1 = 0.f; st2 = 0.f;
+        }
+      }
+      if (do_stats) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // the 4 epilogue warps only
+        const int ng = p.bn / p.gs;
+        if (row < ng) {
+          float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {                     // fixed order => deterministic
+            const float2 t = stat_sm[(as * 4 + w) * 16 + row];
+            s1 += t.x; s2 += t.y;
+          }
+          const int gidx = col0 / p.gs + row;
+          if (gidx < p.G) {
+            const int tapslot = p.up_mode ? (nt * p.bn) / p.cout_per_tap : 0;
+            const long long slot = p.up_mode ? (long long)mt * 4 + tapslot : mt;
+            float* dst = p.stats_part + (slot * p.G + gidx) * 2;
+            dst[0] = s1; dst[1] = s2;
           }
         }
       }
@@ -363,6 +400,16 @@ extern "C" int32_t tvae_conv_gemm(const tvae_conv_args* a, cudaStream_t stream) 
     if (make_tmap_bf16(&maps.b, a->w, 2, dims, strides, box)) return -3;
   }
 
+  p.stats_part = a->stats_part;
+  if (p.stats_part) {
+    p.G = a->stats_groups;
+    TVAE_CHECK(p.G > 0 && a->Cout % p.G == 0, "tvae_conv_gemm: stats_groups must divide Cout");
+    p.gs = a->Cout / p.G;
+    TVAE_CHECK(p.gs % 16 == 0 && p.bn % p.gs == 0 && p.bn / p.gs <= 16,
+               "tvae_conv_gemm: fused statistics need a group size that is a multiple of 16 and divides the N tile");
+    TVAE_CHECK(p.bnimg == 1 && (long long)gH * gW % BM == 0,
+               "tvae_conv_gemm: fused statistics need at least 128 pixels per image");
+  }
   p.out_f32 = a->out_f32; p.ld_f32 = a->out_f32_pitch;
   p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(a->out_bf16); p.ld_bf16 = a->out_bf16_pitch;
   p.bias = a->bias;

@@ -156,6 +156,25 @@ __global__ void gn_stats_kernel(const float* __restrict__ x, int HW, int C, int 
   }
 }
 
+// (mean, rstd) from the conv epilogue's per-tile partial sums; fp64 combine in a fixed order
+__global__ void gn_stats_finalize_kernel(const float* __restrict__ part, int spi, int NG, int G, double count, float eps,
+                                         float* __restrict__ stats) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= NG) return;
+  const int n = i / G, g = i - n * G;
+  double s1 = 0.0, s2 = 0.0;
+  for (int k = 0; k < spi; ++k) {
+    const float* p = part + (((long long)n * spi + k) * G + g) * 2;
+    s1 += (double)p[0];
+    s2 += (double)p[1];
+  }
+  const double mean = s1 / count;
+  double var = s2 / count - mean * mean;
+  if (var < 0) var = 0;
+  stats[2 * i] = (float)mean;
+  stats[2 * i + 1] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
 // ---------------------------------------------------------------------------------------------- GN apply (+GELU)
 template <int VEC>
 __global__ void gn_act_fwd_kernel(const float* __restrict__ x, const float* __restrict__ stats,
@@ -486,6 +505,16 @@ extern "C" int32_t tvae_gn_stats(const float* x, int32_t N, int32_t HW, int32_t 
     gn_stats_kernel<4><<<N * G, 512, 0, stream>>>(x, HW, C, G, eps, stats);
   else
     gn_stats_kernel<1><<<N * G, 512, 0, stream>>>(x, HW, C, G, eps, stats);
+  TVAE_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int32_t tvae_gn_stats_finalize(const float* part, int32_t spi, int32_t N, int32_t G, double count, float eps,
+                                          float* stats, cudaStream_t stream) {
+  TVAE_ENTER(part);
+  TVAE_CHECK(part && stats && spi > 0 && N > 0 && G > 0, "tvae_gn_stats_finalize: bad arguments");
+  const int NG = N * G;
+  gn_stats_finalize_kernel<<<(NG + 127) / 128, 128, 0, stream>>>(part, spi, NG, G, count, eps, stats);
   TVAE_CUDA(cudaGetLastError());
   return 0;
 }

@@ -195,10 +195,11 @@ class _Act(nn.Module):
 class A:
     """An activation in flight: fp32 stream tensor and/or bf16 operand tensor, NHWC, C valid channels."""
 
-    __slots__ = ("f32", "bf16", "C")
+    __slots__ = ("f32", "bf16", "C", "stats")
 
-    def __init__(self, f32=None, bf16=None, C=0):
+    def __init__(self, f32=None, bf16=None, C=0, stats=None):
         self.f32, self.bf16, self.C = f32, bf16, C
+        self.stats = stats      # (G, eps, [N,G,2] mean/rstd) produced by the conv epilogue that wrote f32, or None
 
     def as_bf16(self):
         if self.bf16 is None:
@@ -207,12 +208,26 @@ class A:
 
 
 # =================================================================================================== conv fwd/bwd
-def conv_fwd(mod, x_bf16, Cin, *, residual=None, want_f32=True, want_bf16=False, out_f32=None):
+class ConvOut(tuple):
+    """(out_f32, out_bf16) with the fused GroupNorm statistics of the output attached as `.stats`."""
+    stats = None
+
+
+def conv_fwd(mod, x_bf16, Cin, *, residual=None, want_f32=True, want_bf16=False, out_f32=None, stats_for=None):
+    """stats_for: the GroupNorm that will consume the fp32 output — its statistics are then produced by this conv's
+    epilogue (when the geometry allows) instead of a separate pass over the tensor."""
     kind, R = mod.conv_kind()
     Cout = mod.out_channels
     mode = "up_fwd" if kind == 2 else "fwd"
-    return ops.conv_gemm(x_bf16, Cin, mod.packed(mode), kind=kind, R=R, Cout=Cout, bias=mod.bias, residual=residual,
-                         want_f32=want_f32, want_bf16=want_bf16, out_f32=out_f32)
+    spec = None
+    if stats_for is not None and want_f32 and out_f32 is None and stats_for.num_channels == Cout:
+        spec = (stats_for.num_groups, stats_for.eps)
+    r = ops.conv_gemm(x_bf16, Cin, mod.packed(mode), kind=kind, R=R, Cout=Cout, bias=mod.bias, residual=residual,
+                      want_f32=want_f32, want_bf16=want_bf16, out_f32=out_f32, stats=spec)
+    out = ConvOut(r[:2])
+    if spec is not None and r[2] is not None:
+        out.stats = (spec[0], spec[1], r[2])
+    return out
 
 
 def conv_bwd(mod, dy_bf16, x_bf16, Cin, *, dgrad=None, dgrad_residual=None, bias_grad_from=None):
@@ -249,12 +264,15 @@ def conv_bwd(mod, dy_bf16, x_bf16, Cin, *, dgrad=None, dgrad_residual=None, bias
     return of if dgrad == "f32" else ob
 
 
-def norm_act_fwd(norm, h_f32, act_code):
+def norm_act_fwd(norm, h_f32, act_code, stats=None):
     C = norm.num_channels
     gamma, beta = norm.affine_params()
-    stats = ops.gn_stats(h_f32, C, norm.num_groups, norm.eps)
-    a = ops.gn_act_fwd(h_f32, stats, gamma, beta, norm.num_groups, act_code)
-    return a, stats
+    if stats is not None and stats[0] == norm.num_groups and stats[1] == norm.eps:
+        st = stats[2]
+    else:
+        st = ops.gn_stats(h_f32, C, norm.num_groups, norm.eps)
+    a = ops.gn_act_fwd(h_f32, st, gamma, beta, norm.num_groups, act_code)
+    return a, st
 
 
 def norm_act_bwd(norm, h_f32, stats, da_bf16, gres_bf16, act_code):
@@ -361,18 +379,18 @@ class AttnBlock(nn.Module):
         self.proj_out = get_conv(in_channels, in_channels, dim=self.dim, kernel_size=1, stride=1, padding=0)
 
     # h: A with f32 stream. returns A (f32), saved
-    def fwd(self, h, save):
+    def fwd(self, h, save, next_norm=None):
         C = self.in_channels
         N, H, W, _ = h.f32.shape
-        hn, stats = norm_act_fwd(self.norm, h.f32, 0)
+        hn, stats = norm_act_fwd(self.norm, h.f32, 0, h.stats)
         qkv = torch.empty((N, H, W, 3 * C), dtype=torch.float32, device=h.f32.device)
         for i, m in enumerate((self.q, self.k, self.v)):
             conv_fwd(m, hn, C, out_f32=qkv[..., i * C:(i + 1) * C])
         o_bf16, o_f32, lse = ops.attn_fwd(qkv, C, self.n_heads, N, H * W)
         o4 = o_bf16.view(N, H, W, C)
-        out, _ = conv_fwd(self.proj_out, o4, C, residual=h.f32)
+        r = conv_fwd(self.proj_out, o4, C, residual=h.f32, stats_for=next_norm)
         saved = (h.f32, stats, hn, qkv, o4, o_f32, lse) if save else None
-        return A(f32=out, C=C), saved
+        return A(f32=r[0], C=C, stats=r.stats), saved
 
     def bwd(self, g, saved):
         h_f32, stats, hn, qkv, o4, o_f32, lse = saved
@@ -420,20 +438,21 @@ class ResNetBlock(nn.Module):
         if ch_in != ch_out:
             self.skip_conv = get_conv(ch_in, ch_out, dim=self.dim, kernel_size=1, padding=0)
 
-    def fwd(self, h, save, want_bf16=False):
+    def fwd(self, h, save, want_bf16=False, next_norm=None):
         act = self.net1[1].code
-        a1, st1 = norm_act_fwd(self.net1[0], h.f32, act)
-        h1, _ = conv_fwd(self.net1[2], a1, self.ch_in)
-        a2, st2 = norm_act_fwd(self.net2[0], h1, self.net2[1].code)
+        a1, st1 = norm_act_fwd(self.net1[0], h.f32, act, h.stats)
+        r1 = conv_fwd(self.net1[2], a1, self.ch_in, stats_for=self.net2[0])
+        h1 = r1[0]
+        a2, st2 = norm_act_fwd(self.net2[0], h1, self.net2[1].code, r1.stats)
         if self.ch_in != self.ch_out:
             xb = h.as_bf16()
             res, _ = conv_fwd(self.skip_conv, xb, self.ch_in)
         else:
             xb = None
             res = h.f32
-        out, outb = conv_fwd(self.net2[-1], a2, self.ch_out, residual=res, want_bf16=want_bf16)
+        r2 = conv_fwd(self.net2[-1], a2, self.ch_out, residual=res, want_bf16=want_bf16, stats_for=next_norm)
         saved = (h.f32, st1, a1, h1, st2, a2, xb) if save else None
-        return A(f32=out, bf16=outb, C=self.ch_out), saved
+        return A(f32=r2[0], bf16=r2[1], C=self.ch_out, stats=r2.stats), saved
 
     def bwd(self, g, saved):
         x_f32, st1, a1, h1, st2, a2, xb = saved
@@ -457,23 +476,25 @@ class ResNetDown(nn.Module):
         self.down = get_conv(self.resnet_blocks[-1].ch_out, self.resnet_blocks[-1].ch_out, dim=self.dim,
                              kernel_size=2, stride=2, padding=0)
 
-    def fwd(self, h, save, no_down=False, want_bf16=False):
+    def fwd(self, h, save, no_down=False, want_bf16=False, next_norm=None):
         saved = []
         nb = len(self.resnet_blocks)
         for i, blk in enumerate(self.resnet_blocks):
             last = i == nb - 1
             feeds_conv = last and self.attention_blocks is None and not no_down
-            h, s = blk.fwd(h, save, want_bf16=feeds_conv)
+            after = (self.resnet_blocks[i + 1].net1[0] if not last else (next_norm if no_down else None))
+            blk_next = self.attention_blocks[i].norm if self.attention_blocks is not None else after
+            h, s = blk.fwd(h, save, want_bf16=feeds_conv, next_norm=blk_next)
             saved.append(s)
             if self.attention_blocks is not None:
-                h, s = self.attention_blocks[i].fwd(h, save)
+                h, s = self.attention_blocks[i].fwd(h, save, next_norm=after)
                 saved.append(s)
         if no_down:
             return h, (saved, None)
         xb = h.as_bf16()
         C = self.down.in_channels
-        out, outb = conv_fwd(self.down, xb, C, want_bf16=want_bf16)
-        return A(f32=out, bf16=outb, C=self.down.out_channels), (saved, xb if save else None)
+        r = conv_fwd(self.down, xb, C, want_bf16=want_bf16, stats_for=next_norm)
+        return A(f32=r[0], bf16=r[1], C=self.down.out_channels, stats=r.stats), (saved, xb if save else None)
 
     def bwd(self, g, saved):
         blocks, xb = saved
@@ -499,22 +520,24 @@ class ResNetUp(nn.Module):
         self.up = get_conv(self.resnet_blocks[-1].ch_out, self.ch_out, dim=self.dim, kernel_size=2, stride=2,
                            padding=0, transposed=True)
 
-    def fwd(self, h, save, no_up=False):
+    def fwd(self, h, save, no_up=False, next_norm=None):
         saved = []
         nb = len(self.resnet_blocks)
         for i, blk in enumerate(self.resnet_blocks):
             last = i == nb - 1
             feeds_conv = last and self.attention_blocks is None and not no_up
-            h, s = blk.fwd(h, save, want_bf16=feeds_conv)
+            after = (self.resnet_blocks[i + 1].net1[0] if not last else (next_norm if no_up else None))
+            blk_next = self.attention_blocks[i].norm if self.attention_blocks is not None else after
+            h, s = blk.fwd(h, save, want_bf16=feeds_conv, next_norm=blk_next)
             saved.append(s)
             if self.attention_blocks is not None:
-                h, s = self.attention_blocks[i].fwd(h, save)
+                h, s = self.attention_blocks[i].fwd(h, save, next_norm=after)
                 saved.append(s)
         if no_up:
             return h, (saved, None)
         xb = h.as_bf16()
-        out, _ = conv_fwd(self.up, xb, self.up.in_channels)
-        return A(f32=out, C=self.ch_out), (saved, xb if save else None)
+        r = conv_fwd(self.up, xb, self.up.in_channels, stats_for=next_norm)
+        return A(f32=r[0], C=self.ch_out, stats=r.stats), (saved, xb if save else None)
 
     def bwd(self, g, saved):
         blocks, xb = saved
@@ -607,22 +630,23 @@ class Encoder(nn.Module):
     # ---- engine program: x_bf16 NHWC -> A(conv_out output); `tail_bf16` asks for a bf16 copy (feeds quant_conv)
     def fwd(self, x_bf16, save, tail_bf16=False):
         saved = {}
-        h32, _ = conv_fwd(self.conv_in, x_bf16, self.in_channels)
+        r = conv_fwd(self.conv_in, x_bf16, self.in_channels, stats_for=self.downs[0].resnet_blocks[0].net1[0])
         saved["x"] = x_bf16 if save else None
-        h = A(f32=h32, C=self.chs[0])
+        h = A(f32=r[0], C=self.chs[0], stats=r.stats)
         levels = []
         n = len(self.downs)
         for i, down in enumerate(self.downs):
             last = i == n - 1
             nxt_skip = (not last) and (self.chs[i] != self.chs[i + 1])
-            h, s = down.fwd(h, save, no_down=last, want_bf16=nxt_skip)
+            nxt_norm = self.mid1.net1[0] if last else self.downs[i + 1].resnet_blocks[0].net1[0]
+            h, s = down.fwd(h, save, no_down=last, want_bf16=nxt_skip, next_norm=nxt_norm)
             levels.append(s)
         saved["levels"] = levels
-        h, saved["mid1"] = self.mid1.fwd(h, save)
+        h, saved["mid1"] = self.mid1.fwd(h, save, next_norm=(self.mid_attn1.norm if self.mid_attn else self.mid2.net1[0]))
         if self.mid_attn:
-            h, saved["attn"] = self.mid_attn1.fwd(h, save)
-        h, saved["mid2"] = self.mid2.fwd(h, save)
-        a, st = norm_act_fwd(self.norm_out, h.f32, self.act_out.code)
+            h, saved["attn"] = self.mid_attn1.fwd(h, save, next_norm=self.mid2.net1[0])
+        h, saved["mid2"] = self.mid2.fwd(h, save, next_norm=self.norm_out)
+        a, st = norm_act_fwd(self.norm_out, h.f32, self.act_out.code, h.stats)
         saved["out"] = (h.f32, st, a) if save else None
         Cz = self.conv_out.out_channels
         of, ob = conv_fwd(self.conv_out, a, self.norm_out.num_channels, want_f32=not tail_bf16, want_bf16=tail_bf16)
@@ -684,19 +708,21 @@ class Decoder(nn.Module):
     def fwd(self, z_bf16, save):
         self.last_z_shape = (z_bf16.shape[0], self.z_channels, z_bf16.shape[1], z_bf16.shape[2])
         saved = {}
-        h32, _ = conv_fwd(self.conv_in, z_bf16, self.z_channels)
+        r = conv_fwd(self.conv_in, z_bf16, self.z_channels, stats_for=self.mid1.net1[0])
         saved["z"] = z_bf16 if save else None
-        h = A(f32=h32, C=self.chs[-1])
-        h, saved["mid1"] = self.mid1.fwd(h, save)
+        h = A(f32=r[0], C=self.chs[-1], stats=r.stats)
+        h, saved["mid1"] = self.mid1.fwd(h, save, next_norm=(self.mid_attn1.norm if self.mid_attn else self.mid2.net1[0]))
         if self.mid_attn:
-            h, saved["attn"] = self.mid_attn1.fwd(h, save)
-        h, saved["mid2"] = self.mid2.fwd(h, save)
+            h, saved["attn"] = self.mid_attn1.fwd(h, save, next_norm=self.mid2.net1[0])
+        h, saved["mid2"] = self.mid2.fwd(h, save, next_norm=self.ups[0].resnet_blocks[0].net1[0])
         levels = []
         for i, up in enumerate(self.ups):
-            h, s = up.fwd(h, save, no_up=(i == self.n_sizes - 1))
+            last = i == self.n_sizes - 1
+            nxt_norm = self.norm_out if last else self.ups[i + 1].resnet_blocks[0].net1[0]
+            h, s = up.fwd(h, save, no_up=last, next_norm=nxt_norm)
             levels.append(s)
         saved["levels"] = levels
-        a, st = norm_act_fwd(self.norm_out, h.f32, self.act_out.code)
+        a, st = norm_act_fwd(self.norm_out, h.f32, self.act_out.code, h.stats)
         saved["out"] = (h.f32, st, a) if save else None
         of, _ = conv_fwd(self.conv_out, a, self.norm_out.num_channels)
         return A(f32=of, C=self.in_channels), (saved if save else None)

@@ -47,8 +47,9 @@ class L2PredictionHead(nn.Module):
         saved = []
         for i in range(0, len(mods) - 1, 3):
             conv, norm, act = mods[i], mods[i + 1], mods[i + 2]
-            f32, _ = conv_fwd(conv, h, cin)
-            a, st = norm_act_fwd(norm, f32, act.code)
+            r = conv_fwd(conv, h, cin, stats_for=norm)
+            f32 = r[0]
+            a, st = norm_act_fwd(norm, f32, act.code, r.stats)
             saved.append((h, f32, st))
             h, cin = a, conv.out_channels
         pred, _ = conv_fwd(mods[-1], h, cin)

@@ -33,7 +33,7 @@ KERNEL_LAUNCHES = [0]   # kernels of libtvae_b200.so enqueued through this modul
 _KERNELS_PER_CALL = {
     "tvae_pack_weight": 1, "tvae_conv_gemm": 1, "tvae_wgrad_gemm": 2, "tvae_nchw_f32_to_nhwc_bf16": 1,
     "tvae_nhwc_f32_to_nchw_f32": 1, "tvae_nhwc_bf16_to_nchw_f32": 1, "tvae_f32_to_bf16": 1, "tvae_gn_stats": 1,
-    "tvae_gn_act_fwd": 1, "tvae_gn_act_bwd": 3, "tvae_colsum_bf16": 2, "tvae_attn_fwd": 1, "tvae_attn_bwd": 2,
+    "tvae_gn_act_fwd": 1, "tvae_gn_stats_finalize": 1, "tvae_gn_act_bwd": 3, "tvae_colsum_bf16": 2, "tvae_attn_fwd": 1, "tvae_attn_bwd": 2,
     "tvae_reparam_fwd": 1, "tvae_reparam_bwd": 1, "tvae_nll_fwd": 2, "tvae_vae_loss_finalize": 1,
     "tvae_l2head_loss_fwd": 1, "tvae_l2head_loss_bwd": 1, "tvae_l2head_finalize": 1, "tvae_sumsq": 2, "tvae_adamw": 1,
 }
@@ -108,9 +108,22 @@ def pack_weight(w, mode, out=None):
 
 
 # ----------------------------------------------------------------------------------------------- conv GEMM
+def fused_stats_ok(N, oH, oW, Cout, G, kind, H, W):
+    """Can the conv epilogue produce the GroupNorm statistics of its output? (see tvae_conv_args.stats_part)"""
+    if G <= 0 or Cout % G:
+        return False
+    gs = Cout // G
+    bn = Cout if Cout <= 256 else 256
+    grid = H * W if kind == 2 else oH * oW          # the GEMM's pixel grid
+    return gs % 16 == 0 and Cout % 16 == 0 and (Cout <= 256 or Cout % 256 == 0) and bn % gs == 0 \
+        and bn // gs <= 16 and grid % 128 == 0
+
+
 def conv_gemm(x, C_in, wp, *, kind, R, Cout, flip=False, bias=None, residual=None, want_f32=True, want_bf16=False,
-              bf16_pitch=None, bn=0, out_f32=None, out_bf16=None):
-    """x: bf16 [N,H,W,pitch]. Returns (out_f32 or None, out_bf16 or None) as NHWC tensors."""
+              bf16_pitch=None, bn=0, out_f32=None, out_bf16=None, stats=None):
+    """x: bf16 [N,H,W,pitch]. Returns (out_f32 or None, out_bf16 or None) as NHWC tensors; with stats=(G, eps) the
+    GroupNorm statistics [N, G, 2] of the output are produced by the epilogue and returned as a third value
+    (None when the geometry does not allow it)."""
     N, H, W, _ = x.shape
     pitch = pitch_of(x)
     if kind == 1:
@@ -135,6 +148,13 @@ def conv_gemm(x, C_in, wp, *, kind, R, Cout, flip=False, bias=None, residual=Non
     a.out_f32 = _ptr(out_f32); a.out_f32_pitch = pitch_of(out_f32) if out_f32 is not None else 0
     a.out_bf16 = _ptr(out_bf16); a.out_bf16_pitch = pitch_of(out_bf16) if out_bf16 is not None else 0
     a.bn = bn
+    part = None
+    if stats is not None and fused_stats_ok(N, oH, oW, Cout, stats[0], kind, H, W):
+        grid_px = (H * W) if kind == 2 else (oH * oW)
+        spi = grid_px // 128 * (4 if kind == 2 else 1)
+        part = torch.empty((N * spi, stats[0], 2), dtype=torch.float32, device=dev)
+        a.stats_part = part.data_ptr()
+        a.stats_groups = stats[0]
     prof = PROFILE.get("conv")
     if prof is not None and prof["match"](N * oH * oW if kind != 2 else N * H * W, Cout, C_in, kind, R):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -144,7 +164,14 @@ def conv_gemm(x, C_in, wp, *, kind, R, Cout, flip=False, bias=None, residual=Non
         prof["events"].append((e0, e1))
     else:
         check(lib.tvae_conv_gemm(C.byref(a), _stream()), "tvae_conv_gemm")
-    return out_f32, out_bf16
+    if stats is None:
+        return out_f32, out_bf16
+    st = None
+    if part is not None:
+        st = torch.empty((N, stats[0], 2), dtype=torch.float32, device=dev)
+        check(lib.tvae_gn_stats_finalize(part.data_ptr(), spi, N, stats[0], float(oH * oW * (Cout // stats[0])),
+                                         float(stats[1]), st.data_ptr(), _stream()), "tvae_gn_stats_finalize")
+    return out_f32, out_bf16, st
 
 
 _wgrad_ws = {}

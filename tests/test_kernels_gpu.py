@@ -368,3 +368,35 @@ def test_adamw_and_clip():
         torch.cuda.synchronize()
         assert abs(ss.item() - grad.double().pow(2).sum().item()) / ss.item() < 1e-7
         assert torch.allclose(p, p_ref.detach(), rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout,kind", [(2, 64, 64, 128, 512, 0), (3, 16, 16, 64, 128, 0), (2, 32, 32, 256, 256, 1),
+                                                 (2, 16, 16, 128, 256, 2), (2, 8, 8, 64, 128, 0)])
+def test_conv_fused_groupnorm_stats(N, H, W, Cin, Cout, kind):
+    """The conv epilogue's (mean, rstd) of its own output == a separate statistics pass over that output."""
+    o = ops()
+    g = torch.Generator(device="cuda").manual_seed(13)
+    x = bf16_round(torch.randn((N, Cin, H, W), device="cuda", generator=g))
+    b = torch.randn((Cout,), device="cuda", generator=g)
+    G, eps = 8, 1e-6
+    if kind == 2:
+        w = bf16_round(torch.randn((Cin, Cout, 2, 2), device="cuda", generator=g) / math.sqrt(Cin))
+        wp, R, oH, oW = o.pack_weight(w, "up_fwd"), 2, 2 * H, 2 * W
+    elif kind == 1:
+        w = bf16_round(torch.randn((Cout, Cin, 2, 2), device="cuda", generator=g) / math.sqrt(4 * Cin))
+        wp, R, oH, oW = o.pack_weight(w, "fwd"), 2, H // 2, W // 2
+    else:
+        w = bf16_round(torch.randn((Cout, Cin, 3, 3), device="cuda", generator=g) / math.sqrt(9 * Cin))
+        wp, R, oH, oW = o.pack_weight(w, "fwd"), 3, H, W
+    res = torch.randn((N, oH, oW, Cout), device="cuda", generator=g)
+    of, _, st = o.conv_gemm(nhwc_bf16(x, o.round_up(Cin, 8)), Cin, wp, kind=kind, R=R, Cout=Cout, bias=b, residual=res,
+                            stats=(G, eps))
+    torch.cuda.synchronize()
+    if oH * oW < 128 and kind != 2 or (kind == 2 and H * W < 128):
+        assert st is None          # images smaller than one 128-pixel tile: the caller falls back to gn_stats
+        return
+    assert st is not None
+    ref = o.gn_stats(of, Cout, G, eps)
+    torch.cuda.synchronize()
+    assert torch.allclose(st[..., 0], ref[..., 0], atol=1e-5, rtol=1e-5)
+    assert torch.allclose(st[..., 1], ref[..., 1], rtol=1e-5)
