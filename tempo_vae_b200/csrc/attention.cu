@@ -15,31 +15,14 @@ namespace {
 constexpr int ROWS = 64;  // tokens per block (x heads threads)
 
 // ---------------------------------------------------------------------------------------------- forward
-// Shared-memory row layout: per token `heads` blocks of HD contiguous floats (head-major, de-interleaved while
-// staging) padded by 4 floats, so a thread reads its head's vector with 128-bit loads and the `heads` distinct
-// addresses of a warp fall into different banks.
-template <int HD>
-__device__ __forceinline__ void stage_rows(float* __restrict__ dst, const float* __restrict__ src, int pitch, int rows,
-                                           int heads, long long row0) {
-  constexpr int PH = HD + 4;
-  const int C = HD * heads;
-  for (int i = threadIdx.x; i < rows * C; i += blockDim.x) {
-    const int r = i / C, c = i - r * C;
-    const int d = c / heads, h = c - d * heads;
-    dst[r * heads * PH + h * PH + d] = src[(row0 + r) * pitch + c];
-  }
-}
-
 template <int HD>
 __global__ void attn_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
                                 int pitch, int T, int heads, int KT, float scale, __nv_bfloat16* __restrict__ out_bf16,
                                 float* __restrict__ out_f32, float* __restrict__ lse) {
   extern __shared__ float sm[];
-  constexpr int PH = HD + 4;
   const int C = HD * heads;
-  const int RP = heads * PH;
-  float* sK = sm;                   // [KT][RP]
-  float* sV = sm + (size_t)KT * RP; // [KT][RP]
+  float* sK = sm;                  // [KT][C]
+  float* sV = sm + (size_t)KT * C; // [KT][C]
   const int b = blockIdx.y;
   const int h = threadIdx.x % heads;
   const int tq = blockIdx.x * ROWS + threadIdx.x / heads;
@@ -57,30 +40,25 @@ __global__ void attn_fwd_kernel(const float* __restrict__ q, const float* __rest
   for (int k0 = 0; k0 < T; k0 += KT) {
     const int kt = min(KT, T - k0);
     __syncthreads();
-    stage_rows<HD>(sK, k, pitch, kt, heads, (long long)b * T + k0);
-    stage_rows<HD>(sV, v, pitch, kt, heads, (long long)b * T + k0);
+    for (int i = threadIdx.x; i < kt * C; i += blockDim.x) {
+      const int r = i / C, c = i - r * C;
+      const long long row = (long long)b * T + k0 + r;
+      sK[i] = k[row * pitch + c];
+      sV[i] = v[row * pitch + c];
+    }
     __syncthreads();
     for (int r = 0; r < kt; ++r) {
-      const float4* kr = reinterpret_cast<const float4*>(sK + r * RP + h * PH);
+      const float* kr = sK + r * C + h;
       float s = 0.f;
 #pragma unroll
-      for (int d = 0; d < HD / 4; ++d) {
-        const float4 kk = kr[d];
-        s += qr[4 * d] * kk.x + qr[4 * d + 1] * kk.y + qr[4 * d + 2] * kk.z + qr[4 * d + 3] * kk.w;
-      }
+      for (int d = 0; d < HD; ++d) s += qr[d] * kr[d * heads];
       const float mn = fmaxf(m, s);
       const float corr = __expf(m - mn);
       const float p = __expf(s - mn);
       l = l * corr + p;
-      const float4* vr = reinterpret_cast<const float4*>(sV + r * RP + h * PH);
+      const float* vr = sV + r * C + h;
 #pragma unroll
-      for (int d = 0; d < HD / 4; ++d) {
-        const float4 vv = vr[d];
-        o[4 * d] = o[4 * d] * corr + p * vv.x;
-        o[4 * d + 1] = o[4 * d + 1] * corr + p * vv.y;
-        o[4 * d + 2] = o[4 * d + 2] * corr + p * vv.z;
-        o[4 * d + 3] = o[4 * d + 3] * corr + p * vv.w;
-      }
+      for (int d = 0; d < HD; ++d) o[d] = o[d] * corr + p * vr[d * heads];
       m = mn;
     }
   }
@@ -104,11 +82,9 @@ __global__ void attn_bwd_dq_kernel(const float* __restrict__ q, const float* __r
                                    const float* __restrict__ dout, const float* __restrict__ lse, int T, int heads,
                                    int KT, float scale, __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dsum) {
   extern __shared__ float sm[];
-  constexpr int PH = HD + 4;
   const int C = HD * heads;
-  const int RP = heads * PH;
   float* sK = sm;
-  float* sV = sm + (size_t)KT * RP;
+  float* sV = sm + (size_t)KT * C;
   const int b = blockIdx.y;
   const int h = threadIdx.x % heads;
   const int tq = blockIdx.x * ROWS + threadIdx.x / heads;
@@ -130,26 +106,26 @@ __global__ void attn_bwd_dq_kernel(const float* __restrict__ q, const float* __r
   for (int k0 = 0; k0 < T; k0 += KT) {
     const int kt = min(KT, T - k0);
     __syncthreads();
-    stage_rows<HD>(sK, k, pitch, kt, heads, (long long)b * T + k0);
-    stage_rows<HD>(sV, v, pitch, kt, heads, (long long)b * T + k0);
+    for (int i = threadIdx.x; i < kt * C; i += blockDim.x) {
+      const int r = i / C, c = i - r * C;
+      const long long row = (long long)b * T + k0 + r;
+      sK[i] = k[row * pitch + c];
+      sV[i] = v[row * pitch + c];
+    }
     __syncthreads();
     for (int r = 0; r < kt; ++r) {
-      const float4* kr = reinterpret_cast<const float4*>(sK + r * RP + h * PH);
-      const float4* vr = reinterpret_cast<const float4*>(sV + r * RP + h * PH);
+      const float* kr = sK + r * C + h;
+      const float* vr = sV + r * C + h;
       float s = 0.f, dp = 0.f;
 #pragma unroll
-      for (int d = 0; d < HD / 4; ++d) {
-        const float4 kk = kr[d], vv = vr[d];
-        s += qr[4 * d] * kk.x + qr[4 * d + 1] * kk.y + qr[4 * d + 2] * kk.z + qr[4 * d + 3] * kk.w;
-        dp += dor[4 * d] * vv.x + dor[4 * d + 1] * vv.y + dor[4 * d + 2] * vv.z + dor[4 * d + 3] * vv.w;
+      for (int d = 0; d < HD; ++d) {
+        s += qr[d] * kr[d * heads];
+        dp += dor[d] * vr[d * heads];
       }
       const float p = __expf(s - L);
       const float ds = p * (dp - D);
 #pragma unroll
-      for (int d = 0; d < HD / 4; ++d) {
-        const float4 kk = kr[d];
-        dq[4 * d] += ds * kk.x; dq[4 * d + 1] += ds * kk.y; dq[4 * d + 2] += ds * kk.z; dq[4 * d + 3] += ds * kk.w;
-      }
+      for (int d = 0; d < HD; ++d) dq[d] += ds * kr[d * heads];
     }
   }
   if (active) {
@@ -166,12 +142,10 @@ __global__ void attn_bwd_dkv_kernel(const float* __restrict__ q, const float* __
                                     const float* __restrict__ lse, const float* __restrict__ dsum, int T, int heads,
                                     int QT, float scale, __nv_bfloat16* __restrict__ dqkv) {
   extern __shared__ float sm[];
-  constexpr int PH = HD + 4;
   const int C = HD * heads;
-  const int RP = heads * PH;
-  float* sQ = sm;                        // [QT][RP]
-  float* sDO = sm + (size_t)QT * RP;     // [QT][RP]
-  float* sL = sDO + (size_t)QT * RP;     // [QT][heads]
+  float* sQ = sm;                        // [QT][C]
+  float* sDO = sm + (size_t)QT * C;      // [QT][C]
+  float* sL = sDO + (size_t)QT * C;      // [QT][heads]
   float* sD = sL + (size_t)QT * heads;   // [QT][heads]
   const int b = blockIdx.y;
   const int h = threadIdx.x % heads;
@@ -190,8 +164,12 @@ __global__ void attn_bwd_dkv_kernel(const float* __restrict__ q, const float* __
   for (int q0 = 0; q0 < T; q0 += QT) {
     const int qt = min(QT, T - q0);
     __syncthreads();
-    stage_rows<HD>(sQ, q, pitch, qt, heads, (long long)b * T + q0);
-    stage_rows<HD>(sDO, dout, C, qt, heads, (long long)b * T + q0);
+    for (int i = threadIdx.x; i < qt * C; i += blockDim.x) {
+      const int r = i / C, c = i - r * C;
+      const long long row = (long long)b * T + q0 + r;
+      sQ[i] = q[row * pitch + c];
+      sDO[i] = dout[row * C + c];
+    }
     for (int i = threadIdx.x; i < qt * heads; i += blockDim.x) {
       const int r = i / heads, hh = i - r * heads;
       sL[i] = lse[((long long)b * heads + hh) * T + q0 + r];
@@ -199,22 +177,20 @@ __global__ void attn_bwd_dkv_kernel(const float* __restrict__ q, const float* __
     }
     __syncthreads();
     for (int r = 0; r < qt; ++r) {
-      const float4* qr = reinterpret_cast<const float4*>(sQ + r * RP + h * PH);
-      const float4* dor = reinterpret_cast<const float4*>(sDO + r * RP + h * PH);
+      const float* qr = sQ + r * C + h;
+      const float* dor = sDO + r * C + h;
       float s = 0.f, dp = 0.f;
 #pragma unroll
-      for (int d = 0; d < HD / 4; ++d) {
-        const float4 qq = qr[d], dd = dor[d];
-        s += qq.x * kr[4 * d] + qq.y * kr[4 * d + 1] + qq.z * kr[4 * d + 2] + qq.w * kr[4 * d + 3];
-        dp += dd.x * vr[4 * d] + dd.y * vr[4 * d + 1] + dd.z * vr[4 * d + 2] + dd.w * vr[4 * d + 3];
+      for (int d = 0; d < HD; ++d) {
+        s += qr[d * heads] * kr[d];
+        dp += dor[d * heads] * vr[d];
       }
       const float p = __expf(s * scale - sL[r * heads + h]);
       const float ds = p * (dp - sD[r * heads + h]);
 #pragma unroll
-      for (int d = 0; d < HD / 4; ++d) {
-        const float4 qq = qr[d], dd = dor[d];
-        dv[4 * d] += p * dd.x; dv[4 * d + 1] += p * dd.y; dv[4 * d + 2] += p * dd.z; dv[4 * d + 3] += p * dd.w;
-        dk[4 * d] += ds * qq.x; dk[4 * d + 1] += ds * qq.y; dk[4 * d + 2] += ds * qq.z; dk[4 * d + 3] += ds * qq.w;
+      for (int d = 0; d < HD; ++d) {
+        dv[d] += p * dor[d * heads];
+        dk[d] += ds * qr[d * heads];
       }
     }
   }
@@ -229,7 +205,7 @@ __global__ void attn_bwd_dkv_kernel(const float* __restrict__ q, const float* __
 }
 
 int tile_rows(int C, int arrays) {
-  // rows of C (padded) floats per staged array so that `arrays` of them fit in ~64 KB
+  // rows of C floats per staged array so that `arrays` of them fit in ~64 KB
   int r = (64 * 1024) / (arrays * C * 4);
   int t = 1;
   while (t * 2 <= r && t < 64) t *= 2;
@@ -259,9 +235,8 @@ extern "C" int32_t tvae_attn_fwd(const float* q, const float* k, const float* v,
   TVAE_CHECK(heads > 0 && C % heads == 0 && ROWS * heads <= 1024, "tvae_attn_fwd: bad heads");
   const int hd = C / heads;
   const float scale = 1.0f / sqrtf((float)hd);
-  const int RP = heads * (hd + 4);
-  const int KT = tile_rows(RP, 2);
-  const size_t smem = (size_t)2 * KT * RP * sizeof(float);
+  const int KT = tile_rows(C, 2);
+  const size_t smem = (size_t)2 * KT * C * sizeof(float);
   dim3 grid((T + ROWS - 1) / ROWS, B);
   const int threads = ROWS * heads;
   TVAE_HD_DISPATCH(hd, {
@@ -284,10 +259,9 @@ extern "C" int32_t tvae_attn_bwd(const float* q, const float* k, const float* v,
   dim3 grid((T + ROWS - 1) / ROWS, B);
   const int threads = ROWS * heads;
   __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(dqkv_bf16);
-  const int RP = heads * (hd + 4);
   {
-    const int KT = tile_rows(RP, 2);
-    const size_t smem = (size_t)2 * KT * RP * sizeof(float);
+    const int KT = tile_rows(C, 2);
+    const size_t smem = (size_t)2 * KT * C * sizeof(float);
     TVAE_HD_DISPATCH(hd, {
       TVAE_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       attn_bwd_dq_kernel<HD><<<grid, threads, smem, stream>>>(q, k, v, pitch, o, d_out, lse, T, heads, KT, scale, dp,
@@ -296,8 +270,8 @@ extern "C" int32_t tvae_attn_bwd(const float* q, const float* k, const float* v,
     TVAE_CUDA(cudaGetLastError());
   }
   {
-    const int QT = tile_rows(RP, 2);
-    const size_t smem = ((size_t)2 * QT * RP + (size_t)2 * QT * heads) * sizeof(float);
+    const int QT = tile_rows(C, 2);
+    const size_t smem = ((size_t)2 * QT * C + (size_t)2 * QT * heads) * sizeof(float);
     TVAE_HD_DISPATCH(hd, {
       TVAE_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       attn_bwd_dkv_kernel<HD><<<grid, threads, smem, stream>>>(q, k, v, pitch, d_out, lse, workspace, T, heads, QT,
