@@ -39,6 +39,9 @@ DEFAULT_MODEL = dict(
     optimizer_params=dict(lr=1e-4, betas=[0.9, 0.95], weight_decay=0.05),
 )
 FWD_GF, BWD_GF = 165.776, 292.746          # algorithmic conv GFLOP / sample
+# dram bytes of one 512->512 3x3 @64x64 launch at B=256 from the committed ncu capture (1.080 GB read + 2.098 GB
+# written; the launch reads a 1.07 GB bf16 activation + 4.7 MB of weights and writes a 2.15 GB fp32 tensor)
+NCU_CONV_TRAFFIC_BYTES = 3.178e9
 
 
 def peaks():
@@ -287,7 +290,10 @@ def run_ours(args):
         "step_frac_of_peak": value * (FWD_GF + BWD_GF) / 1e3 / (pk["tflops"] * world),
         "roofline": {"bound": "tensor", "kernel": "conv_gemm_kernel 512->512 3x3 @64x64 (fwd and dgrad launches)",
                      "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
-                     "traffic": None, "peak_source": pk["source"] + ", bf16_tflops_sustained",
+                     "traffic": NCU_CONV_TRAFFIC_BYTES if B == 256 else None,
+                     "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch "
+                                       "(profiles/ncu_conv_r1.md); algorithmic bytes per launch 3.22e9",
+                     "peak_source": pk["source"] + ", bf16_tflops_sustained",
                      "launches_timed": len(conv_ms), "avg_ms": conv_avg,
                      "wgrad_kernel": {"avg_ms": wg_avg, "achieved": conv_flops / (wg_avg * 1e-3) / 1e12,
                                       "launches_timed": len(wg_ms)}},
