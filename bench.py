@@ -319,6 +319,86 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_extra(args):
+    """Secondary workloads (parity-test configs of BASELINE.json measured for reference, not the headline)."""
+    import torch
+    import torch.distributed as dist
+    import tempo_vae_b200 as t
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    t.seed_all(42)
+    model = t.get_model(DEFAULT_MODEL, dev)
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if args.workload == "train_l2":
+        l2 = t.VAEWithL2Supervision(model.vae, latent_channels=32, mlp_hidden=[512, 512]).to(dev)
+        opt = t.FusedAdamW(l2.parameters(), lr=1e-4, betas=(0.9, 0.95), weight_decay=0.05)
+        trainer = t.L2SupervisedTrainer(l2, opt, dev, tempfile.mkdtemp(prefix="tvae_bench_"), kl_weight=1e-6,
+                                        l2_weights={"NO2": 0.1, "O3TOT": 0.1, "HCHO": 0.1, "CLDO4": 0.1})
+        trainer.step = 1
+        g = torch.Generator(device=dev).manual_seed(rank)
+        batch = {"spectral": synthetic_batch(torch, B, (1028, 64, 64), dev, seed=rank)}
+        for p in ("NO2", "O3TOT", "HCHO", "CLDO4"):
+            tg = torch.randn((B, 64, 64), device=dev, generator=g)
+            blob = torch.nn.functional.interpolate(torch.rand((B, 1, 8, 8), device=dev, generator=g), size=(64, 64))[:, 0]
+            tg[blob < 0.15] = float("nan")            # ~15 % invalid pixels in contiguous blobs (SURVEY.md §8d)
+            batch[p] = tg
+        for _ in range(args.warmup):
+            trainer.train_step_device(batch)
+        sync(); e0.record()
+        for _ in range(args.steps):
+            m = trainer.train_step_device(batch)
+        e1.record(); sync()
+        ms = e0.elapsed_time(e1) / args.steps
+        out = {"workload": "VAEWithL2Supervision train step (config 3), default model + 282,628-parameter L2 head",
+               "metric": "train samples/sec (fwd+bwd+AdamW)", "value": world * B / ms * 1e3, "unit": "samples/s",
+               "ms_per_step": ms, "n_gpus": world, "batch_per_gpu": B,
+               "final_metrics": {k: float(v.detach()) for k, v in m.items()}}
+    else:
+        # synthetic granules [131, 2048, 1028] -> normalise -> crop [128, 2048] -> 64 patches of [1028, 64, 64] each
+        n_gran = 4
+        g = torch.Generator(device=dev).manual_seed(100 + rank)
+        mean_s = torch.full((1028,), 3.0, device=dev)
+        std_s = torch.full((1028,), 0.5, device=dev)
+        patches = []
+        for _ in range(n_gran):
+            rad = torch.exp(torch.randn((131, 2048, 1028), device=dev, generator=g) * 0.5 + 3.0)
+            patches.append(t.granule_to_patches(t.normalize_radiance(rad, mean_s, std_s)))
+            del rad
+        patches = torch.cat(patches)                    # [256, 1028, 64, 64] per rank
+        for _ in range(args.warmup):
+            t.encode_patches(model, patches, batch_size=B)
+        sync(); e0.record()
+        for _ in range(args.steps):
+            lat = t.encode_patches(model, patches, batch_size=B)
+        e1.record(); sync()
+        ms = e0.elapsed_time(e1) / args.steps
+        n = patches.shape[0]
+        out = {"workload": "encode-only patch sweep (config 5): posterior means of 64x64 patches of synthetic granules",
+               "metric": "encoded patches/sec", "value": world * n / ms * 1e3, "unit": "patches/s", "ms_per_sweep": ms,
+               "patches_per_gpu": n, "n_gpus": world, "latent_shape": list(lat.shape[1:]),
+               "encoder_tflops": world * n / ms * 1e3 * 84.248 / 1e3}
+    if world > 1:
+        tns = torch.tensor([out["value"]], device=dev, dtype=torch.float64)
+        dist.all_reduce(tns, op=dist.ReduceOp.MIN)
+        out["value"] = float(tns.item())
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -328,11 +408,17 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="samples per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: skip the host-fed leg")
+    ap.add_argument("--workload", default="train", choices=["train", "train_l2", "encode"],
+                    help="train = headline (BASELINE config 2/4); train_l2 = L2-supervised variant (config 3); "
+                         "encode = inference-only patch sweep of synthetic granules (config 5). The extra workloads "
+                         "print their own JSON line and are not the headline metric.")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
-    else:
+    elif args.workload == "train":
         run_ours(args)
+    else:
+        run_extra(args)
 
 
 if __name__ == "__main__":

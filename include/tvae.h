@@ -60,6 +60,13 @@ typedef struct {
    * 128 output pixels; tvae_gn_stats_finalize turns the partials into (mean, rstd). NULL = off. */
   float* stats_part;
   int32_t stats_groups;
+  /* "fp32 mode" (split-bf16 emulation, ~2^-16 relative product error, 3x the tensor work): low-order halves of the
+   * operands, value = hi + lo with hi = bf16(value), lo = bf16(value - hi). Same layouts/pitches as x and w. The
+   * kernel accumulates x*w + x*w_lo + x_lo*w in fp32. Both NULL = plain bf16. out_bf16_lo (optional, pitch of
+   * out_bf16) receives the low-order half of the bf16 output for a split-bf16 consumer. */
+  const void* x_lo;
+  const void* w_lo;
+  void* out_bf16_lo;
 } tvae_conv_args;
 int32_t tvae_conv_gemm(const tvae_conv_args* args, tvae_stream_t stream);
 
@@ -87,20 +94,22 @@ int64_t tvae_wgrad_workspace_bytes(int32_t Cm, int32_t Cn, int32_t ntaps, int32_
 int32_t tvae_wgrad_splits(int32_t Cm, int32_t Cn, int32_t ntaps, int64_t pixels);
 
 /* out[(tr*Crow + cr)][tk*c_pad + c] = bf16(w[cr*s_row + c*s_col + (tr+tk)*s_tap]), zero for c in [C, c_pad).
- * One of TR, TK is 1. Row pitch of `out` is TK*c_pad. */
+ * One of TR, TK is 1. Row pitch of `out` is TK*c_pad. out_lo (optional, same layout) = bf16(w - out): the low-order
+ * half for the split-bf16 "fp32 mode" (every *_lo argument below has the same meaning; NULL = not produced). */
 int32_t tvae_pack_weight(const float* w, void* out_bf16, int32_t Crow, int32_t TR, int32_t TK, int32_t C,
-                         int32_t c_pad, int64_t s_row, int64_t s_col, int64_t s_tap, tvae_stream_t stream);
+                         int32_t c_pad, int64_t s_row, int64_t s_col, int64_t s_tap, void* out_lo,
+                         tvae_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Layout conversion at the API boundary (the reference's tensors are NCHW fp32; src/train_utils.py:154).
  */
 int32_t tvae_nchw_f32_to_nhwc_bf16(const float* x, void* out_bf16, int32_t N, int32_t C, int32_t HW,
-                                   int32_t out_pitch, tvae_stream_t stream);
+                                   int32_t out_pitch, void* out_lo, tvae_stream_t stream);
 int32_t tvae_nhwc_f32_to_nchw_f32(const float* x, float* out, int32_t N, int32_t C, int32_t HW, int32_t in_pitch,
                                   tvae_stream_t stream);
 int32_t tvae_nhwc_bf16_to_nchw_f32(const void* x_bf16, float* out, int32_t N, int32_t C, int32_t HW,
                                    int32_t in_pitch, tvae_stream_t stream);
-int32_t tvae_f32_to_bf16(const float* x, void* out_bf16, int64_t n, tvae_stream_t stream);
+int32_t tvae_f32_to_bf16(const float* x, void* out_bf16, int64_t n, void* out_lo, tvae_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * GroupNorm (+ exact-erf GELU). Replaces nn.GroupNorm + nn.GELU (src/model.py:105,179,202,333-339,400,542;
@@ -114,7 +123,8 @@ int32_t tvae_gn_stats(const float* x, int32_t N, int32_t HW, int32_t C, int32_t 
 int32_t tvae_gn_stats_finalize(const float* stats_part, int32_t slots_per_image, int32_t N, int32_t G, double count,
                                float eps, float* stats, tvae_stream_t stream);
 int32_t tvae_gn_act_fwd(const float* x, const float* stats, const float* gamma, const float* beta, int32_t N,
-                        int32_t HW, int32_t C, int32_t G, int32_t act, void* out_bf16, tvae_stream_t stream);
+                        int32_t HW, int32_t C, int32_t G, int32_t act, void* out_bf16, void* out_lo,
+                        tvae_stream_t stream);
 /* da: bf16 gradient wrt the activation output; gres (optional bf16) is added to dx (residual branch).
  * dgamma/dbeta are overwritten. workspace: tvae_gn_bwd_workspace_bytes(N, HW, C, G). */
 int64_t tvae_gn_bwd_workspace_bytes(int32_t N, int32_t HW, int32_t C, int32_t G);
@@ -152,7 +162,7 @@ int32_t tvae_attn_bwd(const float* q, const float* k, const float* v, int32_t pi
  */
 int32_t tvae_reparam_fwd(const float* moments, const float* eps, uint64_t seed, uint64_t sample_offset, int32_t B,
                          int32_t HW, int32_t Z, void* z_bf16, int32_t z_pitch, float* z_nchw, float* eps_out,
-                         float* kl, tvae_stream_t stream);
+                         float* kl, void* z_lo, tvae_stream_t stream);
 /* d_moments (bf16 NHWC [B*HW][2Z]) = d/d(moments) of  sum_i <dz_i, z_i> + kl_scale * sum_b kl[b],
  * for up to two samples z_i = mean + std*eps_i (dz_i: fp32 NHWC [B*HW][Z], eps_i: fp32 NCHW; pair 2 optional). */
 int32_t tvae_reparam_bwd(const float* moments, const float* dz1, const float* eps1, const float* dz2,

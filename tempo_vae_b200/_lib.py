@@ -32,6 +32,9 @@ class ConvArgs(C.Structure):
         ("bn", C.c_int32),
         ("stats_part", C.c_void_p),
         ("stats_groups", C.c_int32),
+        ("x_lo", C.c_void_p),
+        ("w_lo", C.c_void_p),
+        ("out_bf16_lo", C.c_void_p),
     ]
 
 
@@ -64,21 +67,21 @@ def _load():
         "tvae_wgrad_gemm": (i32, [C.POINTER(WgradArgs), vp]),
         "tvae_wgrad_workspace_bytes": (i64, [i32, i32, i32, i32]),
         "tvae_wgrad_splits": (i32, [i32, i32, i32, i64]),
-        "tvae_pack_weight": (i32, [vp, vp, i32, i32, i32, i32, i32, i64, i64, i64, vp]),
-        "tvae_nchw_f32_to_nhwc_bf16": (i32, [vp, vp, i32, i32, i32, i32, vp]),
+        "tvae_pack_weight": (i32, [vp, vp, i32, i32, i32, i32, i32, i64, i64, i64, vp, vp]),
+        "tvae_nchw_f32_to_nhwc_bf16": (i32, [vp, vp, i32, i32, i32, i32, vp, vp]),
         "tvae_nhwc_f32_to_nchw_f32": (i32, [vp, vp, i32, i32, i32, i32, vp]),
         "tvae_nhwc_bf16_to_nchw_f32": (i32, [vp, vp, i32, i32, i32, i32, vp]),
-        "tvae_f32_to_bf16": (i32, [vp, vp, i64, vp]),
+        "tvae_f32_to_bf16": (i32, [vp, vp, i64, vp, vp]),
         "tvae_gn_stats": (i32, [vp, i32, i32, i32, i32, f32, vp, vp]),
         "tvae_gn_stats_finalize": (i32, [vp, i32, i32, i32, C.c_double, f32, vp, vp]),
-        "tvae_gn_act_fwd": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp]),
+        "tvae_gn_act_fwd": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp]),
         "tvae_gn_bwd_workspace_bytes": (i64, [i32, i32, i32, i32]),
         "tvae_gn_act_bwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp]),
         "tvae_colsum_workspace_bytes": (i64, [i64, i32]),
         "tvae_colsum_bf16": (i32, [vp, i64, i32, i32, vp, vp, vp]),
         "tvae_attn_fwd": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp]),
         "tvae_attn_bwd": (i32, [vp, vp, vp, i32, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp]),
-        "tvae_reparam_fwd": (i32, [vp, vp, u64, u64, i32, i32, i32, vp, i32, vp, vp, vp, vp]),
+        "tvae_reparam_fwd": (i32, [vp, vp, u64, u64, i32, i32, i32, vp, i32, vp, vp, vp, vp, vp]),
         "tvae_reparam_bwd": (i32, [vp, vp, vp, vp, vp, f32, i32, i32, i32, vp, vp]),
         "tvae_nll_workspace_bytes": (i64, []),
         "tvae_nll_fwd": (i32, [vp, i32, vp, i32, i64, i32, i32, vp, i32, vp, i32, vp, vp, vp]),

@@ -36,11 +36,15 @@ constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*b
 struct ConvMaps {
   CUtensorMap a[4];
   CUtensorMap b;
+  // "fp32 mode" (split-bf16 emulation): low-order halves of the operands, x = hi + lo with hi = bf16(x), lo = bf16(x - hi)
+  CUtensorMap alo[4];
+  CUtensorMap blo;
 };
 
 struct ConvParams {
   int m_tiles, n_tiles, bn;
   int num_kb, cblks, ntaps, last_k16;
+  int nseg;   // 1: bf16 operands; 3: split-bf16 products hi*hi + hi*lo + lo*hi into the same fp32 accumulator
   int tiles_w, tiles_h, bw, bh, bnimg;
   int dh[9], dw[9], amap[9];
   // epilogue
@@ -48,6 +52,7 @@ struct ConvParams {
   float* out_f32;
   int ld_f32;
   __nv_bfloat16* out_bf16;
+  __nv_bfloat16* out_bf16_lo;
   int ld_bf16;
   const float* bias;
   const float* res;
@@ -77,6 +82,10 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 4; ++i) tma_prefetch_desc(&maps.a[i]);
     tma_prefetch_desc(&maps.b);
+    if (p.nseg > 1) {
+      for (int i = 0; i < 4; ++i) tma_prefetch_desc(&maps.alo[i]);
+      tma_prefetch_desc(&maps.blo);
+    }
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -109,15 +118,18 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
         const int brow = nt * p.bn;
         int kb = 0;
         for (int tap = 0; tap < p.ntaps; ++tap) {
-          const CUtensorMap* am = &maps.a[p.amap[tap]];
           const int hh = h0 + p.dh[tap], ww = w0 + p.dw[tap];
           for (int cb = 0; cb < p.cblks; ++cb, ++kb) {
-            mbar_wait(&empty_bar[stage], phase ^ 1, 1);
-            uint8_t* sa = smem + stage * STAGE_BYTES;
-            mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
-            tma_load_4d(am, &full_bar[stage], sa, cb * BK, ww, hh, n0);
-            tma_load_2d(&maps.b, &full_bar[stage], sa + A_STAGE_BYTES, kb * BK, brow);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            for (int seg = 0; seg < p.nseg; ++seg) {
+              const CUtensorMap* am = seg == 2 ? &maps.alo[p.amap[tap]] : &maps.a[p.amap[tap]];
+              const CUtensorMap* bm = seg == 1 ? &maps.blo : &maps.b;
+              mbar_wait(&empty_bar[stage], phase ^ 1, 1);
+              uint8_t* sa = smem + stage * STAGE_BYTES;
+              mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+              tma_load_4d(am, &full_bar[stage], sa, cb * BK, ww, hh, n0);
+              tma_load_2d(bm, &full_bar[stage], sa + A_STAGE_BYTES, kb * BK, brow);
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
           }
         }
       }
@@ -137,18 +149,20 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
         int kb = 0;
         for (int tap = 0; tap < p.ntaps; ++tap) {
           for (int cb = 0; cb < p.cblks; ++cb, ++kb) {
-            mbar_wait(&full_bar[stage], phase, 3);
-            tc_fence_after();
-            const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-            const uint64_t da = make_smem_desc_sw128(sa, 16, 1024);
-            const uint64_t db = make_smem_desc_sw128(sa + A_STAGE_BYTES, 16, 1024);
-            const int nk = (cb == p.cblks - 1) ? p.last_k16 : 4;
-            for (int k = 0; k < nk; ++k) {
-              // +32 B per K=16 step inside the 128-B swizzle row (descriptor address is in 16-B units)
-              umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            for (int seg = 0; seg < p.nseg; ++seg) {
+              mbar_wait(&full_bar[stage], phase, 3);
+              tc_fence_after();
+              const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+              const uint64_t da = make_smem_desc_sw128(sa, 16, 1024);
+              const uint64_t db = make_smem_desc_sw128(sa + A_STAGE_BYTES, 16, 1024);
+              const int nk = (cb == p.cblks - 1) ? p.last_k16 : 4;
+              for (int k = 0; k < nk; ++k) {
+                // +32 B per K=16 step inside the 128-B swizzle row (descriptor address is in 16-B units)
+                umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k | seg) != 0);
+              }
+              umma_commit(&empty_bar[stage]);
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
-            umma_commit(&empty_bar[stage]);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
         umma_commit(&tfull_bar[as]);
@@ -242,6 +256,11 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
               for (int j = 0; j < 16; ++j)
                 if (col + j < p.n_valid) op[j] = __float2bfloat16(v[j]);
             }
+            if (p.out_bf16_lo) {     // residual of the bf16 rounding, for split-bf16 consumers
+              __nv_bfloat16* ol = p.out_bf16_lo + opix * p.ld_bf16 + col;
+              for (int j = 0; j < 16; ++j)
+                if (col + j < p.n_valid) ol[j] = __float2bfloat16(v[j] - __bfloat162float(__float2bfloat16(v[j])));
+            }
           }
         }
         if (do_stats && ((c + 16) % p.gs) == 0) {   // a group's columns are complete: reduce over the warp's 32 rows
@@ -312,6 +331,8 @@ extern "C" int32_t tvae_conv_gemm(const tvae_conv_args* a, cudaStream_t stream) 
   ConvMaps maps;
   ConvParams p;
   memset(&p, 0, sizeof(p));
+  const bool split = a->x_lo != nullptr && a->w_lo != nullptr;   // split-bf16 ("fp32 mode") operands
+  TVAE_CHECK((a->x_lo == nullptr) == (a->w_lo == nullptr), "tvae_conv_gemm: x_lo and w_lo must be given together");
 
   // geometry of the A-operand pixel grid (== output grid for kind 0/1, == input grid for kind 2)
   int gH = a->H, gW = a->W;
@@ -346,8 +367,10 @@ extern "C" int32_t tvae_conv_gemm(const tvae_conv_args* a, cudaStream_t stream) 
     uint64_t dims[4] = {(uint64_t)a->C, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->N};
     uint64_t strides[3] = {pitchB, pitchB * a->W, pitchB * a->W * a->H};
     uint32_t box[4] = {BK, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bnimg};
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 4; ++i) {
       if (make_tmap_bf16(&maps.a[i], a->x, 4, dims, strides, box)) return -3;
+      if (make_tmap_bf16(&maps.alo[i], split ? a->x_lo : a->x, 4, dims, strides, box)) return -3;
+    }
   } else if (a->kind == 1) {
     p.ntaps = 4;
     for (int t = 0; t < 4; ++t) {
@@ -358,6 +381,9 @@ extern "C" int32_t tvae_conv_gemm(const tvae_conv_args* a, cudaStream_t stream) 
       uint64_t strides[3] = {2 * pitchB, 2 * pitchB * a->W, pitchB * a->W * a->H};
       uint32_t box[4] = {BK, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bnimg};
       if (make_tmap_bf16(&maps.a[t], base, 4, dims, strides, box)) return -3;
+      const uint8_t* base_lo =
+          reinterpret_cast<const uint8_t*>(split ? a->x_lo : a->x) + ((size_t)ty * a->W + tx) * pitchB;
+      if (make_tmap_bf16(&maps.alo[t], base_lo, 4, dims, strides, box)) return -3;
     }
   } else {
     p.ntaps = 1;
@@ -365,9 +391,12 @@ extern "C" int32_t tvae_conv_gemm(const tvae_conv_args* a, cudaStream_t stream) 
     uint64_t dims[4] = {(uint64_t)a->C, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->N};
     uint64_t strides[3] = {pitchB, pitchB * a->W, pitchB * a->W * a->H};
     uint32_t box[4] = {BK, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bnimg};
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 4; ++i) {
       if (make_tmap_bf16(&maps.a[i], a->x, 4, dims, strides, box)) return -3;
+      if (make_tmap_bf16(&maps.alo[i], split ? a->x_lo : a->x, 4, dims, strides, box)) return -3;
+    }
   }
+  p.nseg = split ? 3 : 1;
   p.num_kb = p.ntaps * p.cblks;
   TVAE_CHECK(a->k_pitch >= p.num_kb * BK, "tvae_conv_gemm: k_pitch %d < taps*c_pad %d", a->k_pitch, p.num_kb * BK);
 
@@ -398,6 +427,7 @@ extern "C" int32_t tvae_conv_gemm(const tvae_conv_args* a, cudaStream_t stream) 
     uint64_t strides[1] = {(uint64_t)a->k_pitch * 2};
     uint32_t box[2] = {BK, (uint32_t)p.bn};
     if (make_tmap_bf16(&maps.b, a->w, 2, dims, strides, box)) return -3;
+    if (make_tmap_bf16(&maps.blo, split ? a->w_lo : a->w, 2, dims, strides, box)) return -3;
   }
 
   p.stats_part = a->stats_part;
@@ -412,6 +442,8 @@ extern "C" int32_t tvae_conv_gemm(const tvae_conv_args* a, cudaStream_t stream) 
   }
   p.out_f32 = a->out_f32; p.ld_f32 = a->out_f32_pitch;
   p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(a->out_bf16); p.ld_bf16 = a->out_bf16_pitch;
+  p.out_bf16_lo = reinterpret_cast<__nv_bfloat16*>(a->out_bf16_lo);
+  TVAE_CHECK(!p.out_bf16_lo || p.out_bf16, "tvae_conv_gemm: out_bf16_lo needs out_bf16");
   p.bias = a->bias;
   p.res = a->residual; p.ld_res = a->res_pitch;
   if (p.out_f32) TVAE_CHECK(p.ld_f32 % 4 == 0 && (reinterpret_cast<uintptr_t>(p.out_f32) & 15) == 0, "out_f32 alignment");

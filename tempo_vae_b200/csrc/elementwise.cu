@@ -17,8 +17,9 @@ inline int ew_grid(long long work_items, int per_block = EW_THREADS, int max_blo
 }
 
 // ---------------------------------------------------------------------------------------------- pack weights
-__global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Crow, int TR,
-                                   int TK, int C, int c_pad, long long s_row, long long s_col, long long s_tap) {
+__global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
+                                   __nv_bfloat16* __restrict__ out_lo, int Crow, int TR, int TK, int C, int c_pad,
+                                   long long s_row, long long s_col, long long s_tap) {
   const long long kp = (long long)TK * c_pad;
   const long long total = (long long)TR * Crow * kp;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -29,14 +30,16 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* _
     const int tr = (int)(row / Crow), cr = (int)(row - (long long)tr * Crow);
     float v = 0.f;
     if (c < C) v = w[cr * s_row + c * s_col + (tr + tk) * s_tap];
-    out[i] = __float2bfloat16(v);
+    const __nv_bfloat16 hi = __float2bfloat16(v);
+    out[i] = hi;
+    if (out_lo) out_lo[i] = __float2bfloat16(v - __bfloat162float(hi));
   }
 }
 
 // ---------------------------------------------------------------------------------------------- transposes
 // NCHW fp32 -> NHWC bf16 (pad lanes [C, pitch) zeroed). Tile: 64 channels x 64 pixels.
-__global__ void nchw_to_nhwc_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int C, int HW,
-                                         int pitch) {
+__global__ void nchw_to_nhwc_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                         __nv_bfloat16* __restrict__ out_lo, int C, int HW, int pitch) {
   __shared__ float tile[64][65];
   const int n = blockIdx.z;
   const int c0 = blockIdx.y * 64, p0 = blockIdx.x * 64;
@@ -57,11 +60,17 @@ __global__ void nchw_to_nhwc_bf16_kernel(const float* __restrict__ x, __nv_bfloa
     for (int i = py; i < 64; i += 8) {
       const int p = p0 + i;
       if (p < HW && c < pitch) {
-        __nv_bfloat16* o = out + ((long long)n * HW + p) * pitch + c;
+        const long long oidx = ((long long)n * HW + p) * pitch + c;
+        __nv_bfloat16* o = out + oidx;
+        const float v0 = tile[2 * cx][i], v1 = tile[2 * cx + 1][i];
         if (c + 1 < pitch) {
-          *reinterpret_cast<uint32_t*>(o) = pack_bf16(tile[2 * cx][i], tile[2 * cx + 1][i]);
+          *reinterpret_cast<uint32_t*>(o) = pack_bf16(v0, v1);
         } else {
-          o[0] = __float2bfloat16(tile[2 * cx][i]);
+          o[0] = __float2bfloat16(v0);
+        }
+        if (out_lo) {
+          out_lo[oidx] = __float2bfloat16(v0 - __bfloat162float(__float2bfloat16(v0)));
+          if (c + 1 < pitch) out_lo[oidx + 1] = __float2bfloat16(v1 - __bfloat162float(__float2bfloat16(v1)));
         }
       }
     }
@@ -96,7 +105,10 @@ __global__ void nhwc_to_nchw_kernel(const T* __restrict__ x, float* __restrict__
   }
 }
 
-__global__ void f32_to_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, long long n) {
+__device__ __forceinline__ float bf16_residual(float v) { return v - __bfloat162float(__float2bfloat16(v)); }
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                   __nv_bfloat16* __restrict__ out_lo, long long n) {
   const long long n4 = n / 4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
        i += (long long)gridDim.x * blockDim.x) {
@@ -105,10 +117,17 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* _
     o.x = pack_bf16(v.x, v.y);
     o.y = pack_bf16(v.z, v.w);
     reinterpret_cast<uint2*>(out)[i] = o;
+    if (out_lo) {
+      uint2 l;
+      l.x = pack_bf16(bf16_residual(v.x), bf16_residual(v.y));
+      l.y = pack_bf16(bf16_residual(v.z), bf16_residual(v.w));
+      reinterpret_cast<uint2*>(out_lo)[i] = l;
+    }
   }
   if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
     const long long i = n4 * 4 + threadIdx.x;
     out[i] = __float2bfloat16(x[i]);
+    if (out_lo) out_lo[i] = __float2bfloat16(bf16_residual(x[i]));
   }
 }
 
@@ -179,7 +198,8 @@ __global__ void gn_stats_finalize_kernel(const float* __restrict__ part, int spi
 template <int VEC>
 __global__ void gn_act_fwd_kernel(const float* __restrict__ x, const float* __restrict__ stats,
                                   const float* __restrict__ gamma, const float* __restrict__ beta, long long rows,
-                                  int HW, int C, int G, int act, __nv_bfloat16* __restrict__ out) {
+                                  int HW, int C, int G, int act, __nv_bfloat16* __restrict__ out,
+                                  __nv_bfloat16* __restrict__ out_lo) {
   const int gs = C / G;
   const int U = C / VEC;
   const long long total = rows * U;
@@ -210,9 +230,17 @@ __global__ void gn_act_fwd_kernel(const float* __restrict__ x, const float* __re
       o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]);
       o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
       *reinterpret_cast<uint4*>(out + row * C + c) = o;
+      if (out_lo) {
+        uint4 l;
+        l.x = pack_bf16(bf16_residual(v[0]), bf16_residual(v[1])); l.y = pack_bf16(bf16_residual(v[2]), bf16_residual(v[3]));
+        l.z = pack_bf16(bf16_residual(v[4]), bf16_residual(v[5])); l.w = pack_bf16(bf16_residual(v[6]), bf16_residual(v[7]));
+        *reinterpret_cast<uint4*>(out_lo + row * C + c) = l;
+      }
     } else {
       float y = (*xp - mean) * rstd * gamma[c] + beta[c];
-      out[row * C + c] = __float2bfloat16(act_f(y, act));
+      const float av = act_f(y, act);
+      out[row * C + c] = __float2bfloat16(av);
+      if (out_lo) out_lo[row * C + c] = __float2bfloat16(bf16_residual(av));
     }
   }
 }
@@ -446,25 +474,28 @@ inline int colsum_blocks(long long rows) {
 using namespace tvae;
 
 extern "C" int32_t tvae_pack_weight(const float* w, void* out, int32_t Crow, int32_t TR, int32_t TK, int32_t C,
-                                    int32_t c_pad, int64_t s_row, int64_t s_col, int64_t s_tap, cudaStream_t stream) {
+                                    int32_t c_pad, int64_t s_row, int64_t s_col, int64_t s_tap, void* out_lo,
+                                    cudaStream_t stream) {
   TVAE_ENTER(w);
   TVAE_CHECK(w && out, "tvae_pack_weight: null pointer");
   TVAE_CHECK(TR == 1 || TK == 1, "tvae_pack_weight: one of TR, TK must be 1");
   TVAE_CHECK(c_pad >= C, "tvae_pack_weight: c_pad < C");
   const long long total = (long long)TR * Crow * TK * c_pad;
-  pack_weight_kernel<<<ew_grid(total), EW_THREADS, 0, stream>>>(w, reinterpret_cast<__nv_bfloat16*>(out), Crow, TR, TK,
-                                                               C, c_pad, s_row, s_col, s_tap);
+  pack_weight_kernel<<<ew_grid(total), EW_THREADS, 0, stream>>>(w, reinterpret_cast<__nv_bfloat16*>(out),
+                                                               reinterpret_cast<__nv_bfloat16*>(out_lo), Crow, TR, TK, C,
+                                                               c_pad, s_row, s_col, s_tap);
   TVAE_CUDA(cudaGetLastError());
   return 0;
 }
 
 extern "C" int32_t tvae_nchw_f32_to_nhwc_bf16(const float* x, void* out, int32_t N, int32_t C, int32_t HW,
-                                              int32_t pitch, cudaStream_t stream) {
+                                              int32_t pitch, void* out_lo, cudaStream_t stream) {
   TVAE_ENTER(x);
   TVAE_CHECK(x && out, "tvae_nchw_f32_to_nhwc_bf16: null pointer");
   TVAE_CHECK(pitch >= C && pitch % 2 == 0, "tvae_nchw_f32_to_nhwc_bf16: bad pitch");
   dim3 grid((HW + 63) / 64, (pitch + 63) / 64, N);
-  nchw_to_nhwc_bf16_kernel<<<grid, 256, 0, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(out), C, HW, pitch);
+  nchw_to_nhwc_bf16_kernel<<<grid, 256, 0, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(out),
+                                                     reinterpret_cast<__nv_bfloat16*>(out_lo), C, HW, pitch);
   TVAE_CUDA(cudaGetLastError());
   return 0;
 }
@@ -487,10 +518,11 @@ extern "C" int32_t tvae_nhwc_bf16_to_nchw_f32(const void* x, float* out, int32_t
   TVAE_CUDA(cudaGetLastError());
   return 0;
 }
-extern "C" int32_t tvae_f32_to_bf16(const float* x, void* out, int64_t n, cudaStream_t stream) {
+extern "C" int32_t tvae_f32_to_bf16(const float* x, void* out, int64_t n, void* out_lo, cudaStream_t stream) {
   TVAE_ENTER(x);
   TVAE_CHECK(x && out, "tvae_f32_to_bf16: null pointer");
-  f32_to_bf16_kernel<<<ew_grid(n / 4 + 1), EW_THREADS, 0, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(out), n);
+  f32_to_bf16_kernel<<<ew_grid(n / 4 + 1), EW_THREADS, 0, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(out),
+                                                                   reinterpret_cast<__nv_bfloat16*>(out_lo), n);
   TVAE_CUDA(cudaGetLastError());
   return 0;
 }
@@ -520,24 +552,26 @@ extern "C" int32_t tvae_gn_stats_finalize(const float* part, int32_t spi, int32_
 }
 
 extern "C" int32_t tvae_gn_act_fwd(const float* x, const float* stats, const float* gamma, const float* beta,
-                                   int32_t N, int32_t HW, int32_t C, int32_t G, int32_t act, void* out,
+                                   int32_t N, int32_t HW, int32_t C, int32_t G, int32_t act, void* out, void* out_lo,
                                    cudaStream_t stream) {
   TVAE_ENTER(x);
   TVAE_CHECK(x && stats && gamma && beta && out, "tvae_gn_act_fwd: null pointer");
   TVAE_CHECK(G > 0 && C % G == 0, "tvae_gn_act_fwd: C %% G != 0");
   const long long rows = (long long)N * HW;
   const int gs = C / G;
-  if (gn_fast_ok(C, G)) {
+  if (gn_fast_ok(C, G) && out_lo == nullptr) {   // the split-bf16 ("fp32 mode") output uses the generic kernel
     gn_act_fwd_fast(x, stats, gamma, beta, N, HW, C, G, act, reinterpret_cast<__nv_bfloat16*>(out), stream);
     TVAE_CUDA(cudaGetLastError());
     return 0;
   }
   if (gs % 8 == 0)
     gn_act_fwd_kernel<8><<<ew_grid(rows * (C / 8)), EW_THREADS, 0, stream>>>(
-        x, stats, gamma, beta, rows, HW, C, G, act, reinterpret_cast<__nv_bfloat16*>(out));
+        x, stats, gamma, beta, rows, HW, C, G, act, reinterpret_cast<__nv_bfloat16*>(out),
+        reinterpret_cast<__nv_bfloat16*>(out_lo));
   else
     gn_act_fwd_kernel<1><<<ew_grid(rows * C), EW_THREADS, 0, stream>>>(x, stats, gamma, beta, rows, HW, C, G, act,
-                                                                        reinterpret_cast<__nv_bfloat16*>(out));
+                                                                        reinterpret_cast<__nv_bfloat16*>(out),
+                                                                        reinterpret_cast<__nv_bfloat16*>(out_lo));
   TVAE_CUDA(cudaGetLastError());
   return 0;
 }

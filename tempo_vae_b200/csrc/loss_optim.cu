@@ -38,8 +38,8 @@ __device__ __forceinline__ float philox_normal(uint64_t seed, uint64_t sample, u
 // one block per sample
 __global__ void reparam_fwd_kernel(const float* __restrict__ moments, const float* __restrict__ eps, uint64_t seed,
                                    uint64_t sample_offset, int HW, int Z, __nv_bfloat16* __restrict__ z_bf16,
-                                   int z_pitch, float* __restrict__ z_nchw, float* __restrict__ eps_out,
-                                   float* __restrict__ kl) {
+                                   __nv_bfloat16* __restrict__ z_lo, int z_pitch, float* __restrict__ z_nchw,
+                                   float* __restrict__ eps_out, float* __restrict__ kl) {
   __shared__ double red[32];
   const int b = blockIdx.x;
   const int total = HW * Z;
@@ -55,6 +55,7 @@ __global__ void reparam_fwd_kernel(const float* __restrict__ moments, const floa
     const float std = expf(0.5f * lv);
     const float z = mean + std * ev;
     if (z_bf16) z_bf16[row * z_pitch + c] = __float2bfloat16(z);
+    if (z_lo) z_lo[row * z_pitch + c] = __float2bfloat16(z - __bfloat162float(__float2bfloat16(z)));
     if (z_nchw) z_nchw[nchw] = z;
     if (eps_out) eps_out[nchw] = ev;
     acc += (double)(0.5f * (mean * mean + expf(lv) - 1.0f - lv));
@@ -333,12 +334,13 @@ using namespace tvae;
 
 extern "C" int32_t tvae_reparam_fwd(const float* moments, const float* eps, uint64_t seed, uint64_t sample_offset,
                                     int32_t B, int32_t HW, int32_t Z, void* z_bf16, int32_t z_pitch, float* z_nchw,
-                                    float* eps_out, float* kl, cudaStream_t stream) {
+                                    float* eps_out, float* kl, void* z_lo, cudaStream_t stream) {
   TVAE_ENTER(moments);
   TVAE_CHECK(moments, "tvae_reparam_fwd: null moments");
   TVAE_CHECK(B > 0 && HW > 0 && Z > 0, "tvae_reparam_fwd: bad shape");
   reparam_fwd_kernel<<<B, 256, 0, stream>>>(moments, eps, seed, sample_offset, HW, Z,
-                                            reinterpret_cast<__nv_bfloat16*>(z_bf16), z_pitch, z_nchw, eps_out, kl);
+                                            reinterpret_cast<__nv_bfloat16*>(z_bf16),
+                                            reinterpret_cast<__nv_bfloat16*>(z_lo), z_pitch, z_nchw, eps_out, kl);
   TVAE_CUDA(cudaGetLastError());
   return 0;
 }

@@ -48,6 +48,20 @@ class _Engine:
 ENGINE = _Engine()
 
 
+def set_precision(mode: str):
+    """"bf16" (default): bf16 tensor-core operands, fp32 accumulation. "fp32": forward GEMMs emulate fp32 products
+    with split-bf16 operands (hi*hi + hi*lo + lo*hi, 3x the tensor work, ~2^-16 relative product error) — the
+    north star's "fp32 mode" for parity runs; backward GEMMs keep plain bf16 operands."""
+    if mode not in ("bf16", "fp32"):
+        raise ValueError("precision must be 'bf16' or 'fp32'")
+    ops.SPLIT_BF16[0] = mode == "fp32"
+    ENGINE.params_changed()
+
+
+def get_precision() -> str:
+    return "fp32" if ops.SPLIT_BF16[0] else "bf16"
+
+
 def _grad_begin(p):
     """Returns (tensor to write, accumulate?) for parameter p, installing the flat-buffer view if there is one."""
     if p.grad is None:
@@ -92,7 +106,7 @@ class _PackedMixin:
     def packed(self, mode):
         packs = self.__dict__.setdefault("_packs", {})
         w = self.weight
-        key = (w.data_ptr(), w._version, ENGINE.param_epoch)
+        key = (w.data_ptr(), w._version, ENGINE.param_epoch, ops.SPLIT_BF16[0])
         ent = packs.get(mode)
         if ent is None or ent.data.device != w.device:
             ent = ops.pack_weight(w, mode)
@@ -236,6 +250,7 @@ def conv_bwd(mod, dy_bf16, x_bf16, Cin, *, dgrad=None, dgrad_residual=None, bias
     kind, R = mod.conv_kind()
     Cout = mod.out_channels
     w = mod.weight
+    x_bf16, dy_bf16 = ops.hi_of(x_bf16), ops.hi_of(dy_bf16)      # backward GEMMs run on plain bf16 operands
     if w.requires_grad:
         def wg(dst):
             if kind == 2:   # ConvTranspose2d [Cin][Cout][2][2]: P = x (coarse), Q = dy (fine)
@@ -387,7 +402,7 @@ class AttnBlock(nn.Module):
         for i, m in enumerate((self.q, self.k, self.v)):
             conv_fwd(m, hn, C, out_f32=qkv[..., i * C:(i + 1) * C])
         o_bf16, o_f32, lse = ops.attn_fwd(qkv, C, self.n_heads, N, H * W)
-        o4 = o_bf16.view(N, H, W, C)
+        o4 = o_bf16.view(N, H, W, C)          # tensor or split-bf16 Pair
         r = conv_fwd(self.proj_out, o4, C, residual=h.f32, stats_for=next_norm)
         saved = (h.f32, stats, hn, qkv, o4, o_f32, lse) if save else None
         return A(f32=r[0], C=C, stats=r.stats), saved

@@ -47,6 +47,47 @@ def round_up(v, m):
     return (v + m - 1) // m * m
 
 
+# "fp32 mode": tensor-core operands carried as split-bf16 pairs (hi = bf16(v), lo = bf16(v - hi)); the conv GEMM then
+# accumulates hi*hi + hi*lo + lo*hi in fp32 (~2^-16 relative product error, 3x the tensor work). Forward only:
+# backward GEMMs use the hi halves. Toggled by tempo_vae_b200.set_precision().
+SPLIT_BF16 = [False]
+
+
+class Pair:
+    """A split-bf16 operand: two same-shaped bf16 tensors."""
+
+    __slots__ = ("hi", "lo")
+
+    def __init__(self, hi, lo):
+        self.hi, self.lo = hi, lo
+
+    @property
+    def shape(self):
+        return self.hi.shape
+
+    @property
+    def device(self):
+        return self.hi.device
+
+    def view(self, *shape):
+        return Pair(self.hi.view(*shape), self.lo.view(*shape))
+
+    def __getitem__(self, idx):
+        return Pair(self.hi[idx], self.lo[idx])
+
+
+def hi_of(x):
+    return x.hi if isinstance(x, Pair) else x
+
+
+def _lo_like(t):
+    return torch.empty_like(t) if SPLIT_BF16[0] else None
+
+
+def _pair(hi, lo):
+    return Pair(hi, lo) if lo is not None else hi
+
+
 def pitch_of(t):
     """Channel pitch (elements between consecutive pixels) of an NHWC / [rows, C] tensor or channel-slice view."""
     assert t.stride(-1) == 1, "channels must be the contiguous dimension"
@@ -63,10 +104,11 @@ def require_cuda(t, name="tensor"):
 class PackedWeight:
     """bf16 K-major GEMM operand [rows][k_pitch] built from a parameter in the reference's layout."""
 
-    __slots__ = ("data", "rows", "k_pitch", "c_pad", "version")
+    __slots__ = ("data", "lo", "rows", "k_pitch", "c_pad", "version")
 
-    def __init__(self, data, rows, k_pitch, c_pad):
+    def __init__(self, data, rows, k_pitch, c_pad, lo=None):
         self.data, self.rows, self.k_pitch, self.c_pad = data, rows, k_pitch, c_pad
+        self.lo = lo            # low-order half (split-bf16 mode) or None
         self.version = -1
 
 
@@ -100,10 +142,13 @@ def pack_weight(w, mode, out=None):
     k_pitch = g["TK"] * c_pad
     if out is None:
         out = PackedWeight(torch.empty((rows, k_pitch), dtype=torch.bfloat16, device=w.device), rows, k_pitch, c_pad)
+    if SPLIT_BF16[0] and out.lo is None:
+        out.lo = torch.empty_like(out.data)
     wc = w.detach()
     assert wc.is_contiguous() and wc.dtype == torch.float32
     check(lib.tvae_pack_weight(wc.data_ptr(), out.data.data_ptr(), g["Crow"], g["TR"], g["TK"], g["C"], c_pad,
-                               g["s_row"], g["s_col"], g["s_tap"], _stream()), "tvae_pack_weight")
+                               g["s_row"], g["s_col"], g["s_tap"], _ptr(out.lo) if SPLIT_BF16[0] else 0, _stream()),
+          "tvae_pack_weight")
     return out
 
 
@@ -124,6 +169,8 @@ def conv_gemm(x, C_in, wp, *, kind, R, Cout, flip=False, bias=None, residual=Non
     """x: bf16 [N,H,W,pitch]. Returns (out_f32 or None, out_bf16 or None) as NHWC tensors; with stats=(G, eps) the
     GroupNorm statistics [N, G, 2] of the output are produced by the epilogue and returned as a third value
     (None when the geometry does not allow it)."""
+    x_lo = x.lo if isinstance(x, Pair) else None
+    x = hi_of(x)
     N, H, W, _ = x.shape
     pitch = pitch_of(x)
     if kind == 1:
@@ -148,6 +195,14 @@ def conv_gemm(x, C_in, wp, *, kind, R, Cout, flip=False, bias=None, residual=Non
     a.out_f32 = _ptr(out_f32); a.out_f32_pitch = pitch_of(out_f32) if out_f32 is not None else 0
     a.out_bf16 = _ptr(out_bf16); a.out_bf16_pitch = pitch_of(out_bf16) if out_bf16 is not None else 0
     a.bn = bn
+    out_lo = None
+    if x_lo is not None and wp.lo is not None and SPLIT_BF16[0]:
+        assert pitch_of(x_lo) == pitch
+        a.x_lo = x_lo.data_ptr()
+        a.w_lo = wp.lo.data_ptr()
+    if out_bf16 is not None and SPLIT_BF16[0] and want_bf16:
+        out_lo = torch.empty_like(out_bf16)
+        a.out_bf16_lo = out_lo.data_ptr()
     part = None
     if stats is not None and fused_stats_ok(N, oH, oW, Cout, stats[0], kind, H, W):
         grid_px = (H * W) if kind == 2 else (oH * oW)
@@ -164,6 +219,7 @@ def conv_gemm(x, C_in, wp, *, kind, R, Cout, flip=False, bias=None, residual=Non
         prof["events"].append((e0, e1))
     else:
         check(lib.tvae_conv_gemm(C.byref(a), _stream()), "tvae_conv_gemm")
+    out_bf16 = _pair(out_bf16, out_lo)
     if stats is None:
         return out_f32, out_bf16
     st = None
@@ -189,6 +245,7 @@ def _workspace(nbytes, device, key="ws"):
 
 def wgrad_gemm(p, Cm, q, Cn, *, kind, R, grad, accumulate=False, splits=0):
     """grad[m][n][tap] (+)= sum_pixels p[pixel][m] * q[pixel (+) tap][n]; p: bf16 [N,H,W,pitch] (the dense grid)."""
+    p, q = hi_of(p), hi_of(q)
     N, H, W, _ = p.shape
     pp = pitch_of(p)
     taps = R * R if kind == 0 else 4
@@ -223,12 +280,14 @@ def nchw_to_nhwc_bf16(x, pitch=None):
     if x.dtype != torch.float32:
         x = x.float()
     out = torch.empty((N, H, W, pitch), dtype=torch.bfloat16, device=x.device)
-    check(lib.tvae_nchw_f32_to_nhwc_bf16(x.data_ptr(), out.data_ptr(), N, Cc, H * W, pitch, _stream()),
+    lo = _lo_like(out)
+    check(lib.tvae_nchw_f32_to_nhwc_bf16(x.data_ptr(), out.data_ptr(), N, Cc, H * W, pitch, _ptr(lo), _stream()),
           "tvae_nchw_f32_to_nhwc_bf16")
-    return out
+    return _pair(out, lo)
 
 
 def nhwc_to_nchw_f32(x, Cc):
+    x = hi_of(x)
     N, H, W, pitch = x.shape
     out = torch.empty((N, Cc, H, W), dtype=torch.float32, device=x.device)
     if x.dtype == torch.float32:
@@ -242,8 +301,9 @@ def nhwc_to_nchw_f32(x, Cc):
 
 def f32_to_bf16(x):
     out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
-    check(lib.tvae_f32_to_bf16(x.data_ptr(), out.data_ptr(), x.numel(), _stream()), "tvae_f32_to_bf16")
-    return out
+    lo = _lo_like(out)
+    check(lib.tvae_f32_to_bf16(x.data_ptr(), out.data_ptr(), x.numel(), _ptr(lo), _stream()), "tvae_f32_to_bf16")
+    return _pair(out, lo)
 
 
 # ----------------------------------------------------------------------------------------------- GroupNorm
@@ -258,9 +318,10 @@ def gn_stats(x, Cc, G, eps):
 def gn_act_fwd(x, stats, gamma, beta, G, act):
     N, H, W, Cc = x.shape
     out = torch.empty((N, H, W, Cc), dtype=torch.bfloat16, device=x.device)
+    lo = _lo_like(out)
     check(lib.tvae_gn_act_fwd(x.data_ptr(), stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), N, H * W, Cc, G,
-                              int(act), out.data_ptr(), _stream()), "tvae_gn_act_fwd")
-    return out
+                              int(act), out.data_ptr(), _ptr(lo), _stream()), "tvae_gn_act_fwd")
+    return _pair(out, lo)
 
 
 def gn_act_bwd(x, stats, gamma, beta, da, gres, G, act, dgamma, dbeta):
@@ -275,6 +336,7 @@ def gn_act_bwd(x, stats, gamma, beta, da, gres, G, act, dgamma, dbeta):
 
 
 def colsum_bf16(x, Cc, out):
+    x = hi_of(x)
     rows = x.numel() // x.shape[-1]
     ws = _workspace(lib.tvae_colsum_workspace_bytes(rows, Cc), x.device, "colsum")
     check(lib.tvae_colsum_bf16(x.data_ptr(), rows, Cc, pitch_of(x), out.data_ptr(), ws.data_ptr(), _stream()),
@@ -292,6 +354,8 @@ def attn_fwd(qkv, Cc, heads, B, T):
     base = qkv.data_ptr()
     check(lib.tvae_attn_fwd(base, base + 4 * Cc, base + 8 * Cc, pitch, B, T, Cc, heads, o_bf16.data_ptr(),
                             o_f32.data_ptr(), lse.data_ptr(), _stream()), "tvae_attn_fwd")
+    if SPLIT_BF16[0]:
+        o_bf16 = f32_to_bf16(o_f32)
     return o_bf16, o_f32, lse
 
 
@@ -322,9 +386,11 @@ def reparam_fwd(moments, Z, *, eps=None, seed=0, sample_offset=0, want_z_nchw=Fa
         eps_out = None
     else:
         eps_out = torch.empty((B, Z, h, w), dtype=torch.float32, device=dev)
+    z_lo = torch.zeros_like(z_bf16) if SPLIT_BF16[0] else None
     check(lib.tvae_reparam_fwd(moments.data_ptr(), _ptr(eps), seed, sample_offset, B, h * w, Z, z_bf16.data_ptr(),
-                               z_pitch, _ptr(z_nchw), _ptr(eps_out), kl.data_ptr(), _stream()), "tvae_reparam_fwd")
-    return z_bf16, z_nchw, (eps if eps is not None else eps_out), kl
+                               z_pitch, _ptr(z_nchw), _ptr(eps_out), kl.data_ptr(), _ptr(z_lo), _stream()),
+          "tvae_reparam_fwd")
+    return _pair(z_bf16, z_lo), z_nchw, (eps if eps is not None else eps_out), kl
 
 
 def reparam_bwd(moments, Z, dz1, eps1, dz2, eps2, kl_scale):
@@ -337,6 +403,7 @@ def reparam_bwd(moments, Z, dz1, eps1, dz2, eps2, kl_scale):
 
 def nll_fwd(x_bf16, xhat, Cc, loss_type, logvar, batch, want_grad):
     """x_bf16 [N,H,W,xp] bf16; xhat [N,H,W,hp] fp32. Returns (sums fp64[3], dxhat bf16 or None)."""
+    x_bf16 = hi_of(x_bf16)
     P = x_bf16.numel() // x_bf16.shape[-1]
     dev = xhat.device
     sums = torch.empty((3,), dtype=torch.float64, device=dev)

@@ -400,3 +400,33 @@ def test_conv_fused_groupnorm_stats(N, H, W, Cin, Cout, kind):
     torch.cuda.synchronize()
     assert torch.allclose(st[..., 0], ref[..., 0], atol=1e-5, rtol=1e-5)
     assert torch.allclose(st[..., 1], ref[..., 1], rtol=1e-5)
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout,R", [(2, 16, 16, 128, 128, 3), (1, 64, 64, 1028, 512, 3), (2, 16, 16, 64, 64, 1)])
+def test_conv_split_bf16_fp32_mode(N, H, W, Cin, Cout, R):
+    """Split-bf16 operands (hi + lo): the conv matches an fp32 convolution of the UNROUNDED inputs to ~2^-16."""
+    o = ops()
+    g = torch.Generator(device="cuda").manual_seed(14)
+    x = torch.randn((N, Cin, H, W), device="cuda", generator=g)
+    w = torch.randn((Cout, Cin, R, R), device="cuda", generator=g) / math.sqrt(Cin * R * R)
+    b = torch.randn((Cout,), device="cuda", generator=g)
+    ref = F.conv2d(x.double(), w.double(), b.double(), padding=R // 2).float()
+    o.SPLIT_BF16[0] = True
+    try:
+        xp = o.nchw_to_nhwc_bf16(x, o.round_up(Cin, 8))
+        assert isinstance(xp, o.Pair)
+        rec = (xp.hi.float() + xp.lo.float())[..., :Cin].permute(0, 3, 1, 2)
+        assert rel_err(rec, x) < 2e-5
+        wp = o.pack_weight(w, "fwd")
+        of, ob = o.conv_gemm(xp, Cin, wp, kind=0, R=R, Cout=Cout, bias=b, want_bf16=True)
+        torch.cuda.synchronize()
+        assert rel_err(of[..., :Cout].permute(0, 3, 1, 2), ref) < 5e-5
+        assert isinstance(ob, o.Pair)
+        assert rel_err((ob.hi.float() + ob.lo.float())[..., :Cout].permute(0, 3, 1, 2), ref) < 5e-5
+    finally:
+        o.SPLIT_BF16[0] = False
+    # plain bf16 operands on the same unrounded inputs are ~100x less accurate: the mode really is in effect
+    of2, _ = o.conv_gemm(o.nchw_to_nhwc_bf16(x, o.round_up(Cin, 8)), Cin, o.pack_weight(w, "fwd"), kind=0, R=R, Cout=Cout,
+                         bias=b)
+    torch.cuda.synchronize()
+    assert rel_err(of2[..., :Cout].permute(0, 3, 1, 2), ref) > 5e-4

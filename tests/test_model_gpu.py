@@ -367,3 +367,37 @@ def test_inference_patch_sweep_and_whole_granule_vs_oracle(capsys):
     with capsys.disabled():
         print(f"\n[inference] patch-sweep latent rel-L2 {e_patch:.3e}; whole-granule (2048-token attention) {e_whole:.3e}")
     assert e_patch < 1.5e-2 and e_whole < 1.5e-2
+
+
+def test_fp32_mode_forward_parity_1e4(capsys):
+    """North star: forward recon, mu and logvar within rel 1e-4 in fp32 mode (split-bf16 emulated fp32 GEMMs)."""
+    import tempo_vae_b200 as t
+    t.set_precision("fp32")
+    try:
+        fx = gold("tiny_train.pt")
+        model = build(fx["cfg"], fx["state_dict"])
+        s = fx["steps"][0]
+        with torch.no_grad():
+            recon, post = model.vae(fx["x"][0].cuda(), eps=fx["eps"][0].cuda())
+        e_tiny = (rel(post.mean, s["mean"]), rel(post.logvar, s["logvar"]), rel(recon, s["recon"]))
+        loss, metrics = model.get_loss(fx["x"][0].cuda(), eps=fx["eps"][0].cuda())
+        assert abs(loss.item() - s["loss"]) / s["loss"] < 1e-5
+        assert abs(metrics["kl_loss"].item() - s["kl_loss"]) / s["kl_loss"] < 1e-3
+        loss.backward()                                    # backward still works (bf16 operands, hi halves)
+        fxd = gold("default_train_b2.pt")
+        cfg = fxd["cfg"]
+        model = build(cfg)
+        sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+        orc.rerandomize_zero_init(sd, seed=1234)
+        model.load_state_dict(sd)
+        s0 = fxd["steps"][0]
+        x = orc.structured_batch(fxd["B"], cfg, seed=fxd["x_seeds"][0]).cuda()
+        with torch.no_grad():
+            recon, post = model.vae(x, eps=fxd["eps"][0].cuda())
+        e_def = (rel(post.mean, s0["mean"]), rel(post.logvar, s0["logvar"]), rel(recon[:, ::16, ::4, ::4], s0["recon"]))
+    finally:
+        t.set_precision("bf16")
+    with capsys.disabled():
+        print(f"\n[fp32 mode] forward rel-L2 (mean, logvar, recon): tiny {tuple(f'{v:.2e}' for v in e_tiny)}, "
+              f"default B=2 {tuple(f'{v:.2e}' for v in e_def)}")
+    assert max(e_tiny) < 1e-4 and max(e_def) < 1e-4, (e_tiny, e_def)
