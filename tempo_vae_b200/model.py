@@ -269,13 +269,14 @@ def conv_bwd(mod, dy_bf16, x_bf16, Cin, *, dgrad=None, dgrad_residual=None, bias
         return None
     if kind == 0:
         of, ob = ops.conv_gemm(dy_bf16, Cout, mod.packed("dgrad"), kind=0, R=R, Cout=Cin, flip=True,
-                               residual=dgrad_residual, want_f32=(dgrad == "f32"), want_bf16=(dgrad == "bf16"))
+                               residual=dgrad_residual, want_f32=(dgrad == "f32"), want_bf16=(dgrad == "bf16"),
+                               split_out=False)
     elif kind == 1:
         of, ob = ops.conv_gemm(dy_bf16, Cout, mod.packed("down_dgrad"), kind=2, R=2, Cout=Cin,
-                               want_f32=(dgrad == "f32"), want_bf16=(dgrad == "bf16"))
+                               want_f32=(dgrad == "f32"), want_bf16=(dgrad == "bf16"), split_out=False)
     else:
         of, ob = ops.conv_gemm(dy_bf16, Cout, mod.packed("up_dgrad"), kind=1, R=2, Cout=Cin,
-                               want_f32=(dgrad == "f32"), want_bf16=(dgrad == "bf16"))
+                               want_f32=(dgrad == "f32"), want_bf16=(dgrad == "bf16"), split_out=False)
     return of if dgrad == "f32" else ob
 
 

@@ -165,7 +165,7 @@ def fused_stats_ok(N, oH, oW, Cout, G, kind, H, W):
 
 
 def conv_gemm(x, C_in, wp, *, kind, R, Cout, flip=False, bias=None, residual=None, want_f32=True, want_bf16=False,
-              bf16_pitch=None, bn=0, out_f32=None, out_bf16=None, stats=None):
+              bf16_pitch=None, bn=0, out_f32=None, out_bf16=None, stats=None, split_out=True):
     """x: bf16 [N,H,W,pitch]. Returns (out_f32 or None, out_bf16 or None) as NHWC tensors; with stats=(G, eps) the
     GroupNorm statistics [N, G, 2] of the output are produced by the epilogue and returned as a third value
     (None when the geometry does not allow it)."""
@@ -200,7 +200,7 @@ def conv_gemm(x, C_in, wp, *, kind, R, Cout, flip=False, bias=None, residual=Non
         assert pitch_of(x_lo) == pitch
         a.x_lo = x_lo.data_ptr()
         a.w_lo = wp.lo.data_ptr()
-    if out_bf16 is not None and SPLIT_BF16[0] and want_bf16:
+    if out_bf16 is not None and SPLIT_BF16[0] and want_bf16 and split_out:
         out_lo = torch.empty_like(out_bf16)
         a.out_bf16_lo = out_lo.data_ptr()
     part = None
@@ -326,6 +326,7 @@ def gn_act_fwd(x, stats, gamma, beta, G, act):
 
 def gn_act_bwd(x, stats, gamma, beta, da, gres, G, act, dgamma, dbeta):
     N, H, W, Cc = x.shape
+    da, gres = hi_of(da), hi_of(gres)
     assert da.shape[-1] == Cc and da.dtype == torch.bfloat16
     dx = torch.empty((N, H, W, Cc), dtype=torch.bfloat16, device=x.device)
     ws = _workspace(lib.tvae_gn_bwd_workspace_bytes(N, H * W, Cc, G), x.device, "gn")
