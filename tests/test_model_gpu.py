@@ -401,3 +401,56 @@ def test_fp32_mode_forward_parity_1e4(capsys):
         print(f"\n[fp32 mode] forward rel-L2 (mean, logvar, recon): tiny {tuple(f'{v:.2e}' for v in e_tiny)}, "
               f"default B=2 {tuple(f'{v:.2e}' for v in e_def)}")
     assert max(e_tiny) < 1e-4 and max(e_def) < 1e-4, (e_tiny, e_def)
+
+
+VARIANTS = {
+    # every knob get_model honours (src/model.py:713-742) that changes the executed program
+    "relu_l2loss": dict(act="relu", nll_loss_type="l2"),
+    "silu_two_blocks": dict(act="silu", num_res_blocks=2),
+    "attn_at_8": dict(attn_sizes=[8]),
+    "no_mid_attn_wide": dict(mid_attn=False, chs=[64, 32, 32], shape=(12, 32, 32)),
+    "no_affine": dict(norm_affine=False),
+    "two_levels_odd_batch": dict(chs=[32, 32], shape=(20, 16, 16)),
+}
+
+
+@pytest.mark.parametrize("name", sorted(VARIANTS))
+def test_config_variants_loss_and_grads_vs_oracle(name, capsys):
+    import tempo_vae_b200 as t
+    cfg = dict(orc.TINY_CFG, norm_affine=True)
+    cfg.update(VARIANTS[name])
+    B = 3 if "odd_batch" in name else 2
+    mp = params_for({**cfg})
+    mp["architecture_params"]["enc_dec_params"]["norm_affine"] = cfg["norm_affine"]
+    t.seed_all(11)
+    model = t.get_model(mp, torch.device("cuda"))
+    sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    orc.rerandomize_zero_init(sd, seed=4321)
+    model.load_state_dict(sd)
+    x = orc.structured_batch(B, cfg, seed=31)
+    hz = cfg["shape"][1] // 2 ** (len(cfg["chs"]) - 1)
+    eps = torch.randn((B, cfg["embed_dim"], hz, hz), generator=torch.Generator().manual_seed(8))
+    loss, metrics = model.get_loss(x.cuda(), eps=eps.cuda())
+    model.optimizer.zero_grad()
+    loss.backward()
+    grads, out = orc.grads_of(lambda leaves: orc.vae_loss(leaves, x, eps, cfg), sd)
+    assert abs(loss.item() - out["loss"].item()) / out["loss"].item() < 1e-4
+    assert abs(metrics["kl_loss"].item() - out["kl_loss"].item()) / out["kl_loss"].item() < 3e-2
+    assert abs(model.vae.last_pixel_mse().item() - out["pixel_mse"].item()) / out["pixel_mse"].item() < 2e-2
+    report = []
+    check_grads(model, grads, 4e-1, report, global_tol=1e-1, median_tol=1.2e-1)
+    with capsys.disabled():
+        print(f"\n[variant {name}] " + report[0])
+
+
+def test_unsupported_geometry_and_inputs_raise():
+    import tempo_vae_b200 as t
+    model = build(orc.TINY_CFG)
+    with pytest.raises(t.TvaeError):
+        model.vae.encode(torch.zeros(2, 20, 16, 16))                        # CPU tensor
+    with pytest.raises(t.TvaeError):
+        model.vae.encode(torch.zeros(2, 19, 16, 16, device="cuda"))         # wrong channel count
+    with pytest.raises(t.TvaeError):
+        model.vae.encode(torch.zeros(2, 20, 12, 12, device="cuda"))         # 12 is not a power of two / multiple of 128
+    z = torch.zeros(1, 4, 4, 4, device="cuda")
+    assert model.vae.decode(z).shape == (1, 20, 16, 16)                     # batch of one works
