@@ -430,3 +430,53 @@ def test_conv_split_bf16_fp32_mode(N, H, W, Cin, Cout, R):
                          bias=b)
     torch.cuda.synchronize()
     assert rel_err(of2[..., :Cout].permute(0, 3, 1, 2), ref) > 5e-4
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout,kind", [(3, 8, 8, 64, 1028, 0), (5, 4, 4, 32, 48, 0), (1, 64, 64, 512, 1028, 0),
+                                                 (3, 8, 8, 32, 16, 2), (3, 8, 8, 32, 48, 1)])
+def test_conv_epilogue_writes_stay_in_bounds(N, H, W, Cin, Cout, kind):
+    """compute-sanitizer is closed on this pool, so the masked epilogue (partial N tiles, rows past the last pixel,
+    pixel-shuffle scatter) is checked with guard bands: outputs are views into the middle of sentinel-filled
+    buffers and the sentinels must survive."""
+    o = ops()
+    g = torch.Generator(device="cuda").manual_seed(15)
+    x = bf16_round(torch.randn((N, Cin, H, W), device="cuda", generator=g))
+    if kind == 2:
+        w = bf16_round(torch.randn((Cin, Cout, 2, 2), device="cuda", generator=g))
+        wp, R, oH, oW = o.pack_weight(w, "up_fwd"), 2, 2 * H, 2 * W
+    elif kind == 1:
+        w = bf16_round(torch.randn((Cout, Cin, 2, 2), device="cuda", generator=g))
+        wp, R, oH, oW = o.pack_weight(w, "fwd"), 2, H // 2, W // 2
+    else:
+        w = bf16_round(torch.randn((Cout, Cin, 3, 3), device="cuda", generator=g))
+        wp, R, oH, oW = o.pack_weight(w, "fwd"), 3, H, W
+    pf, pb = o.round_up(Cout, 4), o.round_up(Cout, 8)
+    guard = 4096
+    n32, n16 = N * oH * oW * pf, N * oH * oW * pb
+    buf32 = torch.full((n32 + 2 * guard,), 12345.0, device="cuda")
+    buf16 = torch.full((n16 + 2 * guard,), 77.0, device="cuda", dtype=torch.bfloat16)
+    of = buf32[guard:guard + n32].view(N, oH, oW, pf)
+    ob = buf16[guard:guard + n16].view(N, oH, oW, pb)
+    o.conv_gemm(nhwc_bf16(x, o.round_up(Cin, 8)), Cin, wp, kind=kind, R=R, Cout=Cout, want_f32=True, want_bf16=True,
+                out_f32=of, out_bf16=ob)
+    torch.cuda.synchronize()
+    assert (buf32[:guard] == 12345.0).all() and (buf32[guard + n32:] == 12345.0).all()
+    assert (buf16[:guard] == 77.0).all() and (buf16[guard + n16:] == 77.0).all()
+    assert (of[..., Cout:] == 12345.0).all() and (ob[..., Cout:] == 77.0).all()      # pad lanes are never written
+    assert torch.isfinite(of[..., :Cout]).all() and (of[..., :Cout] != 12345.0).any()
+
+
+def test_wgrad_writes_stay_in_bounds():
+    o = ops()
+    g = torch.Generator(device="cuda").manual_seed(16)
+    N, H, W, Cin, Cout = 3, 8, 8, 20, 36
+    x = bf16_round(torch.randn((N, Cin, H, W), device="cuda", generator=g))
+    dy = bf16_round(torch.randn((N, Cout, H, W), device="cuda", generator=g))
+    n = Cout * Cin * 9
+    buf = torch.full((n + 2048,), 555.0, device="cuda")
+    grad = buf[1024:1024 + n].view(Cout, Cin, 3, 3)
+    o.wgrad_gemm(nhwc_bf16(dy, o.round_up(Cout, 8)), Cout, nhwc_bf16(x, o.round_up(Cin, 8)), Cin, kind=0, R=3, grad=grad)
+    torch.cuda.synchronize()
+    assert (buf[:1024] == 555.0).all() and (buf[1024 + n:] == 555.0).all()
+    ref = torch.nn.grad.conv2d_weight(x, (Cout, Cin, 3, 3), dy, padding=1)
+    assert rel_err(grad, ref) < 2e-3
