@@ -152,6 +152,15 @@ int32_t tvae_attn_bwd(const float* q, const float* k, const float* v, int32_t pi
                       const float* d_out, const float* lse, int32_t B, int32_t T, int32_t C, int32_t heads,
                       void* dqkv_bf16, float* workspace, tvae_stream_t stream);
 
+/* Tensor-core (mma.sync TF32, fp32 accumulate) variants of the two calls above for head dimension 32 (C == 32*heads);
+ * same arguments, same layouts, any T. ~5e-4 relative error on the logits; the exact kernels above stay the path
+ * for other head sizes and for the fp32 mode. */
+int32_t tvae_attn_fwd_tc(const float* q, const float* k, const float* v, int32_t pitch, int32_t B, int32_t T,
+                         int32_t C, int32_t heads, void* out_bf16, float* out_f32, float* lse, tvae_stream_t stream);
+int32_t tvae_attn_bwd_tc(const float* q, const float* k, const float* v, int32_t pitch, const float* o,
+                         const float* d_out, const float* lse, int32_t B, int32_t T, int32_t C, int32_t heads,
+                         void* dqkv_bf16, float* workspace, tvae_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Reparameterisation + KL. Replaces DiagonalGaussianDistribution.__init__/sample/kl (src/model.py:47-75).
  * moments fp32 NHWC [B*HW][2Z] = (mean | logvar); logvar is clamped to [-30, 20].

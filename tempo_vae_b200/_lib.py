@@ -81,6 +81,8 @@ def _load():
         "tvae_colsum_bf16": (i32, [vp, i64, i32, i32, vp, vp, vp]),
         "tvae_attn_fwd": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp]),
         "tvae_attn_bwd": (i32, [vp, vp, vp, i32, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp]),
+        "tvae_attn_fwd_tc": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp]),
+        "tvae_attn_bwd_tc": (i32, [vp, vp, vp, i32, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp]),
         "tvae_reparam_fwd": (i32, [vp, vp, u64, u64, i32, i32, i32, vp, i32, vp, vp, vp, vp, vp]),
         "tvae_reparam_bwd": (i32, [vp, vp, vp, vp, vp, f32, i32, i32, i32, vp, vp]),
         "tvae_nll_workspace_bytes": (i64, []),

@@ -33,7 +33,7 @@ KERNEL_LAUNCHES = [0]   # kernels of libtvae_b200.so enqueued through this modul
 _KERNELS_PER_CALL = {
     "tvae_pack_weight": 1, "tvae_conv_gemm": 1, "tvae_wgrad_gemm": 2, "tvae_nchw_f32_to_nhwc_bf16": 1,
     "tvae_nhwc_f32_to_nchw_f32": 1, "tvae_nhwc_bf16_to_nchw_f32": 1, "tvae_f32_to_bf16": 1, "tvae_gn_stats": 1,
-    "tvae_gn_act_fwd": 1, "tvae_gn_stats_finalize": 1, "tvae_gn_act_bwd": 3, "tvae_colsum_bf16": 2, "tvae_attn_fwd": 1, "tvae_attn_bwd": 2,
+    "tvae_gn_act_fwd": 1, "tvae_gn_stats_finalize": 1, "tvae_gn_act_bwd": 3, "tvae_colsum_bf16": 2, "tvae_attn_fwd": 1, "tvae_attn_bwd": 2, "tvae_attn_fwd_tc": 1, "tvae_attn_bwd_tc": 2,
     "tvae_reparam_fwd": 1, "tvae_reparam_bwd": 1, "tvae_nll_fwd": 2, "tvae_vae_loss_finalize": 1,
     "tvae_l2head_loss_fwd": 1, "tvae_l2head_loss_bwd": 1, "tvae_l2head_finalize": 1, "tvae_sumsq": 2, "tvae_adamw": 1,
 }
@@ -345,6 +345,13 @@ def colsum_bf16(x, Cc, out):
 
 
 # ----------------------------------------------------------------------------------------------- attention
+ATTN_TENSOR_CORES = [True]     # TF32 mma.sync kernels for head dim 32; the exact fp32 kernels otherwise / in fp32 mode
+
+
+def attn_uses_tensor_cores(Cc, heads):
+    return ATTN_TENSOR_CORES[0] and not SPLIT_BF16[0] and Cc == 32 * heads
+
+
 def attn_fwd(qkv, Cc, heads, B, T):
     """qkv: fp32 [B*T (any leading shape), 3C]. Returns (o_bf16, o_f32, lse)."""
     pitch = qkv.shape[-1]
@@ -353,8 +360,12 @@ def attn_fwd(qkv, Cc, heads, B, T):
     o_f32 = torch.empty((B * T, Cc), dtype=torch.float32, device=dev)
     lse = torch.empty((B, heads, T), dtype=torch.float32, device=dev)
     base = qkv.data_ptr()
-    check(lib.tvae_attn_fwd(base, base + 4 * Cc, base + 8 * Cc, pitch, B, T, Cc, heads, o_bf16.data_ptr(),
-                            o_f32.data_ptr(), lse.data_ptr(), _stream()), "tvae_attn_fwd")
+    if attn_uses_tensor_cores(Cc, heads):
+        check(lib.tvae_attn_fwd_tc(base, base + 4 * Cc, base + 8 * Cc, pitch, B, T, Cc, heads, o_bf16.data_ptr(),
+                                   o_f32.data_ptr(), lse.data_ptr(), _stream()), "tvae_attn_fwd_tc")
+    else:
+        check(lib.tvae_attn_fwd(base, base + 4 * Cc, base + 8 * Cc, pitch, B, T, Cc, heads, o_bf16.data_ptr(),
+                                o_f32.data_ptr(), lse.data_ptr(), _stream()), "tvae_attn_fwd")
     if SPLIT_BF16[0]:
         o_bf16 = f32_to_bf16(o_f32)
     return o_bf16, o_f32, lse
@@ -366,9 +377,10 @@ def attn_bwd(qkv, o_f32, d_out, lse, Cc, heads, B, T):
     dqkv = torch.empty((B * T, 3 * Cc), dtype=torch.bfloat16, device=dev)
     ws = torch.empty((B * heads * T,), dtype=torch.float32, device=dev)
     base = qkv.data_ptr()
-    check(lib.tvae_attn_bwd(base, base + 4 * Cc, base + 8 * Cc, pitch, o_f32.data_ptr(), d_out.data_ptr(),
-                            lse.data_ptr(), B, T, Cc, heads, dqkv.data_ptr(), ws.data_ptr(), _stream()),
-          "tvae_attn_bwd")
+    fn, name = (lib.tvae_attn_bwd_tc, "tvae_attn_bwd_tc") if attn_uses_tensor_cores(Cc, heads) else \
+        (lib.tvae_attn_bwd, "tvae_attn_bwd")
+    check(fn(base, base + 4 * Cc, base + 8 * Cc, pitch, o_f32.data_ptr(), d_out.data_ptr(), lse.data_ptr(), B, T, Cc,
+             heads, dqkv.data_ptr(), ws.data_ptr(), _stream()), name)
     return dqkv
 
 

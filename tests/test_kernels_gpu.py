@@ -230,9 +230,21 @@ def test_colsum(rows, C, pitch):
     assert rel_err(out, x[:, :C].float().sum(0)) < 1e-4
 
 
-@pytest.mark.parametrize("B,T,C,heads", [(3, 256, 128, 4), (2, 64, 16, 4), (1, 1024, 128, 4), (2, 100, 32, 4)])
-def test_attention_fwd_bwd(B, T, C, heads):
+@pytest.mark.parametrize("B,T,C,heads,tc", [(3, 256, 128, 4, True), (2, 64, 16, 4, False), (1, 1024, 128, 4, True),
+                                            (2, 100, 32, 4, False), (2, 100, 128, 4, True), (1, 700, 64, 2, True),
+                                            (3, 256, 128, 4, False)])
+def test_attention_fwd_bwd(B, T, C, heads, tc):
+    """tc=True: TF32 tensor-core kernels (head dim 32), tolerance 3e-3 of the max; tc=False: exact fp32 kernels, 1e-4."""
     o = ops()
+    o.ATTN_TENSOR_CORES[0] = tc
+    assert o.attn_uses_tensor_cores(C, heads) == (tc and C == 32 * heads)
+    try:
+        _attention_case(o, B, T, C, heads, 3e-3 if tc else 1e-4)
+    finally:
+        o.ATTN_TENSOR_CORES[0] = True
+
+
+def _attention_case(o, B, T, C, heads, tol):
     g = torch.Generator(device="cuda").manual_seed(8)
     qkv = torch.randn((B * T, 3 * C), device="cuda", generator=g).requires_grad_(True)
     hd = C // heads
@@ -252,7 +264,8 @@ def test_attention_fwd_bwd(B, T, C, heads):
     ref.backward(d_out)
     ob, of, lse = o.attn_fwd(qkv.detach(), C, heads, B, T)
     torch.cuda.synchronize()
-    assert rel_err(of, ref.detach()) < 1e-4
+    assert rel_err(of, ref.detach()) < tol
+    assert rel_err(ob.float(), ref.detach()) < 1e-2
     dqkv = o.attn_bwd(qkv.detach(), of, d_out, lse, C, heads, B, T)
     torch.cuda.synchronize()
     assert rel_err(dqkv.float(), qkv.grad) < 1e-2  # bf16 output
