@@ -168,6 +168,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        from tempo_vae_b200.parallel import bind_to_gpu_numa
+        bind_to_gpu_numa(local)          # pinned host batches on the GPU's own NUMA node
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
     shape = (1028, 64, 64)

@@ -23,6 +23,28 @@ import torch
 import torch.distributed as dist
 
 
+def bind_to_gpu_numa(device_index: int) -> bool:
+    """Pin the calling process to the CPU cores that are local to GPU `device_index` (NVML's ideal CPU affinity), so
+    that pinned host buffers allocated afterwards land on the GPU's NUMA node and H2D copies of 8 ranks do not all
+    cross the inter-socket link. Best effort: returns False when NVML or the affinity call is unavailable."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        ncpu = os.cpu_count() or 1
+        words = (ncpu + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [64 * i + b for i, w in enumerate(mask) for b in range(64) if (w >> b) & 1]
+        cpus = [c for c in cpus if c < ncpu]
+        if not cpus:
+            return False
+        os.sched_setaffinity(0, cpus)
+        return True
+    except Exception:  # noqa: BLE001
+        return False
+
+
 class GradBucketer:
     """Device-agnostic bucket bookkeeping over a flat gradient buffer (also exercised on CPU with gloo)."""
 
