@@ -121,7 +121,7 @@ gn_bwd_apply_fast_kernel(const float* __restrict__ x, const float* __restrict__ 
 
 // Stage A1: grid (row chunks, N) like the apply kernel (full 2 KB rows => long DRAM bursts): per-channel partial sums
 // of dy and dy*xhat over the chunk's rows -> part[n][chunk][2][C].
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 gn_bwd_rowsum_fast_kernel(const float* __restrict__ x, const float* __restrict__ stats,
                           const float* __restrict__ gamma, const float* __restrict__ beta,
                           const __nv_bfloat16* __restrict__ da, int HW, int C, int G, int act, int rpb,
@@ -132,48 +132,34 @@ gn_bwd_rowsum_fast_kernel(const float* __restrict__ x, const float* __restrict__
   const int c = u << 3, n = blockIdx.y;
   const int sg = n * G + c / (C / G);
   const float mean = stats[2 * sg], rstd = stats[2 * sg + 1];
-  float gm[8], bt[8], s1[8], s2[8];
-  load8(gamma + c, gm);
-  load8(beta + c, bt);
+  // y = x*sc + sh (sc = gamma*rstd, sh = beta - mean*sc); sum(dy*xhat) = rstd*(sum(dy*x) - mean*sum(dy)) is formed
+  // once per thread at the end, so the loop body is one FMA for y, act', and two accumulations per element
+  float sc[8], sh[8], s1[8], s2[8];
+  load8(gamma + c, sc);
+  load8(beta + c, sh);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+  for (int j = 0; j < 8; ++j) {
+    sc[j] *= rstd;
+    sh[j] = fmaf(-mean, sc[j], sh[j]);
+    s1[j] = 0.f; s2[j] = 0.f;
+  }
   const int r0 = blockIdx.x * rpb;
   const int r1 = min(r0 + rpb, HW);
   const long long base = (long long)n * HW * C + c;
-  int r = r0 + lane;
-  for (; r + lanes < r1; r += 2 * lanes) {
-    float xa[8], da_[8], xb[8], db_[8];
-    load8(x + base + (long long)r * C, xa);
-    load8_bf16(da + base + (long long)r * C, da_);
-    load8(x + base + (long long)(r + lanes) * C, xb);
-    load8_bf16(da + base + (long long)(r + lanes) * C, db_);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float xh = (xa[j] - mean) * rstd;
-      float dy = da_[j];
-      if (act) dy *= act_grad_fast(fmaf(xh, gm[j], bt[j]), act);
-      s1[j] += dy;
-      s2[j] = fmaf(dy, xh, s2[j]);
-      const float xh2 = (xb[j] - mean) * rstd;
-      float dy2 = db_[j];
-      if (act) dy2 *= act_grad_fast(fmaf(xh2, gm[j], bt[j]), act);
-      s1[j] += dy2;
-      s2[j] = fmaf(dy2, xh2, s2[j]);
-    }
-  }
-  if (r < r1) {
+  for (int r = r0 + lane; r < r1; r += lanes) {
     float xa[8], da_[8];
     load8(x + base + (long long)r * C, xa);
     load8_bf16(da + base + (long long)r * C, da_);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float xh = (xa[j] - mean) * rstd;
       float dy = da_[j];
-      if (act) dy *= act_grad_fast(fmaf(xh, gm[j], bt[j]), act);
+      if (act) dy *= act_grad_fast(fmaf(xa[j], sc[j], sh[j]), act);
       s1[j] += dy;
-      s2[j] = fmaf(dy, xh, s2[j]);
+      s2[j] = fmaf(dy, xa[j], s2[j]);
     }
   }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s2[j] = (s2[j] - mean * s1[j]) * rstd;     // sum dy*x  ->  sum dy*xhat
   float* mine = sm + (size_t)threadIdx.x * 16;
 #pragma unroll
   for (int j = 0; j < 8; ++j) { mine[j] = s1[j]; mine[8 + j] = s2[j]; }
