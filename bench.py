@@ -303,6 +303,7 @@ def run_ours(args):
                 "ms_per_step": e2e_ms, "api": "Trainer.train_step over DevicePrefetcher (pinned host batches)"},
         "gpu_launches": launches,
         "host_enqueue_ms_per_step": host_enqueue_ms,
+        "peak_hbm_gb": torch.cuda.max_memory_allocated(dev) / 1e9,
         "clocks": clocks,
         "final_metrics": final,
     }
