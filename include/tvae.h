@@ -88,6 +88,11 @@ typedef struct {
   float* workspace;
   float* grad;          /* fp32 [Cm][Cn][taps] */
   int32_t accumulate;   /* 0: overwrite grad, 1: add into it */
+  /* kind 0 only. flip = 1 exchanges the operand roles: P = x (dense, Cm = Cin), Q = dY read at pixel (-) tap
+   * (Cn = Cout); grad is then written as [Cn][Cm][taps], i.e. still the Conv2d OIHW layout. Lets the 1028-channel
+   * side of encoder.conv_in sit on the GEMM's M dimension (9 row tiles, 11 % padding) instead of its N dimension
+   * (5 column tiles of 208 with 23 % wasted operand loads). */
+  int32_t flip;
 } tvae_wgrad_args;
 int32_t tvae_wgrad_gemm(const tvae_wgrad_args* args, tvae_stream_t stream);
 int64_t tvae_wgrad_workspace_bytes(int32_t Cm, int32_t Cn, int32_t ntaps, int32_t splits);

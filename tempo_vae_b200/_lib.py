@@ -50,6 +50,7 @@ class WgradArgs(C.Structure):
         ("workspace", C.c_void_p),
         ("grad", C.c_void_p),
         ("accumulate", C.c_int32),
+        ("flip", C.c_int32),
     ]
 
 

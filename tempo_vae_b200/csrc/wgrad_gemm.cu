@@ -213,16 +213,26 @@ wgrad_gemm_kernel(const __grid_constant__ WgradMaps maps, const __grid_constant_
 }
 
 // grad[m][n][tap] (+)= sum_s part[s][m][tap][n]
+// grad[m][n][tap] (+)= sum_s part[s][m][tap][n]; with `swapped` the GEMM ran with the operand roles exchanged
+// (part[s][n'][tap][m'] with m' = n, n' = m of the parameter), which only changes where an element is read from
 __global__ void wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ grad, int cm, int cn,
-                                    int ntaps, int cn_pitch, int splits, int accumulate) {
+                                    int ntaps, int cn_pitch, int splits, int accumulate, int swapped) {
+  // cm, cn, cn_pitch describe the GEMM (rows, columns, column pitch of the partials)
   const long long total = (long long)cm * cn * ntaps;
   const long long split_stride = (long long)cm * ntaps * cn_pitch;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int tap = (int)(i % ntaps);
-    const long long mn = i / ntaps;
-    const int n = (int)(mn % cn);
-    const long long m = mn / cn;
+    const long long rc = i / ntaps;
+    long long m;
+    int n;
+    if (!swapped) {            // parameter [cm][cn][tap]
+      n = (int)(rc % cn);
+      m = rc / cn;
+    } else {                   // parameter [cn][cm][tap]
+      m = rc % cm;
+      n = (int)(rc / cm);
+    }
     const float* src = part + (m * ntaps + tap) * cn_pitch + n;
     float s = 0.f;
     for (int k = 0; k < splits; ++k) s += src[k * split_stride];
@@ -263,6 +273,7 @@ extern "C" int32_t tvae_wgrad_gemm(const tvae_wgrad_args* a, cudaStream_t stream
   TVAE_CHECK(a->kind >= 0 && a->kind <= 2, "tvae_wgrad_gemm: bad kind");
   TVAE_CHECK(a->p_pitch % 8 == 0 && a->q_pitch % 8 == 0, "tvae_wgrad_gemm: pitches must be multiples of 8");
   TVAE_CHECK(a->splits >= 1, "tvae_wgrad_gemm: splits must be >= 1");
+  TVAE_CHECK(!a->flip || a->kind == 0, "tvae_wgrad_gemm: flip (exchanged operand roles) is for stride-1 convs only");
 
   WgradMaps maps;
   WgradParams p;
@@ -297,6 +308,7 @@ extern "C" int32_t tvae_wgrad_gemm(const tvae_wgrad_args* a, cudaStream_t stream
     p.ntaps = a->R * a->R;
     for (int t = 0; t < p.ntaps; ++t) {
       p.dh[t] = t / a->R - a->R / 2; p.dw[t] = t % a->R - a->R / 2; p.qmap[t] = 0;
+      if (a->flip) { p.dh[t] = -p.dh[t]; p.dw[t] = -p.dw[t]; }
     }
     uint64_t dims[4] = {(uint64_t)a->Cn, (uint64_t)gW, (uint64_t)gH, (uint64_t)a->N};
     uint64_t strides[3] = {qp, qp * gW, qp * gW * gH};
@@ -327,7 +339,7 @@ extern "C" int32_t tvae_wgrad_gemm(const tvae_wgrad_args* a, cudaStream_t stream
   int rgrid = (int)((total_out + 255) / 256);
   if (rgrid > 148 * 16) rgrid = 148 * 16;
   wgrad_reduce_kernel<<<rgrid, 256, 0, stream>>>(p.part, a->grad, a->Cm, a->Cn, p.ntaps, p.cn_pitch, p.splits,
-                                                a->accumulate);
+                                                a->accumulate, a->flip);
   TVAE_CUDA(cudaGetLastError());
   return 0;
 }

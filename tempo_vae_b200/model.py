@@ -255,6 +255,9 @@ def conv_bwd(mod, dy_bf16, x_bf16, Cin, *, dgrad=None, dgrad_residual=None, bias
         def wg(dst):
             if kind == 2:   # ConvTranspose2d [Cin][Cout][2][2]: P = x (coarse), Q = dy (fine)
                 ops.wgrad_gemm(x_bf16, Cin, dy_bf16, Cout, kind=1, R=2, grad=dst)
+            elif kind == 0 and Cin > 256 and Cin % 256 and Cout % 128 == 0:
+                # a wide, awkward channel count (1028) goes on the GEMM's M side: operand roles exchanged
+                ops.wgrad_gemm(x_bf16, Cin, dy_bf16, Cout, kind=0, R=R, grad=dst, flip=True)
             else:
                 ops.wgrad_gemm(dy_bf16, Cout, x_bf16, Cin, kind=kind, R=R, grad=dst)
         _write_grad(w, wg)

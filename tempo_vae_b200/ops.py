@@ -243,8 +243,9 @@ def _workspace(nbytes, device, key="ws"):
     return buf
 
 
-def wgrad_gemm(p, Cm, q, Cn, *, kind, R, grad, accumulate=False, splits=0):
-    """grad[m][n][tap] (+)= sum_pixels p[pixel][m] * q[pixel (+) tap][n]; p: bf16 [N,H,W,pitch] (the dense grid)."""
+def wgrad_gemm(p, Cm, q, Cn, *, kind, R, grad, accumulate=False, splits=0, flip=False):
+    """grad[m][n][tap] (+)= sum_pixels p[pixel][m] * q[pixel (+) tap][n]; p: bf16 [N,H,W,pitch] (the dense grid).
+    flip=True (stride-1 only): p = x, q = dY read at pixel (-) tap, grad written as [n][m][tap] (see include/tvae.h)."""
     p, q = hi_of(p), hi_of(q)
     N, H, W, _ = p.shape
     pp = pitch_of(p)
@@ -259,7 +260,7 @@ def wgrad_gemm(p, Cm, q, Cn, *, kind, R, grad, accumulate=False, splits=0):
     a.q = q.data_ptr(); a.q_pitch = pitch_of(q); a.Cn = Cn
     a.N, a.H, a.W = N, H, W
     a.kind, a.R, a.splits = kind, R, splits
-    a.workspace = ws.data_ptr(); a.grad = grad.data_ptr(); a.accumulate = int(accumulate)
+    a.workspace = ws.data_ptr(); a.grad = grad.data_ptr(); a.accumulate = int(accumulate); a.flip = int(flip)
     prof = PROFILE.get("wgrad")
     if prof is not None and prof["match"](N * H * W, Cm, Cn, kind, R):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -493,3 +493,17 @@ def test_wgrad_writes_stay_in_bounds():
     assert (buf[:1024] == 555.0).all() and (buf[1024 + n:] == 555.0).all()
     ref = torch.nn.grad.conv2d_weight(x, (Cout, Cin, 3, 3), dy, padding=1)
     assert rel_err(grad, ref) < 2e-3
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout,R", [(2, 16, 16, 300, 128, 3), (1, 64, 64, 1028, 512, 3), (2, 16, 16, 260, 128, 1)])
+def test_wgrad_exchanged_operand_roles(N, H, W, Cin, Cout, R):
+    o = ops()
+    g = torch.Generator(device="cuda").manual_seed(17)
+    x = bf16_round(torch.randn((N, Cin, H, W), device="cuda", generator=g))
+    dy = bf16_round(torch.randn((N, Cout, H, W), device="cuda", generator=g))
+    ref = torch.nn.grad.conv2d_weight(x, (Cout, Cin, R, R), dy, padding=R // 2)
+    grad = torch.full((Cout, Cin, R, R), float("nan"), device="cuda")
+    o.wgrad_gemm(nhwc_bf16(x, o.round_up(Cin, 8)), Cin, nhwc_bf16(dy, o.round_up(Cout, 8)), Cout, kind=0, R=R, grad=grad,
+                 flip=True)
+    torch.cuda.synchronize()
+    assert rel_err(grad, ref) < 2e-3
