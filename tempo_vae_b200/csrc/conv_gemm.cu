@@ -31,7 +31,8 @@ constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int STAGES = 4;
 constexpr int NTHREADS = 192;                    // warp0: TMA, warp1: MMA + TMEM alloc, warps 2-5: epilogue
 constexpr int TMEM_COLS = 512;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*stats*/;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*stats*/ +
+                           8192 /*GN-backward column sums*/;
 
 struct ConvMaps {
   CUtensorMap a[4];
@@ -61,7 +62,30 @@ struct ConvParams {
   // fused GroupNorm statistics of the output: per-tile partial (sum, sum of squares) per group
   float* stats_part;   // [slots][G][2], slot = m_tile (x4 + tap for the transposed conv); NULL = off
   int gs, G;           // group size (multiple of 16, divides BN), number of groups
+  // fused first stage of the GroupNorm(+activation) BACKWARD that consumes this dgrad's output `da`:
+  // per 128-pixel tile and channel, sum(dy) and sum(dy * x) with dy = bf16(da) * act'(gamma*xhat + beta)
+  const float* gnb_x;        // pre-norm fp32 tensor (pitch = Cout of this GEMM), NULL = off
+  const float* gnb_stats;    // [N][G][2] (mean, rstd)
+  const float* gnb_gamma;
+  const float* gnb_beta;
+  float* gnb_part;           // [m_tiles][2][Cout]
+  int gnb_act, gnb_gs, gnb_G, gnb_hw;
 };
+
+// Warp reduce-scatter of 32 per-lane values: afterwards lane l holds sum over lanes of v[l] (31 shuffles).
+__device__ __forceinline__ float warp_reduce_scatter32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int ofs = 16; ofs >= 1; ofs >>= 1) {
+    const bool hi = (lane & ofs) != 0;
+#pragma unroll
+    for (int i = 0; i < ofs; ++i) {
+      const float send = hi ? v[i] : v[i + ofs];
+      const float keep = hi ? v[i + ofs] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, ofs);
+    }
+  }
+  return v[0];
+}
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ ConvParams p) {
@@ -75,6 +99,7 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float2* stat_sm = reinterpret_cast<float2*>(smem + STAGES * STAGE_BYTES + 256);   // [2 acc stages][4 warps][16 groups]
+  float* colacc = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256 + 1024);  // [4 warps][16 chunks][32]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -196,6 +221,9 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * 256u;
       const bool do_stats = p.stats_part != nullptr;
       float st1 = 0.f, st2 = 0.f;
+      const bool do_gnb = p.gnb_x != nullptr;
+      const int gnb_n = do_gnb ? (int)(((long long)mt * BM) / p.gnb_hw) : 0;   // one image per tile (host-checked)
+      float gsum[32];
       for (int c = 0; c < p.bn; c += 16) {
         uint32_t r[16];
         tmem_ld16(taddr + (uint32_t)c, r);
@@ -231,6 +259,31 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
               st2 = fmaf(v[j], v[j], st2);
             }
           }
+          if (do_gnb) {     // full chunks guaranteed by the host (Cout % 16 == 0)
+            const int sg = gnb_n * p.gnb_G + col / p.gnb_gs;
+            const float mean = __ldg(p.gnb_stats + 2 * sg), rstd = __ldg(p.gnb_stats + 2 * sg + 1);
+            const float* xp = p.gnb_x + opix * p.n_valid + col;
+#pragma unroll
+            for (int j4 = 0; j4 < 16; j4 += 4) {
+              const float4 xv = *reinterpret_cast<const float4*>(xp + j4);
+              const float4 gm = __ldg(reinterpret_cast<const float4*>(p.gnb_gamma + col + j4));
+              const float4 bt = __ldg(reinterpret_cast<const float4*>(p.gnb_beta + col + j4));
+              const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+              const float gs4[4] = {gm.x, gm.y, gm.z, gm.w};
+              const float bs4[4] = {bt.x, bt.y, bt.z, bt.w};
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) {
+                const int j = j4 + jj;
+                const float sc = gs4[jj] * rstd;
+                const float y = fmaf(xs[jj], sc, fmaf(-mean, sc, bs4[jj]));
+                float dy = __bfloat162float(__float2bfloat16(v[j]));    // what the apply kernel will read back
+                if (p.gnb_act == 1) dy *= gelu_grad_fast(y);
+                else if (p.gnb_act) dy *= act_grad_f(y, p.gnb_act);
+                gsum[j] = dy;
+                gsum[16 + j] = dy * xs[jj];
+              }
+            }
+          }
           if (p.out_f32) {
             float* op = p.out_f32 + opix * p.ld_f32 + col;
             if (full) {
@@ -263,6 +316,14 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
             }
           }
         }
+        if (do_gnb) {
+          if (!(row_ok && col < p.n_valid)) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) gsum[j] = 0.f;
+          }
+          const float tot = warp_reduce_scatter32(gsum, lane);   // lane l: column (l & 15), l < 16: sum dy, else sum dy*x
+          colacc[(q * 16 + (c >> 4)) * 32 + lane] = tot;
+        }
         if (do_stats && ((c + 16) % p.gs) == 0) {   // a group's columns are complete: reduce over the warp's 32 rows
           const float w1 = warp_sum(st1), w2 = warp_sum(st2);
           if (lane == 0) stat_sm[(as * 4 + q) * 16 + c / p.gs] = make_float2(w1, w2);
@@ -287,6 +348,19 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
             dst[0] = s1; dst[1] = s2;
           }
         }
+      }
+      if (do_gnb) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int nch = p.bn >> 4;
+        for (int i = row; i < nch * 32; i += 128) {          // (chunk, value) pairs of this tile
+          const int ch = i >> 5, l = i & 31;
+          const float t4 = colacc[(0 * 16 + ch) * 32 + l] + colacc[(1 * 16 + ch) * 32 + l] +
+                           colacc[(2 * 16 + ch) * 32 + l] + colacc[(3 * 16 + ch) * 32 + l];
+          const int ccol = col0 + ch * 16 + (l & 15);
+          if (ccol < p.n_valid)
+            p.gnb_part[((long long)mt * 2 + (l >> 4)) * p.n_valid + ccol] = t4;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");       // colacc is reused by the next tile
       }
       tc_fence_before();
       __syncwarp();
@@ -439,6 +513,19 @@ extern "C" int32_t tvae_conv_gemm(const tvae_conv_args* a, cudaStream_t stream) 
                "tvae_conv_gemm: fused statistics need a group size that is a multiple of 16 and divides the N tile");
     TVAE_CHECK(p.bnimg == 1 && (long long)gH * gW % BM == 0,
                "tvae_conv_gemm: fused statistics need at least 128 pixels per image");
+  }
+  p.gnb_x = a->gnb_x;
+  if (p.gnb_x) {
+    TVAE_CHECK(a->gnb_stats && a->gnb_gamma && a->gnb_beta && a->gnb_part, "tvae_conv_gemm: incomplete gnb_* arguments");
+    TVAE_CHECK(a->kind != 2 && a->out_bf16 && a->Cout % 16 == 0 && a->gnb_groups > 0 && a->Cout % a->gnb_groups == 0 &&
+                   (a->Cout / a->gnb_groups) % 16 == 0,
+               "tvae_conv_gemm: fused GroupNorm-backward sums need a dense bf16 output and 16-aligned groups");
+    TVAE_CHECK(p.bnimg == 1 && (long long)gH * gW % BM == 0,
+               "tvae_conv_gemm: fused GroupNorm-backward sums need at least 128 pixels per image");
+    TVAE_CHECK(((reinterpret_cast<uintptr_t>(a->gnb_x) | reinterpret_cast<uintptr_t>(a->gnb_gamma) |
+                 reinterpret_cast<uintptr_t>(a->gnb_beta)) & 15) == 0, "tvae_conv_gemm: gnb_* pointers must be 16-byte aligned");
+    p.gnb_stats = a->gnb_stats; p.gnb_gamma = a->gnb_gamma; p.gnb_beta = a->gnb_beta; p.gnb_part = a->gnb_part;
+    p.gnb_act = a->gnb_act; p.gnb_G = a->gnb_groups; p.gnb_gs = a->Cout / a->gnb_groups; p.gnb_hw = gH * gW;
   }
   p.out_f32 = a->out_f32; p.ld_f32 = a->out_f32_pitch;
   p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(a->out_bf16); p.ld_bf16 = a->out_bf16_pitch;

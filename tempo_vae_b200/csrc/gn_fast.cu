@@ -176,7 +176,7 @@ gn_bwd_rowsum_fast_kernel(const float* __restrict__ x, const float* __restrict__
 // Stage A2: one block per sample: S1/S2[n][c] = sum over chunks; group means m1 = mean(dy*gamma), m2 = mean(dy*gamma*xhat)
 __global__ void __launch_bounds__(256)
 gn_bwd_finalize_fast_kernel(const float* __restrict__ part, const float* __restrict__ gamma, int chunks, int HW, int C,
-                            int G, int N, float* __restrict__ ws) {
+                            int G, int N, float* __restrict__ ws, const float* __restrict__ raw_stats) {
   extern __shared__ float sm[];  // [2][C]
   const int n = blockIdx.x;
   const float* pn = part + (long long)n * chunks * 2 * C;
@@ -185,6 +185,10 @@ gn_bwd_finalize_fast_kernel(const float* __restrict__ part, const float* __restr
     for (int k = 0; k < chunks; ++k) {
       a += pn[(long long)k * 2 * C + c];
       b += pn[(long long)k * 2 * C + C + c];
+    }
+    if (raw_stats) {   // partials hold sum(dy * x): convert to sum(dy * xhat)
+      const int sg = n * G + c / (C / G);
+      b = (b - raw_stats[2 * sg] * a) * raw_stats[2 * sg + 1];
     }
     ws[(long long)n * C + c] = a;                     // S1 (sum dy)
     ws[((long long)N + n) * C + c] = b;               // S2 (sum dy*xhat)
@@ -265,8 +269,23 @@ int gn_act_bwd_fast(const float* x, const float* stats, const float* gamma, cons
   float* part = ws + 2ll * N * C + 2ll * N * G;
   gn_bwd_rowsum_fast_kernel<<<grid, 256, 256 * 16 * sizeof(float), stream>>>(x, stats, gamma, beta, da, HW, C, G, act,
                                                                             rpb, part);
-  gn_bwd_finalize_fast_kernel<<<N, 256, 2 * C * sizeof(float), stream>>>(part, gamma, chunks, HW, C, G, N, ws);
+  gn_bwd_finalize_fast_kernel<<<N, 256, 2 * C * sizeof(float), stream>>>(part, gamma, chunks, HW, C, G, N, ws, nullptr);
   gn_bwd_param_fast_kernel<<<(C + 31) / 32, 256, 0, stream>>>(ws, N, C, dgamma, dbeta);
+  gn_bwd_apply_fast_kernel<<<grid, 256, 0, stream>>>(x, stats, gamma, beta, da, gres, ws + 2ll * N * C, HW, C, G, act,
+                                                     rpb, dx);
+  return 0;
+}
+
+// backward with the per-tile column sums already produced by the dgrad epilogue (conv_gemm.cu, gnb_part)
+int gn_act_bwd_from_tiles_fast(const float* x, const float* stats, const float* gamma, const float* beta,
+                               const __nv_bfloat16* da, const __nv_bfloat16* gres, const float* tile_part, int N, int HW,
+                               int C, int G, int act, __nv_bfloat16* dx, float* dgamma, float* dbeta, float* ws,
+                               cudaStream_t stream) {
+  const int tiles = HW / 128;
+  gn_bwd_finalize_fast_kernel<<<N, 256, 2 * C * sizeof(float), stream>>>(tile_part, gamma, tiles, HW, C, G, N, ws, stats);
+  gn_bwd_param_fast_kernel<<<(C + 31) / 32, 256, 0, stream>>>(ws, N, C, dgamma, dbeta);
+  const int rpb = rows_per_block(HW);
+  dim3 grid((HW + rpb - 1) / rpb, N);
   gn_bwd_apply_fast_kernel<<<grid, 256, 0, stream>>>(x, stats, gamma, beta, da, gres, ws + 2ll * N * C, HW, C, G, act,
                                                      rpb, dx);
   return 0;
