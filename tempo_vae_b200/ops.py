@@ -333,11 +333,18 @@ def gn_act_fwd(x, stats, gamma, beta, G, act):
     return _pair(out, lo)
 
 
+# Measured at B=256 (round 1): with the sums in the epilogue a 512-channel dgrad launch takes 7 ms instead of 4 ms — four
+# single-issue epilogue warps need ~60 us per 128x256 tile for the extra x loads, GELU' and column reductions, three
+# times the MMA window — while the stand-alone rowsum kernel costs 0.9 ms. So the fusion is OFF by default; the
+# kernel path stays (and is tested) for a future epilogue with more warps.
+FUSE_GN_BWD = [False]
+
+
 def gn_bwd_fusable(Cc, G, HW, K):
-    """Can the dgrad that produces `da` also produce the GroupNorm-backward column sums in its epilogue?
-    (16-aligned groups, whole 128-pixel tiles per image, and a reduction long enough to hide the extra epilogue work)"""
-    return (G > 0 and Cc % G == 0 and (Cc // G) % 16 == 0 and (Cc // 8) <= 256 and 256 % (Cc // 8) == 0
-            and HW % 128 == 0 and Cc >= 256 and K >= 2048)
+    """Can (and should) the dgrad that produces `da` also produce the GroupNorm-backward column sums in its epilogue?
+    (16-aligned groups, whole 128-pixel tiles per image, a long reduction) — gated by FUSE_GN_BWD."""
+    return (FUSE_GN_BWD[0] and G > 0 and Cc % G == 0 and (Cc // G) % 16 == 0 and (Cc // 8) <= 256
+            and 256 % (Cc // 8) == 0 and HW % 128 == 0 and Cc >= 256 and K >= 2048)
 
 
 def gn_act_bwd(x, stats, gamma, beta, da, gres, G, act, dgamma, dbeta):
