@@ -67,17 +67,6 @@ typedef struct {
   const void* x_lo;
   const void* w_lo;
   void* out_bf16_lo;
-  /* Optional fusion of the first stage of tvae_gn_act_bwd into a data-gradient launch (kind 0/1) whose bf16 output is
-   * the `da` of a GroupNorm(+activation) backward: per 128-pixel tile t and channel c,
-   *   gnb_part[t][0][c] = sum dy,  gnb_part[t][1][c] = sum dy * x,   dy = bf16(da) * act'(gamma*xhat + beta),
-   * x = gnb_x (the norm's fp32 input, pitch Cout), statistics gnb_stats[N][gnb_groups][2]. The caller then runs
-   * tvae_gn_act_bwd_from_tiles instead of tvae_gn_act_bwd. Same geometry limits as stats_part. NULL = off. */
-  const float* gnb_x;
-  const float* gnb_stats;
-  const float* gnb_gamma;
-  const float* gnb_beta;
-  float* gnb_part;
-  int32_t gnb_groups, gnb_act;
 } tvae_conv_args;
 int32_t tvae_conv_gemm(const tvae_conv_args* args, tvae_stream_t stream);
 
@@ -147,13 +136,6 @@ int64_t tvae_gn_bwd_workspace_bytes(int32_t N, int32_t HW, int32_t C, int32_t G)
 int32_t tvae_gn_act_bwd(const float* x, const float* stats, const float* gamma, const float* beta, const void* da_bf16,
                         const void* gres_bf16, int32_t N, int32_t HW, int32_t C, int32_t G, int32_t act,
                         void* dx_bf16, float* dgamma, float* dbeta, float* workspace, tvae_stream_t stream);
-
-/* tvae_gn_act_bwd with its first stage (per-channel sums) already produced per 128-pixel tile by the dgrad epilogue
- * (tvae_conv_args.gnb_part, tiles_per_image = HW/128). workspace: tvae_gn_bwd_workspace_bytes(N, HW, C, G). */
-int32_t tvae_gn_act_bwd_from_tiles(const float* x, const float* stats, const float* gamma, const float* beta,
-                                   const void* da_bf16, const void* gres_bf16, const float* tile_part, int32_t N,
-                                   int32_t HW, int32_t C, int32_t G, int32_t act, void* dx_bf16, float* dgamma,
-                                   float* dbeta, float* workspace, tvae_stream_t stream);
 
 /* Column sums: out[c] = sum_rows x[row][c] (bias gradients). x bf16 [rows][pitch]; workspace rows_blocks*C floats:
  * tvae_colsum_workspace_bytes(rows, C). */

@@ -35,12 +35,6 @@ class ConvArgs(C.Structure):
         ("x_lo", C.c_void_p),
         ("w_lo", C.c_void_p),
         ("out_bf16_lo", C.c_void_p),
-        ("gnb_x", C.c_void_p),
-        ("gnb_stats", C.c_void_p),
-        ("gnb_gamma", C.c_void_p),
-        ("gnb_beta", C.c_void_p),
-        ("gnb_part", C.c_void_p),
-        ("gnb_groups", C.c_int32), ("gnb_act", C.c_int32),
     ]
 
 
@@ -84,7 +78,6 @@ def _load():
         "tvae_gn_act_fwd": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp]),
         "tvae_gn_bwd_workspace_bytes": (i64, [i32, i32, i32, i32]),
         "tvae_gn_act_bwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp]),
-        "tvae_gn_act_bwd_from_tiles": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp]),
         "tvae_colsum_workspace_bytes": (i64, [i64, i32]),
         "tvae_colsum_bf16": (i32, [vp, i64, i32, i32, vp, vp, vp]),
         "tvae_attn_fwd": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp]),

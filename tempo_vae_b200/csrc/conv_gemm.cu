@@ -9,7 +9,7 @@
 //   swizzle, which is exactly the canonical K-major UMMA operand layout.
 // * B (packed weights [rows][taps * c_pad] bf16, K-major) is a 2-D TMA box {64, BN}.
 // * One elected thread issues tcgen05.mma (M=128, N=BN<=256, K=16) into a double-buffered fp32 TMEM
-//   accumulator (2 x 256 columns); a 4-warp epilogue drains it with tcgen05.ld while the next tile's MMAs run.
+//   accumulator (2 x 256 columns); an 8-warp epilogue drains it with tcgen05.ld while the next tile's MMAs run.
 // * Persistent: grid = #SMs, static round-robin over (m_tile, n_tile) with n fastest so the CTAs that share
 //   an A tile run at the same time and hit L2.
 //
@@ -29,10 +29,9 @@ constexpr int A_STAGE_BYTES = BM * BK * 2;       // 16 KB
 constexpr int B_STAGE_BYTES = 256 * BK * 2;      // 32 KB (BN <= 256)
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int STAGES = 4;
-constexpr int NTHREADS = 192;                    // warp0: TMA, warp1: MMA + TMEM alloc, warps 2-5: epilogue
+constexpr int NTHREADS = 320;                    // warp0: TMA, warp1: MMA + TMEM alloc, warps 2-9: epilogue
 constexpr int TMEM_COLS = 512;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*stats*/ +
-                           8192 /*GN-backward column sums*/;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*stats*/;
 
 struct ConvMaps {
   CUtensorMap a[4];
@@ -62,30 +61,8 @@ struct ConvParams {
   // fused GroupNorm statistics of the output: per-tile partial (sum, sum of squares) per group
   float* stats_part;   // [slots][G][2], slot = m_tile (x4 + tap for the transposed conv); NULL = off
   int gs, G;           // group size (multiple of 16, divides BN), number of groups
-  // fused first stage of the GroupNorm(+activation) BACKWARD that consumes this dgrad's output `da`:
-  // per 128-pixel tile and channel, sum(dy) and sum(dy * x) with dy = bf16(da) * act'(gamma*xhat + beta)
-  const float* gnb_x;        // pre-norm fp32 tensor (pitch = Cout of this GEMM), NULL = off
-  const float* gnb_stats;    // [N][G][2] (mean, rstd)
-  const float* gnb_gamma;
-  const float* gnb_beta;
-  float* gnb_part;           // [m_tiles][2][Cout]
-  int gnb_act, gnb_gs, gnb_G, gnb_hw;
+  int split_chunk;     // first 16-column chunk handled by the second warp of each TMEM lane quarter
 };
-
-// Warp reduce-scatter of 32 per-lane values: afterwards lane l holds sum over lanes of v[l] (31 shuffles).
-__device__ __forceinline__ float warp_reduce_scatter32(float (&v)[32], int lane) {
-#pragma unroll
-  for (int ofs = 16; ofs >= 1; ofs >>= 1) {
-    const bool hi = (lane & ofs) != 0;
-#pragma unroll
-    for (int i = 0; i < ofs; ++i) {
-      const float send = hi ? v[i] : v[i + ofs];
-      const float keep = hi ? v[i + ofs] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, ofs);
-    }
-  }
-  return v[0];
-}
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ ConvParams p) {
@@ -99,7 +76,6 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float2* stat_sm = reinterpret_cast<float2*>(smem + STAGES * STAGE_BYTES + 256);   // [2 acc stages][4 warps][16 groups]
-  float* colacc = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256 + 1024);  // [4 warps][16 chunks][32]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -117,7 +93,7 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[i], 8);  // one arrive per epilogue warp
     }
     fence_mbar_init();
   }
@@ -196,9 +172,16 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (4 warps, 128 rows)
-    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    // ------------------------------------------------------------------ epilogue (8 warps: 128 rows x 2 column halves)
+    // TMEM lane quarter q = warp % 4 is a hardware rule; the two warps that share a quarter split the tile's
+    // 16-column chunks between them, and each one keeps the NEXT chunk's tcgen05.ld and residual loads in flight
+    // while it processes the current one: the epilogue is latency-bound (one in-order warp per scheduler), and for
+    // fp32-output layers it used to be as long as the MMA window itself.
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
+    const int nch = p.bn >> 4;
+    const int cbeg = half ? p.split_chunk : 0, cend = half ? nch : p.split_chunk;
     int as = 0;
     uint32_t aphase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -221,35 +204,57 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * 256u;
       const bool do_stats = p.stats_part != nullptr;
       float st1 = 0.f, st2 = 0.f;
-      const bool do_gnb = p.gnb_x != nullptr;
-      const int gnb_n = do_gnb ? (int)(((long long)mt * BM) / p.gnb_hw) : 0;   // one image per tile (host-checked)
-      float gsum[32];
-      for (int c = 0; c < p.bn; c += 16) {
-        uint32_t r[16];
-        tmem_ld16(taddr + (uint32_t)c, r);
-        tmem_ld_wait();
-        const int col = col0 + c;
-        if (row_ok && col < p.n_valid) {
-          float v[16];
+      const float* res_row = p.res ? p.res + opix * p.ld_res : nullptr;
+
+      uint32_t r[16];
+      float4 rs[4];
+      if (cbeg < cend) {                                    // prologue: first chunk in flight
+        tmem_ld16(taddr + (uint32_t)(cbeg << 4), r);
+        const int col = col0 + (cbeg << 4);
+        if (res_row && row_ok && col + 16 <= p.n_valid) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+          for (int j = 0; j < 4; ++j) rs[j] = *reinterpret_cast<const float4*>(res_row + col + 4 * j);
+        }
+      }
+      for (int ch = cbeg; ch < cend; ++ch) {
+        const int c = ch << 4;
+        const int col = col0 + c;
+        tmem_ld_wait();
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+        float rv[16];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { rv[4 * j] = rs[j].x; rv[4 * j + 1] = rs[j].y; rv[4 * j + 2] = rs[j].z; rv[4 * j + 3] = rs[j].w; }
+        if (ch + 1 < cend) {                                // next chunk: TMEM load + residual loads go out now
+          tmem_ld16(taddr + (uint32_t)(c + 16), r);
+          const int ncol = col + 16;
+          if (res_row && row_ok && ncol + 16 <= p.n_valid) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) rs[j] = *reinterpret_cast<const float4*>(res_row + ncol + 4 * j);
+          }
+        }
+        if (row_ok && col < p.n_valid) {
           const bool full = (col + 16 <= p.n_valid);
           if (p.bias) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (full || col + j < p.n_valid) v[j] += __ldg(p.bias + col + j);
-          }
-          if (p.res) {
-            const float* rp = p.res + opix * p.ld_res + col;
             if (full) {
 #pragma unroll
               for (int j = 0; j < 16; j += 4) {
-                const float4 x = *reinterpret_cast<const float4*>(rp + j);
-                v[j] += x.x; v[j + 1] += x.y; v[j + 2] += x.z; v[j + 3] += x.w;
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + col + j));
+                v[j] += bb.x; v[j + 1] += bb.y; v[j + 2] += bb.z; v[j + 3] += bb.w;
               }
             } else {
               for (int j = 0; j < 16; ++j)
-                if (col + j < p.n_valid) v[j] += rp[j];
+                if (col + j < p.n_valid) v[j] += __ldg(p.bias + col + j);
+            }
+          }
+          if (res_row) {
+            if (full) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] += rv[j];
+            } else {
+              for (int j = 0; j < 16; ++j)
+                if (col + j < p.n_valid) v[j] += res_row[col + j];
             }
           }
           if (do_stats) {   // host guarantees full 16-column chunks (Cout % gs == 0, gs % 16 == 0)
@@ -257,31 +262,6 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
             for (int j = 0; j < 16; ++j) {
               st1 += v[j];
               st2 = fmaf(v[j], v[j], st2);
-            }
-          }
-          if (do_gnb) {     // full chunks guaranteed by the host (Cout % 16 == 0)
-            const int sg = gnb_n * p.gnb_G + col / p.gnb_gs;
-            const float mean = __ldg(p.gnb_stats + 2 * sg), rstd = __ldg(p.gnb_stats + 2 * sg + 1);
-            const float* xp = p.gnb_x + opix * p.n_valid + col;
-#pragma unroll
-            for (int j4 = 0; j4 < 16; j4 += 4) {
-              const float4 xv = *reinterpret_cast<const float4*>(xp + j4);
-              const float4 gm = __ldg(reinterpret_cast<const float4*>(p.gnb_gamma + col + j4));
-              const float4 bt = __ldg(reinterpret_cast<const float4*>(p.gnb_beta + col + j4));
-              const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
-              const float gs4[4] = {gm.x, gm.y, gm.z, gm.w};
-              const float bs4[4] = {bt.x, bt.y, bt.z, bt.w};
-#pragma unroll
-              for (int jj = 0; jj < 4; ++jj) {
-                const int j = j4 + jj;
-                const float sc = gs4[jj] * rstd;
-                const float y = fmaf(xs[jj], sc, fmaf(-mean, sc, bs4[jj]));
-                float dy = __bfloat162float(__float2bfloat16(v[j]));    // what the apply kernel will read back
-                if (p.gnb_act == 1) dy *= gelu_grad_fast(y);
-                else if (p.gnb_act) dy *= act_grad_f(y, p.gnb_act);
-                gsum[j] = dy;
-                gsum[16 + j] = dy * xs[jj];
-              }
             }
           }
           if (p.out_f32) {
@@ -316,14 +296,6 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
             }
           }
         }
-        if (do_gnb) {
-          if (!(row_ok && col < p.n_valid)) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) gsum[j] = 0.f;
-          }
-          const float tot = warp_reduce_scatter32(gsum, lane);   // lane l: column (l & 15), l < 16: sum dy, else sum dy*x
-          colacc[(q * 16 + (c >> 4)) * 32 + lane] = tot;
-        }
         if (do_stats && ((c + 16) % p.gs) == 0) {   // a group's columns are complete: reduce over the warp's 32 rows
           const float w1 = warp_sum(st1), w2 = warp_sum(st2);
           if (lane == 0) stat_sm[(as * 4 + q) * 16 + c / p.gs] = make_float2(w1, w2);
@@ -331,14 +303,14 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
         }
       }
       if (do_stats) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");   // the 4 epilogue warps only
+        asm volatile("bar.sync 1, 256;" ::: "memory");   // the 8 epilogue warps only
         const int ng = p.bn / p.gs;
-        if (row < ng) {
+        if (half == 0 && row < ng) {
           float s1 = 0.f, s2 = 0.f;
 #pragma unroll
           for (int w = 0; w < 4; ++w) {                     // fixed order => deterministic
-            const float2 t = stat_sm[(as * 4 + w) * 16 + row];
-            s1 += t.x; s2 += t.y;
+            const float2 t2 = stat_sm[(as * 4 + w) * 16 + row];
+            s1 += t2.x; s2 += t2.y;
           }
           const int gidx = col0 / p.gs + row;
           if (gidx < p.G) {
@@ -348,19 +320,6 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
             dst[0] = s1; dst[1] = s2;
           }
         }
-      }
-      if (do_gnb) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        const int nch = p.bn >> 4;
-        for (int i = row; i < nch * 32; i += 128) {          // (chunk, value) pairs of this tile
-          const int ch = i >> 5, l = i & 31;
-          const float t4 = colacc[(0 * 16 + ch) * 32 + l] + colacc[(1 * 16 + ch) * 32 + l] +
-                           colacc[(2 * 16 + ch) * 32 + l] + colacc[(3 * 16 + ch) * 32 + l];
-          const int ccol = col0 + ch * 16 + (l & 15);
-          if (ccol < p.n_valid)
-            p.gnb_part[((long long)mt * 2 + (l >> 4)) * p.n_valid + ccol] = t4;
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");       // colacc is reused by the next tile
       }
       tc_fence_before();
       __syncwarp();
@@ -514,18 +473,14 @@ extern "C" int32_t tvae_conv_gemm(const tvae_conv_args* a, cudaStream_t stream) 
     TVAE_CHECK(p.bnimg == 1 && (long long)gH * gW % BM == 0,
                "tvae_conv_gemm: fused statistics need at least 128 pixels per image");
   }
-  p.gnb_x = a->gnb_x;
-  if (p.gnb_x) {
-    TVAE_CHECK(a->gnb_stats && a->gnb_gamma && a->gnb_beta && a->gnb_part, "tvae_conv_gemm: incomplete gnb_* arguments");
-    TVAE_CHECK(a->kind != 2 && a->out_bf16 && a->Cout % 16 == 0 && a->gnb_groups > 0 && a->Cout % a->gnb_groups == 0 &&
-                   (a->Cout / a->gnb_groups) % 16 == 0,
-               "tvae_conv_gemm: fused GroupNorm-backward sums need a dense bf16 output and 16-aligned groups");
-    TVAE_CHECK(p.bnimg == 1 && (long long)gH * gW % BM == 0,
-               "tvae_conv_gemm: fused GroupNorm-backward sums need at least 128 pixels per image");
-    TVAE_CHECK(((reinterpret_cast<uintptr_t>(a->gnb_x) | reinterpret_cast<uintptr_t>(a->gnb_gamma) |
-                 reinterpret_cast<uintptr_t>(a->gnb_beta)) & 15) == 0, "tvae_conv_gemm: gnb_* pointers must be 16-byte aligned");
-    p.gnb_stats = a->gnb_stats; p.gnb_gamma = a->gnb_gamma; p.gnb_beta = a->gnb_beta; p.gnb_part = a->gnb_part;
-    p.gnb_act = a->gnb_act; p.gnb_G = a->gnb_groups; p.gnb_gs = a->Cout / a->gnb_groups; p.gnb_hw = gH * gW;
+  {  // column split between the two epilogue warps of a lane quarter (aligned to GroupNorm groups when stats are on)
+    const int nch = p.bn / 16;
+    int first = (nch + 1) / 2;
+    if (p.stats_part) {
+      const int gpc = p.gs / 16;
+      first = (first + gpc - 1) / gpc * gpc;
+    }
+    p.split_chunk = first > nch ? nch : first;
   }
   p.out_f32 = a->out_f32; p.ld_f32 = a->out_f32_pitch;
   p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(a->out_bf16); p.ld_bf16 = a->out_bf16_pitch;
@@ -535,6 +490,7 @@ extern "C" int32_t tvae_conv_gemm(const tvae_conv_args* a, cudaStream_t stream) 
   p.res = a->residual; p.ld_res = a->res_pitch;
   if (p.out_f32) TVAE_CHECK(p.ld_f32 % 4 == 0 && (reinterpret_cast<uintptr_t>(p.out_f32) & 15) == 0, "out_f32 alignment");
   if (p.out_bf16) TVAE_CHECK(p.ld_bf16 % 8 == 0 && (reinterpret_cast<uintptr_t>(p.out_bf16) & 15) == 0, "out_bf16 alignment");
+  if (p.bias) TVAE_CHECK((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0, "bias must be 16-byte aligned");
   if (p.res) TVAE_CHECK(p.ld_res % 4 == 0 && (reinterpret_cast<uintptr_t>(p.res) & 15) == 0, "residual alignment");
 
   TVAE_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));

@@ -621,22 +621,6 @@ extern "C" int32_t tvae_gn_act_bwd(const float* x, const float* stats, const flo
   return 0;
 }
 
-extern "C" int32_t tvae_gn_act_bwd_from_tiles(const float* x, const float* stats, const float* gamma, const float* beta,
-                                              const void* da, const void* gres, const float* tile_part, int32_t N,
-                                              int32_t HW, int32_t C, int32_t G, int32_t act, void* dx, float* dgamma,
-                                              float* dbeta, float* ws, cudaStream_t stream) {
-  TVAE_ENTER(x);
-  TVAE_CHECK(x && stats && gamma && beta && da && tile_part && dx && dgamma && dbeta && ws,
-             "tvae_gn_act_bwd_from_tiles: null pointer");
-  TVAE_CHECK(gn_fast_ok(C, G) && HW % 128 == 0 && (C / G) % 16 == 0,
-             "tvae_gn_act_bwd_from_tiles: needs 16-aligned groups and a multiple of 128 pixels per image");
-  gn_act_bwd_from_tiles_fast(x, stats, gamma, beta, reinterpret_cast<const __nv_bfloat16*>(da),
-                             reinterpret_cast<const __nv_bfloat16*>(gres), tile_part, N, HW, C, G, act,
-                             reinterpret_cast<__nv_bfloat16*>(dx), dgamma, dbeta, ws, stream);
-  TVAE_CUDA(cudaGetLastError());
-  return 0;
-}
-
 extern "C" int64_t tvae_colsum_workspace_bytes(int64_t rows, int32_t C) {
   return (int64_t)colsum_blocks(rows) * C * 4;
 }

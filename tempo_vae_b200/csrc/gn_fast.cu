@@ -276,19 +276,4 @@ int gn_act_bwd_fast(const float* x, const float* stats, const float* gamma, cons
   return 0;
 }
 
-// backward with the per-tile column sums already produced by the dgrad epilogue (conv_gemm.cu, gnb_part)
-int gn_act_bwd_from_tiles_fast(const float* x, const float* stats, const float* gamma, const float* beta,
-                               const __nv_bfloat16* da, const __nv_bfloat16* gres, const float* tile_part, int N, int HW,
-                               int C, int G, int act, __nv_bfloat16* dx, float* dgamma, float* dbeta, float* ws,
-                               cudaStream_t stream) {
-  const int tiles = HW / 128;
-  gn_bwd_finalize_fast_kernel<<<N, 256, 2 * C * sizeof(float), stream>>>(tile_part, gamma, tiles, HW, C, G, N, ws, stats);
-  gn_bwd_param_fast_kernel<<<(C + 31) / 32, 256, 0, stream>>>(ws, N, C, dgamma, dbeta);
-  const int rpb = rows_per_block(HW);
-  dim3 grid((HW + rpb - 1) / rpb, N);
-  gn_bwd_apply_fast_kernel<<<grid, 256, 0, stream>>>(x, stats, gamma, beta, da, gres, ws + 2ll * N * C, HW, C, G, act,
-                                                     rpb, dx);
-  return 0;
-}
-
 }  // namespace tvae

@@ -244,11 +244,9 @@ def conv_fwd(mod, x_bf16, Cin, *, residual=None, want_f32=True, want_bf16=False,
     return out
 
 
-def conv_bwd(mod, dy_bf16, x_bf16, Cin, *, dgrad=None, dgrad_residual=None, bias_grad_from=None, fuse_gn=None):
+def conv_bwd(mod, dy_bf16, x_bf16, Cin, *, dgrad=None, dgrad_residual=None, bias_grad_from=None):
     """Backward of conv_fwd. dy_bf16: gradient wrt the conv output (bf16 NHWC). Writes weight/bias grads.
-    dgrad: None | "bf16" | "f32" — format of the returned input gradient.
-    fuse_gn = (norm, h_f32, stats, act_code): the returned bf16 gradient feeds that GroupNorm's backward, whose
-    per-channel sums are then produced by this dgrad's epilogue when the geometry allows."""
+    dgrad: None | "bf16" | "f32" — format of the returned input gradient."""
     kind, R = mod.conv_kind()
     Cout = mod.out_channels
     w = mod.weight
@@ -273,16 +271,9 @@ def conv_bwd(mod, dy_bf16, x_bf16, Cin, *, dgrad=None, dgrad_residual=None, bias
     if dgrad is None:
         return None
     if kind == 0:
-        gnb = None
-        if fuse_gn is not None and dgrad == "bf16" and dgrad_residual is None:
-            norm, h_f32, st, act_code = fuse_gn
-            HW = dy_bf16.shape[1] * dy_bf16.shape[2]
-            if norm.num_channels == Cin and ops.gn_bwd_fusable(Cin, norm.num_groups, HW, R * R * Cout):
-                gamma, beta = norm.affine_params()
-                gnb = (h_f32, st, gamma, beta, norm.num_groups, act_code)
         of, ob = ops.conv_gemm(dy_bf16, Cout, mod.packed("dgrad"), kind=0, R=R, Cout=Cin, flip=True,
                                residual=dgrad_residual, want_f32=(dgrad == "f32"), want_bf16=(dgrad == "bf16"),
-                               split_out=False, gn_bwd=gnb)
+                               split_out=False)
     elif kind == 1:
         of, ob = ops.conv_gemm(dy_bf16, Cout, mod.packed("down_dgrad"), kind=2, R=2, Cout=Cin,
                                want_f32=(dgrad == "f32"), want_bf16=(dgrad == "bf16"), split_out=False)
@@ -485,11 +476,9 @@ class ResNetBlock(nn.Module):
     def bwd(self, g, saved):
         x_f32, st1, a1, h1, st2, a2, xb = saved
         skip = self.ch_in != self.ch_out
-        d_a2 = conv_bwd(self.net2[-1], g, a2, self.ch_out, dgrad="bf16",
-                        fuse_gn=(self.net2[0], h1, st2, self.net2[1].code))
+        d_a2 = conv_bwd(self.net2[-1], g, a2, self.ch_out, dgrad="bf16")
         d_h1 = norm_act_bwd(self.net2[0], h1, st2, d_a2, None, self.net2[1].code)
-        d_a1 = conv_bwd(self.net1[2], d_h1, a1, self.ch_in, dgrad="bf16",
-                        fuse_gn=(self.net1[0], x_f32, st1, self.net1[1].code))
+        d_a1 = conv_bwd(self.net1[2], d_h1, a1, self.ch_in, dgrad="bf16")
         if skip:
             g_res = conv_bwd(self.skip_conv, g, xb, self.ch_in, dgrad="bf16")
         else:
@@ -684,8 +673,7 @@ class Encoder(nn.Module):
 
     def bwd(self, g_bf16, saved, need_input_grad=False):
         h_f32, st, a = saved["out"]
-        d_a = conv_bwd(self.conv_out, g_bf16, a, self.norm_out.num_channels, dgrad="bf16",
-                       fuse_gn=(self.norm_out, h_f32, st, self.act_out.code))
+        d_a = conv_bwd(self.conv_out, g_bf16, a, self.norm_out.num_channels, dgrad="bf16")
         g = norm_act_bwd(self.norm_out, h_f32, st, d_a, None, self.act_out.code)
         g = self.mid2.bwd(g, saved["mid2"])
         if self.mid_attn:
@@ -760,8 +748,7 @@ class Decoder(nn.Module):
 
     def bwd(self, g_bf16, saved, input_grad="bf16"):
         h_f32, st, a = saved["out"]
-        d_a = conv_bwd(self.conv_out, g_bf16, a, self.norm_out.num_channels, dgrad="bf16",
-                       fuse_gn=(self.norm_out, h_f32, st, self.act_out.code))
+        d_a = conv_bwd(self.conv_out, g_bf16, a, self.norm_out.num_channels, dgrad="bf16")
         g = norm_act_bwd(self.norm_out, h_f32, st, d_a, None, self.act_out.code)
         for up, s in zip(reversed(self.ups), reversed(saved["levels"])):
             g = up.bwd(g, s)

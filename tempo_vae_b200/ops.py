@@ -33,7 +33,7 @@ KERNEL_LAUNCHES = [0]   # kernels of libtvae_b200.so enqueued through this modul
 _KERNELS_PER_CALL = {
     "tvae_pack_weight": 1, "tvae_conv_gemm": 1, "tvae_wgrad_gemm": 2, "tvae_nchw_f32_to_nhwc_bf16": 1,
     "tvae_nhwc_f32_to_nchw_f32": 1, "tvae_nhwc_bf16_to_nchw_f32": 1, "tvae_f32_to_bf16": 1, "tvae_gn_stats": 1,
-    "tvae_gn_act_fwd": 1, "tvae_gn_stats_finalize": 1, "tvae_gn_act_bwd_from_tiles": 3, "tvae_gn_act_bwd": 3, "tvae_colsum_bf16": 2, "tvae_attn_fwd": 1, "tvae_attn_bwd": 2, "tvae_attn_fwd_tc": 1, "tvae_attn_bwd_tc": 2,
+    "tvae_gn_act_fwd": 1, "tvae_gn_stats_finalize": 1, "tvae_gn_act_bwd": 3, "tvae_colsum_bf16": 2, "tvae_attn_fwd": 1, "tvae_attn_bwd": 2, "tvae_attn_fwd_tc": 1, "tvae_attn_bwd_tc": 2,
     "tvae_reparam_fwd": 1, "tvae_reparam_bwd": 1, "tvae_nll_fwd": 2, "tvae_vae_loss_finalize": 1,
     "tvae_l2head_loss_fwd": 1, "tvae_l2head_loss_bwd": 1, "tvae_l2head_finalize": 1, "tvae_sumsq": 2, "tvae_adamw": 1,
 }
@@ -165,7 +165,7 @@ def fused_stats_ok(N, oH, oW, Cout, G, kind, H, W):
 
 
 def conv_gemm(x, C_in, wp, *, kind, R, Cout, flip=False, bias=None, residual=None, want_f32=True, want_bf16=False,
-              bf16_pitch=None, bn=0, out_f32=None, out_bf16=None, stats=None, split_out=True, gn_bwd=None):
+              bf16_pitch=None, bn=0, out_f32=None, out_bf16=None, stats=None, split_out=True):
     """x: bf16 [N,H,W,pitch]. Returns (out_f32 or None, out_bf16 or None) as NHWC tensors; with stats=(G, eps) the
     GroupNorm statistics [N, G, 2] of the output are produced by the epilogue and returned as a third value
     (None when the geometry does not allow it)."""
@@ -203,12 +203,6 @@ def conv_gemm(x, C_in, wp, *, kind, R, Cout, flip=False, bias=None, residual=Non
     if out_bf16 is not None and SPLIT_BF16[0] and want_bf16 and split_out:
         out_lo = torch.empty_like(out_bf16)
         a.out_bf16_lo = out_lo.data_ptr()
-    gnb_part = None
-    if gn_bwd is not None:      # (x_f32, stats, gamma, beta, G, act): first stage of the consuming GroupNorm backward
-        gx, gst, gga, gbe, gG, gact = gn_bwd
-        gnb_part = torch.empty(((N * oH * oW) // 128, 2, Cout), dtype=torch.float32, device=dev)
-        a.gnb_x, a.gnb_stats, a.gnb_gamma, a.gnb_beta = gx.data_ptr(), gst.data_ptr(), gga.data_ptr(), gbe.data_ptr()
-        a.gnb_part, a.gnb_groups, a.gnb_act = gnb_part.data_ptr(), gG, int(gact)
     part = None
     if stats is not None and fused_stats_ok(N, oH, oW, Cout, stats[0], kind, H, W):
         grid_px = (H * W) if kind == 2 else (oH * oW)
@@ -226,8 +220,6 @@ def conv_gemm(x, C_in, wp, *, kind, R, Cout, flip=False, bias=None, residual=Non
     else:
         check(lib.tvae_conv_gemm(C.byref(a), _stream()), "tvae_conv_gemm")
     out_bf16 = _pair(out_bf16, out_lo)
-    if gnb_part is not None:
-        out_bf16._gnb_part = gnb_part           # picked up by gn_act_bwd (python attribute on the tensor)
     if stats is None:
         return out_f32, out_bf16
     st = None
@@ -333,33 +325,12 @@ def gn_act_fwd(x, stats, gamma, beta, G, act):
     return _pair(out, lo)
 
 
-# Measured at B=256 (round 1): with the sums in the epilogue a 512-channel dgrad launch takes 7 ms instead of 4 ms — four
-# single-issue epilogue warps need ~60 us per 128x256 tile for the extra x loads, GELU' and column reductions, three
-# times the MMA window — while the stand-alone rowsum kernel costs 0.9 ms. So the fusion is OFF by default; the
-# kernel path stays (and is tested) for a future epilogue with more warps.
-FUSE_GN_BWD = [False]
-
-
-def gn_bwd_fusable(Cc, G, HW, K):
-    """Can (and should) the dgrad that produces `da` also produce the GroupNorm-backward column sums in its epilogue?
-    (16-aligned groups, whole 128-pixel tiles per image, a long reduction) — gated by FUSE_GN_BWD."""
-    return (FUSE_GN_BWD[0] and G > 0 and Cc % G == 0 and (Cc // G) % 16 == 0 and (Cc // 8) <= 256
-            and 256 % (Cc // 8) == 0 and HW % 128 == 0 and Cc >= 256 and K >= 2048)
-
-
 def gn_act_bwd(x, stats, gamma, beta, da, gres, G, act, dgamma, dbeta):
     N, H, W, Cc = x.shape
     da, gres = hi_of(da), hi_of(gres)
     assert da.shape[-1] == Cc and da.dtype == torch.bfloat16
     dx = torch.empty((N, H, W, Cc), dtype=torch.bfloat16, device=x.device)
     ws = _workspace(lib.tvae_gn_bwd_workspace_bytes(N, H * W, Cc, G), x.device, "gn")
-    tiles = getattr(da, "_gnb_part", None)
-    if tiles is not None:
-        check(lib.tvae_gn_act_bwd_from_tiles(x.data_ptr(), stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
-                                             da.data_ptr(), _ptr(gres), tiles.data_ptr(), N, H * W, Cc, G, int(act),
-                                             dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), ws.data_ptr(),
-                                             _stream()), "tvae_gn_act_bwd_from_tiles")
-        return dx
     check(lib.tvae_gn_act_bwd(x.data_ptr(), stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), da.data_ptr(),
                               _ptr(gres), N, H * W, Cc, G, int(act), dx.data_ptr(), dgamma.data_ptr(),
                               dbeta.data_ptr(), ws.data_ptr(), _stream()), "tvae_gn_act_bwd")

@@ -507,36 +507,3 @@ def test_wgrad_exchanged_operand_roles(N, H, W, Cin, Cout, R):
                  flip=True)
     torch.cuda.synchronize()
     assert rel_err(grad, ref) < 2e-3
-
-
-@pytest.mark.parametrize("N,H,W,C,Cout,act", [(2, 16, 16, 256, 256, 1), (2, 32, 32, 512, 256, 1), (3, 16, 16, 256, 512, 3)])
-def test_groupnorm_backward_sums_fused_into_dgrad_epilogue(N, H, W, C, Cout, act):
-    """dgrad with gn_bwd=...: same dx / dgamma / dbeta as the stand-alone three-kernel GroupNorm backward."""
-    o = ops()
-    g = torch.Generator(device="cuda").manual_seed(18)
-    G, eps = 8, 1e-6
-    w = bf16_round(torch.randn((Cout, C, 3, 3), device="cuda", generator=g) / math.sqrt(9 * Cout))
-    dy = bf16_round(torch.randn((N, Cout, H, W), device="cuda", generator=g))
-    x = torch.randn((N, H, W, C), device="cuda", generator=g) * 1.3 + 0.2
-    gamma = torch.randn((C,), device="cuda", generator=g) * 0.5 + 1.0
-    beta = torch.randn((C,), device="cuda", generator=g) * 0.2
-    gres = torch.randn((N, H, W, C), device="cuda", generator=g).to(torch.bfloat16)
-    st = o.gn_stats(x, C, G, eps)
-    wp = o.pack_weight(w, "dgrad")
-    dyp = nhwc_bf16(dy, Cout)
-    assert not o.gn_bwd_fusable(C, G, H * W, 9 * Cout)          # off by default (measured slower, see ops.FUSE_GN_BWD)
-    o.FUSE_GN_BWD[0] = True
-    try:
-        assert o.gn_bwd_fusable(C, G, H * W, 9 * Cout)
-    finally:
-        o.FUSE_GN_BWD[0] = False
-    _, da_f = o.conv_gemm(dyp, Cout, wp, kind=0, R=3, Cout=C, flip=True, want_f32=False, want_bf16=True,
-                          gn_bwd=(x, st, gamma, beta, G, act))
-    _, da_p = o.conv_gemm(dyp, Cout, wp, kind=0, R=3, Cout=C, flip=True, want_f32=False, want_bf16=True)
-    assert torch.equal(da_f, da_p) and hasattr(da_f, "_gnb_part") and not hasattr(da_p, "_gnb_part")
-    dg1, db1, dg2, db2 = (torch.empty((C,), device="cuda") for _ in range(4))
-    dx1 = o.gn_act_bwd(x, st, gamma, beta, da_f, gres, G, act, dg1, db1)
-    dx2 = o.gn_act_bwd(x, st, gamma, beta, da_p, gres, G, act, dg2, db2)
-    torch.cuda.synchronize()
-    assert rel_err(dg1, dg2) < 1e-4 and rel_err(db1, db2) < 1e-4
-    assert rel_err(dx1.float(), dx2.float()) < 1e-2          # bf16 outputs of slightly different group means
