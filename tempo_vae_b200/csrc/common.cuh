@@ -167,6 +167,25 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): one full 32-byte sector per thread per instruction. The GEMM
+// epilogues own one output ROW per thread, so 128-bit stores would fill every sector in two half-sector requests.
+__device__ __forceinline__ void st_global_v8(float* p, const float (&v)[16], int o) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[o]), "f"(v[o + 1]), "f"(v[o + 2]),
+               "f"(v[o + 3]), "f"(v[o + 4]), "f"(v[o + 5]), "f"(v[o + 6]), "f"(v[o + 7])
+               : "memory");
+}
+__device__ __forceinline__ void st_global_v8_b32(void* p, const uint32_t (&w)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
+               "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+               : "memory");
+}
+__device__ __forceinline__ void ld_global_v8(const float* p, float (&v)[16], int o) {
+  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v[o]), "=f"(v[o + 1]), "=f"(v[o + 2]), "=f"(v[o + 3]), "=f"(v[o + 4]), "=f"(v[o + 5]),
+                 "=f"(v[o + 6]), "=f"(v[o + 7])
+               : "l"(p));
+}
+
 // Shared-memory matrix descriptor (see cute/arch/mma_sm100_desc.hpp: SmemDescriptor):
 // [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version=1, [61,64) layout (2 = SWIZZLE_128B)
 __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {

@@ -62,6 +62,7 @@ struct ConvParams {
   float* stats_part;   // [slots][G][2], slot = m_tile (x4 + tap for the transposed conv); NULL = off
   int gs, G;           // group size (multiple of 16, divides BN), number of groups
   int split_chunk;     // first 16-column chunk handled by the second warp of each TMEM lane quarter
+  int wide;            // bit 0/1/2: fp32 output / bf16 output / residual rows are 32-byte aligned => 256-bit accesses
 };
 
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -207,14 +208,23 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
       const float* res_row = p.res ? p.res + opix * p.ld_res : nullptr;
 
       uint32_t r[16];
-      float4 rs[4];
+      float rs[16];
+      auto load_res = [&](int col) {
+        if (p.wide & 4) {
+          ld_global_v8(res_row + col, rs, 0);
+          ld_global_v8(res_row + col + 8, rs, 8);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 x4 = *reinterpret_cast<const float4*>(res_row + col + 4 * j);
+            rs[4 * j] = x4.x; rs[4 * j + 1] = x4.y; rs[4 * j + 2] = x4.z; rs[4 * j + 3] = x4.w;
+          }
+        }
+      };
       if (cbeg < cend) {                                    // prologue: first chunk in flight
         tmem_ld16(taddr + (uint32_t)(cbeg << 4), r);
         const int col = col0 + (cbeg << 4);
-        if (res_row && row_ok && col + 16 <= p.n_valid) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) rs[j] = *reinterpret_cast<const float4*>(res_row + col + 4 * j);
-        }
+        if (res_row && row_ok && col + 16 <= p.n_valid) load_res(col);
       }
       for (int ch = cbeg; ch < cend; ++ch) {
         const int c = ch << 4;
@@ -225,14 +235,11 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
         for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
         float rv[16];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { rv[4 * j] = rs[j].x; rv[4 * j + 1] = rs[j].y; rv[4 * j + 2] = rs[j].z; rv[4 * j + 3] = rs[j].w; }
+        for (int j = 0; j < 16; ++j) rv[j] = rs[j];
         if (ch + 1 < cend) {                                // next chunk: TMEM load + residual loads go out now
           tmem_ld16(taddr + (uint32_t)(c + 16), r);
           const int ncol = col + 16;
-          if (res_row && row_ok && ncol + 16 <= p.n_valid) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) rs[j] = *reinterpret_cast<const float4*>(res_row + ncol + 4 * j);
-          }
+          if (res_row && row_ok && ncol + 16 <= p.n_valid) load_res(ncol);
         }
         if (row_ok && col < p.n_valid) {
           const bool full = (col + 16 <= p.n_valid);
@@ -266,7 +273,10 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
           }
           if (p.out_f32) {
             float* op = p.out_f32 + opix * p.ld_f32 + col;
-            if (full) {
+            if (full && (p.wide & 1)) {
+              st_global_v8(op, v, 0);
+              st_global_v8(op + 8, v, 8);
+            } else if (full) {
 #pragma unroll
               for (int j = 0; j < 16; j += 4)
                 *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
@@ -278,13 +288,15 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
           if (p.out_bf16) {
             __nv_bfloat16* op = p.out_bf16 + opix * p.ld_bf16 + col;
             if (full) {
-              uint4 a, b;
-              a.x = pack_bf16(v[0], v[1]); a.y = pack_bf16(v[2], v[3]);
-              a.z = pack_bf16(v[4], v[5]); a.w = pack_bf16(v[6], v[7]);
-              b.x = pack_bf16(v[8], v[9]); b.y = pack_bf16(v[10], v[11]);
-              b.z = pack_bf16(v[12], v[13]); b.w = pack_bf16(v[14], v[15]);
-              *reinterpret_cast<uint4*>(op) = a;
-              *reinterpret_cast<uint4*>(op + 8) = b;
+              uint32_t w8[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) w8[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
+              if (p.wide & 2) {
+                st_global_v8_b32(op, w8);
+              } else {
+                *reinterpret_cast<uint4*>(op) = make_uint4(w8[0], w8[1], w8[2], w8[3]);
+                *reinterpret_cast<uint4*>(op + 8) = make_uint4(w8[4], w8[5], w8[6], w8[7]);
+              }
             } else {
               for (int j = 0; j < 16; ++j)
                 if (col + j < p.n_valid) op[j] = __float2bfloat16(v[j]);
@@ -490,6 +502,9 @@ extern "C" int32_t tvae_conv_gemm(const tvae_conv_args* a, cudaStream_t stream) 
   p.res = a->residual; p.ld_res = a->res_pitch;
   if (p.out_f32) TVAE_CHECK(p.ld_f32 % 4 == 0 && (reinterpret_cast<uintptr_t>(p.out_f32) & 15) == 0, "out_f32 alignment");
   if (p.out_bf16) TVAE_CHECK(p.ld_bf16 % 8 == 0 && (reinterpret_cast<uintptr_t>(p.out_bf16) & 15) == 0, "out_bf16 alignment");
+  if (p.out_f32 && p.ld_f32 % 8 == 0 && (reinterpret_cast<uintptr_t>(p.out_f32) & 31) == 0) p.wide |= 1;
+  if (p.out_bf16 && p.ld_bf16 % 16 == 0 && (reinterpret_cast<uintptr_t>(p.out_bf16) & 31) == 0) p.wide |= 2;
+  if (p.res && p.ld_res % 8 == 0 && (reinterpret_cast<uintptr_t>(p.res) & 31) == 0) p.wide |= 4;
   if (p.bias) TVAE_CHECK((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0, "bias must be 16-byte aligned");
   if (p.res) TVAE_CHECK(p.ld_res % 4 == 0 && (reinterpret_cast<uintptr_t>(p.res) & 15) == 0, "residual alignment");
 
