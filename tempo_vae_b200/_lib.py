@@ -65,6 +65,7 @@ def _load():
         "tvae_last_error": (C.c_char_p, []),
         "tvae_abi_version": (i32, []),
         "tvae_conv_gemm": (i32, [C.POINTER(ConvArgs), vp]),
+        "tvae_conv_set_cta_pair": (i32, [i32]),
         "tvae_wgrad_gemm": (i32, [C.POINTER(WgradArgs), vp]),
         "tvae_wgrad_workspace_bytes": (i64, [i32, i32, i32, i32]),
         "tvae_wgrad_splits": (i32, [i32, i32, i32, i64]),
@@ -104,6 +105,8 @@ def _load():
 
 
 lib, EXPORTED = _load()
+if os.environ.get("TVAE_CONV_CTA_PAIR") in ("0", "1"):     # A/B switch of the conv schedule (results are bit-identical)
+    lib.tvae_conv_set_cta_pair(int(os.environ["TVAE_CONV_CTA_PAIR"]))
 
 
 def last_error() -> str:

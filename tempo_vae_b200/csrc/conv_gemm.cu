@@ -29,6 +29,10 @@ constexpr int A_STAGE_BYTES = BM * BK * 2;       // 16 KB
 constexpr int B_STAGE_BYTES = 256 * BK * 2;      // 32 KB (BN <= 256)
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int STAGES = 4;
+// CTA-pair variant: every CTA stages its 128 A rows and half of the B tile => 32 KB per stage, 6 stages
+constexpr int PAIR_STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES / 2;
+constexpr int PAIR_STAGES = 6;
+static_assert(PAIR_STAGES * PAIR_STAGE_BYTES == STAGES * STAGE_BYTES, "both variants use the same shared-memory budget");
 constexpr int NTHREADS = 320;                    // warp0: TMA, warp1: MMA + TMEM alloc, warps 2-9: epilogue
 constexpr int TMEM_COLS = 512;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*stats*/;
@@ -65,8 +69,17 @@ struct ConvParams {
   int wide;            // bit 0/1/2: fp32 output / bf16 output / residual rows are 32-byte aligned => 256-bit accesses
 };
 
+// PAIR = true: launched as clusters of two CTAs (one TPC). The pair owns two vertically adjacent M tiles and one
+// N tile; the leader CTA's MMA thread issues tcgen05.mma.cta_group::2 with M = 256, which reads A rows 0-127 /
+// 128-255 and B rows 0-bn/2 / bn/2-bn from the leader's / the peer's shared memory and writes each CTA's 128
+// accumulator rows into that CTA's own TMEM. Barrier topology: "full" lives in the leader (both producers' TMA
+// bytes are counted there), "empty" and "tmem full" are per CTA and signalled by a multicast commit, "tmem empty"
+// lives in the leader and collects the 16 epilogue warps of both CTAs.
+template <bool PAIR>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ ConvParams p) {
+  constexpr int STAGES = PAIR ? PAIR_STAGES : tvae::STAGES;
+  constexpr int STAGE_BYTES = PAIR ? PAIR_STAGE_BYTES : tvae::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
@@ -94,30 +107,39 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 8);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[i], PAIR ? 16 : 8);  // one arrive per epilogue warp (of both CTAs of a pair)
     }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+  if (warp == 1) {
+    if (PAIR) tmem_alloc_pair(tmem_ptr_smem, TMEM_COLS);
+    else tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();   // the peer's TMA / arrives must not reach a barrier that is not initialised yet
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  const int total_tiles = p.m_tiles * p.n_tiles;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const int unit0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int nunits = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int total_tiles = (PAIR ? (p.m_tiles + 1) / 2 : p.m_tiles) * p.n_tiles;
+  auto m_tile_of = [&](int t) { return PAIR ? 2 * (t / p.n_tiles) + (int)rank : t / p.n_tiles; };
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t tx_bytes = A_STAGE_BYTES + (uint32_t)p.bn * (BK * 2);
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int mt = t / p.n_tiles, nt = t % p.n_tiles;
+      // bytes of BOTH CTAs' loads for a pair (counted on the leader's barrier)
+      const uint32_t tx_bytes = (PAIR ? 2u : 1u) * A_STAGE_BYTES + (uint32_t)p.bn * (BK * 2);
+      for (int t = unit0; t < total_tiles; t += nunits) {
+        const int mt = m_tile_of(t), nt = t % p.n_tiles;
         const int w0 = (mt % p.tiles_w) * p.bw;
         const int h0 = ((mt / p.tiles_w) % p.tiles_h) * p.bh;
-        const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.bnimg;
-        const int brow = nt * p.bn;
+        const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.bnimg;   // past the last image for the odd tail: zero fill
+        const int brow = nt * p.bn + (PAIR ? (int)rank * (p.bn >> 1) : 0);
         int kb = 0;
         for (int tap = 0; tap < p.ntaps; ++tap) {
           const int hh = h0 + p.dh[tap], ww = w0 + p.dw[tap];
@@ -127,9 +149,16 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
               const CUtensorMap* bm = seg == 1 ? &maps.blo : &maps.b;
               mbar_wait(&empty_bar[stage], phase ^ 1, 1);
               uint8_t* sa = smem + stage * STAGE_BYTES;
-              mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
-              tma_load_4d(am, &full_bar[stage], sa, cb * BK, ww, hh, n0);
-              tma_load_2d(bm, &full_bar[stage], sa + A_STAGE_BYTES, kb * BK, brow);
+              if (PAIR) {
+                const uint32_t fb = mapa_u32(smem_u32(&full_bar[stage]), 0);
+                if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+                tma_load_4d_pair(am, fb, sa, cb * BK, ww, hh, n0);
+                tma_load_2d_pair(bm, fb, sa + A_STAGE_BYTES, kb * BK, brow);
+              } else {
+                mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+                tma_load_4d(am, &full_bar[stage], sa, cb * BK, ww, hh, n0);
+                tma_load_2d(bm, &full_bar[stage], sa + A_STAGE_BYTES, kb * BK, brow);
+              }
               if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
           }
@@ -138,13 +167,13 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(BM, p.bn, 0, 0);
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = make_idesc_bf16(PAIR ? 2 * BM : BM, p.bn, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = unit0; t < total_tiles; t += nunits) {
         mbar_wait(&tempty_bar[as], aphase ^ 1, 2);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)as * 256u;
@@ -160,14 +189,17 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
               const int nk = (cb == p.cblks - 1) ? p.last_k16 : 4;
               for (int k = 0; k < nk; ++k) {
                 // +32 B per K=16 step inside the 128-B swizzle row (descriptor address is in 16-B units)
-                umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k | seg) != 0);
+                if (PAIR) umma_bf16_pair(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k | seg) != 0);
+                else umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k | seg) != 0);
               }
-              umma_commit(&empty_bar[stage]);
+              if (PAIR) umma_commit_pair(&empty_bar[stage]);
+              else umma_commit(&empty_bar[stage]);
               if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
           }
         }
-        umma_commit(&tfull_bar[as]);
+        if (PAIR) umma_commit_pair(&tfull_bar[as]);
+        else umma_commit(&tfull_bar[as]);
         as ^= 1;
         if (as == 0) aphase ^= 1;
       }
@@ -185,8 +217,8 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
     const int cbeg = half ? p.split_chunk : 0, cend = half ? nch : p.split_chunk;
     int as = 0;
     uint32_t aphase = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const int mt = t / p.n_tiles, nt = t % p.n_tiles;
+    for (int t = unit0; t < total_tiles; t += nunits) {
+      const int mt = m_tile_of(t), nt = t % p.n_tiles;
       mbar_wait(&tfull_bar[as], aphase, 4);
       tc_fence_after();
       const long long pix = (long long)mt * BM + row;
@@ -325,7 +357,7 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
             s1 += t2.x; s2 += t2.y;
           }
           const int gidx = col0 / p.gs + row;
-          if (gidx < p.G) {
+          if (gidx < p.G && mt < p.m_tiles) {
             const int tapslot = p.up_mode ? (nt * p.bn) / p.cout_per_tap : 0;
             const long long slot = p.up_mode ? (long long)mt * 4 + tapslot : mt;
             float* dst = p.stats_part + (slot * p.G + gidx) * 2;
@@ -335,19 +367,29 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[as]), 0));
+        else mbar_arrive(&tempty_bar[as]);
+      }
       as ^= 1;
       if (as == 0) aphase ^= 1;
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();   // the leader's barriers and both CTAs' operands stay alive until the pair is done
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (PAIR) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
+
+// Off by default: measured on B200 (B=256 train step, alternating runs) the pair schedule is 1.1 % SLOWER
+// (137.8/138.4 vs 136.3/136.7 ms per step). The single-CTA kernel already runs at the power-capped tensor roofline
+// (1.40 PFLOP/s = the sustained cuBLAS bf16 figure), so saving a third of the L2->SM operand traffic buys nothing.
+int g_conv_cta_pair = 0;
 
 int pick_bn(int cout) {
   if (cout <= 256) return (cout + 15) / 16 * 16;
@@ -465,12 +507,14 @@ extern "C" int32_t tvae_conv_gemm(const tvae_conv_args* a, cudaStream_t stream) 
   }
   TVAE_CHECK(p.bn % 16 == 0 && p.bn >= 16 && p.bn <= 256, "tvae_conv_gemm: bad bn %d", p.bn);
   p.n_tiles = (n_cols + p.bn - 1) / p.bn;
+  // CTA pairs (cta_group::2) whenever there are at least two M tiles to pair up
+  const bool pair = g_conv_cta_pair != 0 && p.m_tiles >= 2;
   p.n_valid = a->Cout;
   TVAE_CHECK(a->w_rows >= n_cols, "tvae_conv_gemm: packed weight has %d rows, need %d", a->w_rows, n_cols);
   {
     uint64_t dims[2] = {(uint64_t)a->k_pitch, (uint64_t)a->w_rows};
     uint64_t strides[1] = {(uint64_t)a->k_pitch * 2};
-    uint32_t box[2] = {BK, (uint32_t)p.bn};
+    uint32_t box[2] = {BK, (uint32_t)(pair ? p.bn / 2 : p.bn)};
     if (make_tmap_bf16(&maps.b, a->w, 2, dims, strides, box)) return -3;
     if (make_tmap_bf16(&maps.blo, split ? a->w_lo : a->w, 2, dims, strides, box)) return -3;
   }
@@ -508,11 +552,43 @@ extern "C" int32_t tvae_conv_gemm(const tvae_conv_args* a, cudaStream_t stream) 
   if (p.bias) TVAE_CHECK((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0, "bias must be 16-byte aligned");
   if (p.res) TVAE_CHECK(p.ld_res % 4 == 0 && (reinterpret_cast<uintptr_t>(p.res) & 15) == 0, "residual alignment");
 
-  TVAE_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  const int total = p.m_tiles * p.n_tiles;
-  int grid = num_sms();
-  if (grid > total) grid = total;
-  conv_gemm_kernel<<<grid, NTHREADS, SMEM_BYTES, stream>>>(maps, p);
+  if (pair) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      TVAE_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      attr_set = true;
+    }
+    const int total = (p.m_tiles + 1) / 2 * p.n_tiles;
+    int grid = num_sms() / 2;
+    if (grid > total) grid = total;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * grid);
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    TVAE_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<true>, maps, p));
+  } else {
+    static bool attr_set = false;
+    if (!attr_set) {
+      TVAE_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      attr_set = true;
+    }
+    const int total = p.m_tiles * p.n_tiles;
+    int grid = num_sms();
+    if (grid > total) grid = total;
+    conv_gemm_kernel<false><<<grid, NTHREADS, SMEM_BYTES, stream>>>(maps, p);
+  }
   TVAE_CUDA(cudaGetLastError());
   return 0;
+}
+
+extern "C" int32_t tvae_conv_set_cta_pair(int32_t enable) {
+  const int prev = g_conv_cta_pair;
+  g_conv_cta_pair = enable ? 1 : 0;
+  return prev;
 }

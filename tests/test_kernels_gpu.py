@@ -24,6 +24,15 @@ def ops():
     return o
 
 
+@pytest.fixture(params=["cta_pair", "single_cta"])
+def conv_sched(request):
+    """Run a conv test under both schedules of tvae_conv_gemm (cta_group::2 CTA pairs / one CTA per SM)."""
+    from tempo_vae_b200._lib import lib
+    prev = lib.tvae_conv_set_cta_pair(1 if request.param == "cta_pair" else 0)
+    yield request.param
+    lib.tvae_conv_set_cta_pair(prev)
+
+
 def bf16_round(t):
     return t.to(torch.bfloat16).float()
 
@@ -56,6 +65,7 @@ CONV_CASES = [
 ]
 
 
+@pytest.mark.usefixtures("conv_sched")
 @pytest.mark.parametrize("N,H,W,Cin,Cout,R", CONV_CASES)
 def test_conv_fwd(N, H, W, Cin, Cout, R):
     o = ops()
@@ -77,6 +87,7 @@ def test_conv_fwd(N, H, W, Cin, Cout, R):
     assert rel_err(gotb, ref) < 1e-2
 
 
+@pytest.mark.usefixtures("conv_sched")
 @pytest.mark.parametrize("N,H,W,Cin,Cout,R", [(2, 16, 16, 64, 128, 3), (2, 32, 32, 256, 512, 3), (1, 64, 64, 1028, 512, 3),
                                                (2, 16, 16, 128, 128, 1)])
 def test_conv_dgrad(N, H, W, Cin, Cout, R):
@@ -92,6 +103,7 @@ def test_conv_dgrad(N, H, W, Cin, Cout, R):
     assert rel_err(of[..., :Cin].permute(0, 3, 1, 2), ref) < 2e-3
 
 
+@pytest.mark.usefixtures("conv_sched")
 @pytest.mark.parametrize("N,H,W,Cin,Cout", [(2, 16, 16, 64, 64), (2, 64, 64, 512, 512), (3, 32, 32, 256, 256), (2, 8, 8, 32, 16)])
 def test_conv_down_and_dgrad(N, H, W, Cin, Cout):
     o = ops()
@@ -113,6 +125,7 @@ def test_conv_down_and_dgrad(N, H, W, Cin, Cout):
     assert rel_err(od[..., :Cin].permute(0, 3, 1, 2), refd) < 2e-3
 
 
+@pytest.mark.usefixtures("conv_sched")
 @pytest.mark.parametrize("N,H,W,Cin,Cout", [(2, 16, 16, 128, 256), (2, 32, 32, 256, 512), (2, 8, 8, 32, 16)])
 def test_convT_up_and_dgrad(N, H, W, Cin, Cout):
     o = ops()
@@ -383,6 +396,7 @@ def test_adamw_and_clip():
         assert torch.allclose(p, p_ref.detach(), rtol=1e-5, atol=1e-7)
 
 
+@pytest.mark.usefixtures("conv_sched")
 @pytest.mark.parametrize("N,H,W,Cin,Cout,kind", [(2, 64, 64, 128, 512, 0), (3, 16, 16, 64, 128, 0), (2, 32, 32, 256, 256, 1),
                                                  (2, 16, 16, 128, 256, 2), (2, 8, 8, 64, 128, 0)])
 def test_conv_fused_groupnorm_stats(N, H, W, Cin, Cout, kind):
@@ -415,6 +429,7 @@ def test_conv_fused_groupnorm_stats(N, H, W, Cin, Cout, kind):
     assert torch.allclose(st[..., 1], ref[..., 1], rtol=1e-5)
 
 
+@pytest.mark.usefixtures("conv_sched")
 @pytest.mark.parametrize("N,H,W,Cin,Cout,R", [(2, 16, 16, 128, 128, 3), (1, 64, 64, 1028, 512, 3), (2, 16, 16, 64, 64, 1)])
 def test_conv_split_bf16_fp32_mode(N, H, W, Cin, Cout, R):
     """Split-bf16 operands (hi + lo): the conv matches an fp32 convolution of the UNROUNDED inputs to ~2^-16."""
@@ -445,6 +460,7 @@ def test_conv_split_bf16_fp32_mode(N, H, W, Cin, Cout, R):
     assert rel_err(of2[..., :Cout].permute(0, 3, 1, 2), ref) > 5e-4
 
 
+@pytest.mark.usefixtures("conv_sched")
 @pytest.mark.parametrize("N,H,W,Cin,Cout,kind", [(3, 8, 8, 64, 1028, 0), (5, 4, 4, 32, 48, 0), (1, 64, 64, 512, 1028, 0),
                                                  (3, 8, 8, 32, 16, 2), (3, 8, 8, 32, 48, 1)])
 def test_conv_epilogue_writes_stay_in_bounds(N, H, W, Cin, Cout, kind):
@@ -507,3 +523,29 @@ def test_wgrad_exchanged_operand_roles(N, H, W, Cin, Cout, R):
                  flip=True)
     torch.cuda.synchronize()
     assert rel_err(grad, ref) < 2e-3
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout,R", [(3, 32, 32, 256, 256, 3), (5, 8, 8, 64, 48, 3), (1, 64, 64, 512, 1028, 3)])
+def test_conv_cta_pair_is_bit_identical_to_single_cta(N, H, W, Cin, Cout, R):
+    """Both schedules accumulate the same K blocks in the same order into fp32 TMEM: outputs must match bit for bit
+    (includes an odd number of M tiles, where the peer CTA of the last pair works on zero-filled rows)."""
+    from tempo_vae_b200._lib import lib
+    o = ops()
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = bf16_round(torch.randn((N, Cin, H, W), device="cuda", generator=g))
+    w = bf16_round(torch.randn((Cout, Cin, R, R), device="cuda", generator=g) / math.sqrt(Cin * R * R))
+    b = torch.randn((Cout,), device="cuda", generator=g)
+    xp = nhwc_bf16(x, o.round_up(Cin, 8))
+    wp = o.pack_weight(w, "fwd")
+    outs = []
+    prev = lib.tvae_conv_set_cta_pair(1)
+    try:
+        for mode in (1, 0):
+            lib.tvae_conv_set_cta_pair(mode)
+            of, ob = o.conv_gemm(xp, Cin, wp, kind=0, R=R, Cout=Cout, bias=b, want_f32=True, want_bf16=True)
+            torch.cuda.synchronize()
+            outs.append((of[..., :Cout].clone(), ob[..., :Cout].clone()))
+    finally:
+        lib.tvae_conv_set_cta_pair(prev)
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert torch.equal(outs[0][1], outs[1][1])
