@@ -102,26 +102,69 @@ def synthetic_batch(torch, B, shape, device, seed):
 
 
 # ================================================================================================= reference arm
-def oracle_step_fn(torch, cfg_B):
+def oracle_step_fn(torch, device="cpu", autocast=False):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import tempo_vae_oracle as orc
     import tempo_vae_b200.model as m
     torch.manual_seed(42)
     vae = m.AutoencoderKL({k: v for k, v in m.DEFAULT_ENC_DEC.items()}, embed_dim=32, kl_weight=1e-6, nll_loss_type="l1")
-    params = {k: v.detach().clone() for k, v in m.SpectralVAE(vae).state_dict().items()}
+    params = {k: v.detach().clone().to(device) for k, v in m.SpectralVAE(vae).state_dict().items()}
     state = {}
     cfg = orc.DEFAULT_CFG
-    g = torch.Generator().manual_seed(0)
+    g = torch.Generator(device=device).manual_seed(0)
     step_no = [0]
 
-    def step(B):
-        x = torch.randn((B, 1028, 64, 64), generator=g).clamp_(-10, 10)
-        eps = torch.randn((B, 32, 16, 16), generator=g)
-        grads, out = orc.grads_of(lambda leaves: orc.vae_loss(leaves, x, eps, cfg), params)
+    def step(B, x=None):
+        if x is None:
+            x = torch.randn((B, 1028, 64, 64), generator=g, device=device).clamp_(-10, 10)
+        eps = torch.randn((B, 32, 16, 16), generator=g, device=device)
+
+        def loss_fn(leaves):
+            if autocast:
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    return orc.vae_loss(leaves, x, eps, cfg)
+            return orc.vae_loss(leaves, x, eps, cfg)
+        grads, out = orc.grads_of(loss_fn, params)
         step_no[0] += 1
         orc.clip_and_adamw(params, grads, state, step=step_no[0])
-        return float(out["loss"])
+        return out["loss"]
     return step
+
+
+def run_reference_gpu(args):
+    """Same-box comparator: the oracle's restatement of the reference train step executed by
+    stock PyTorch eager kernels (cuDNN/cuBLAS/ATen) on the B200 -- what a user of the reference gets on this GPU.
+    `--ref-device cuda --ref-precision {fp32,tf32,bf16}`; inputs resident in HBM, CUDA events."""
+    import torch
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    dev = torch.device("cuda", 0)
+    torch.backends.cudnn.benchmark = True
+    tf32 = args.ref_precision != "fp32"
+    torch.backends.cudnn.allow_tf32 = tf32
+    torch.backends.cuda.matmul.allow_tf32 = tf32
+    step = oracle_step_fn(torch, dev, autocast=(args.ref_precision == "bf16"))
+    B = args.batch
+    xs = [synthetic_batch(torch, B, (1028, 64, 64), dev, seed=i) for i in range(2)]
+    for i in range(max(args.warmup, 1)):
+        step(B, xs[i % 2])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        loss = step(B, xs[i % 2])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    v = B / (ms / 1e3)
+    print(json.dumps({
+        "impl": "reference", "comparator": f"oracle restatement on PyTorch eager CUDA kernels, {args.ref_precision}",
+        "metric": "train samples/sec (fwd+bwd+AdamW)", "value": v, "unit": "samples/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": args.ref_precision, "data": "synthetic",
+        "config": {"workload": "default TEMPO-VAE train step, synthetic patches [1028,64,64]", "batch_per_gpu": B},
+        "peak_hbm_gb": torch.cuda.max_memory_allocated(dev) / 1e9, "final_loss": float(loss),
+    }), flush=True)
 
 
 def run_reference(args):
@@ -131,7 +174,7 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    step = oracle_step_fn(torch, None)
+    step = oracle_step_fn(torch)
     t0 = time.perf_counter(); step(1); t1 = time.perf_counter() - t0            # also the first warm-up
     budget = 150.0
     B = int(max(1, min(8, budget / max(1e-3, (args.steps + max(args.warmup - 1, 0)) * t1))))
@@ -310,7 +353,7 @@ def run_ours(args):
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
-        step = oracle_step_fn(torch, None)
+        step = oracle_step_fn(torch)
         step(1)
         cb = 4
         t0 = time.perf_counter(); step(cb); dt = time.perf_counter() - t0
@@ -410,13 +453,18 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="samples per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
+                    help="--impl reference only: cpu = the contract's reference arm; cuda = same-box PyTorch-eager comparator")
+    ap.add_argument("--ref-precision", default="tf32", choices=["fp32", "tf32", "bf16"])
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: skip the host-fed leg")
     ap.add_argument("--workload", default="train", choices=["train", "train_l2", "encode"],
                     help="train = headline (BASELINE config 2/4); train_l2 = L2-supervised variant (config 3); "
                          "encode = inference-only patch sweep of synthetic granules (config 5). The extra workloads "
                          "print their own JSON line and are not the headline metric.")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.impl == "reference" and args.ref_device == "cuda":
+        run_reference_gpu(args)
+    elif args.impl == "reference":
         run_reference(args)
     elif args.workload == "train":
         run_ours(args)

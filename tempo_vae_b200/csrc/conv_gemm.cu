@@ -561,8 +561,7 @@ extern "C" int32_t tvae_conv_gemm(const tvae_conv_args* a, cudaStream_t stream) 
     const int total = (p.m_tiles + 1) / 2 * p.n_tiles;
     int grid = num_sms() / 2;
     if (grid > total) grid = total;
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * grid);
     cfg.blockDim = dim3(NTHREADS);
     cfg.dynamicSmemBytes = SMEM_BYTES;
