@@ -212,8 +212,10 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         from tempo_vae_b200.parallel import bind_to_gpu_numa
-        bind_to_gpu_numa(local)          # pinned host batches on the GPU's own NUMA node
+        numa_bound = bind_to_gpu_numa(local)          # pinned host batches on the GPU's own NUMA node
         dist.init_process_group("nccl", device_id=dev)
+    else:
+        numa_bound = None
     B = args.batch
     shape = (1028, 64, 64)
 
@@ -346,6 +348,7 @@ def run_ours(args):
                 "ms_per_step": e2e_ms, "api": "Trainer.train_step over DevicePrefetcher (pinned host batches)"},
         "gpu_launches": launches,
         "host_enqueue_ms_per_step": host_enqueue_ms,
+        "numa_bound": numa_bound, "host_cpus": len(os.sched_getaffinity(0)),
         "peak_hbm_gb": torch.cuda.max_memory_allocated(dev) / 1e9,
         "clocks": clocks,
         "final_metrics": final,

@@ -69,10 +69,9 @@ typedef struct {
   void* out_bf16_lo;
 } tvae_conv_args;
 int32_t tvae_conv_gemm(const tvae_conv_args* args, tvae_stream_t stream);
-/* Scheduling switch (results are bit-identical either way): 1 runs tvae_conv_gemm as clusters of two CTAs that
- * share one 256-row tcgen05 MMA (cta_group::2, each SM stages half of the weight tile); 0 (default: measured 1 %
- * faster in the train step, the kernel is power-bound, not operand-bound) runs one CTA per SM.
- * Returns the previous setting. Process-wide; meant for A/B measurements and tests. */
+/* Scheduling switch (results are bit-identical either way): 1 (default) runs tvae_conv_gemm as clusters of two CTAs
+ * that share one 256-row tcgen05 MMA (cta_group::2, each SM stages half of the weight tile, a third less operand
+ * traffic per SM); 0 runs one CTA per SM. Returns the previous setting. Process-wide; for A/B measurements and tests. */
 int32_t tvae_conv_set_cta_pair(int32_t enable);
 
 /* Weight gradient: grad[m][n][tap] (=|+=) sum_pixels P[pixel][m] * Q[pixel (+) tap][n].

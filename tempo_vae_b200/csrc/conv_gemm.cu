@@ -129,7 +129,10 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // The whole warp runs the loop and one elected lane issues: with warp-uniform control flow the compiler keeps
+    // coordinates and addresses in uniform registers and emits each UTMALDG once. (Under `if (lane == 0)` every
+    // uniform-datapath instruction was wrapped in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop.)
+    {
       int stage = 0;
       uint32_t phase = 0;
       // bytes of BOTH CTAs' loads for a pair (counted on the leader's barrier)
@@ -149,16 +152,19 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
               const CUtensorMap* bm = seg == 1 ? &maps.blo : &maps.b;
               mbar_wait(&empty_bar[stage], phase ^ 1, 1);
               uint8_t* sa = smem + stage * STAGE_BYTES;
-              if (PAIR) {
-                const uint32_t fb = mapa_u32(smem_u32(&full_bar[stage]), 0);
-                if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
-                tma_load_4d_pair(am, fb, sa, cb * BK, ww, hh, n0);
-                tma_load_2d_pair(bm, fb, sa + A_STAGE_BYTES, kb * BK, brow);
-              } else {
-                mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
-                tma_load_4d(am, &full_bar[stage], sa, cb * BK, ww, hh, n0);
-                tma_load_2d(bm, &full_bar[stage], sa + A_STAGE_BYTES, kb * BK, brow);
+              if (elect_one()) {
+                if (PAIR) {
+                  const uint32_t fb = mapa_u32(smem_u32(&full_bar[stage]), 0);
+                  if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+                  tma_load_4d_pair(am, fb, sa, cb * BK, ww, hh, n0);
+                  tma_load_2d_pair(bm, fb, sa + A_STAGE_BYTES, kb * BK, brow);
+                } else {
+                  mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+                  tma_load_4d(am, &full_bar[stage], sa, cb * BK, ww, hh, n0);
+                  tma_load_2d(bm, &full_bar[stage], sa + A_STAGE_BYTES, kb * BK, brow);
+                }
               }
+              __syncwarp();
               if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
           }
@@ -167,7 +173,10 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0 && rank == 0) {
+    // Same structure: all lanes wait and count, one elected lane issues the MMAs and their commits. The issuing
+    // thread was the bottleneck (ncu source view: ~90 SASS instructions per K block, 655 cycles per 512 cycles of
+    // tensor work) as long as the whole loop lived inside a single-lane branch.
+    if (rank == 0) {
       const uint32_t idesc = make_idesc_bf16(PAIR ? 2 * BM : BM, p.bn, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -187,19 +196,26 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
               const uint64_t da = make_smem_desc_sw128(sa, 16, 1024);
               const uint64_t db = make_smem_desc_sw128(sa + A_STAGE_BYTES, 16, 1024);
               const int nk = (cb == p.cblks - 1) ? p.last_k16 : 4;
-              for (int k = 0; k < nk; ++k) {
-                // +32 B per K=16 step inside the 128-B swizzle row (descriptor address is in 16-B units)
-                if (PAIR) umma_bf16_pair(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k | seg) != 0);
-                else umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k | seg) != 0);
+              const bool last = (kb == p.num_kb - 1) && (seg == p.nseg - 1);
+              if (elect_one()) {
+                for (int k = 0; k < nk; ++k) {
+                  // +32 B per K=16 step inside the 128-B swizzle row (descriptor address is in 16-B units)
+                  if (PAIR) umma_bf16_pair(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k | seg) != 0);
+                  else umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k | seg) != 0);
+                }
+                // commits track the MMAs of the issuing thread: same elected lane
+                if (PAIR) umma_commit_pair(&empty_bar[stage]);
+                else umma_commit(&empty_bar[stage]);
+                if (last) {
+                  if (PAIR) umma_commit_pair(&tfull_bar[as]);
+                  else umma_commit(&tfull_bar[as]);
+                }
               }
-              if (PAIR) umma_commit_pair(&empty_bar[stage]);
-              else umma_commit(&empty_bar[stage]);
+              __syncwarp();
               if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
           }
         }
-        if (PAIR) umma_commit_pair(&tfull_bar[as]);
-        else umma_commit(&tfull_bar[as]);
         as ^= 1;
         if (as == 0) aphase ^= 1;
       }
@@ -386,10 +402,12 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
   }
 }
 
-// Off by default: measured on B200 (B=256 train step, alternating runs) the pair schedule is 1.1 % SLOWER
-// (137.8/138.4 vs 136.3/136.7 ms per step). The single-CTA kernel already runs at the power-capped tensor roofline
-// (1.40 PFLOP/s = the sustained cuBLAS bf16 figure), so saving a third of the L2->SM operand traffic buys nothing.
-int g_conv_cta_pair = 0;
+// On by default. History (B=256 train step, alternating runs on one box): while the MMA-issuing thread was the
+// bottleneck (single-lane branch, see the MMA issuer above) the pair schedule was 1 % slower than one CTA per SM;
+// with the elected-lane issue loop it is 5 % faster in the step (116.4 vs 123.1 ms) and the bf16-output launch runs
+// at 1.64 PFLOP/s (3.01 ms) against 1.1-1.2 PFLOP/s for the single-CTA schedule, which is then limited by the
+// 96 B/clk/SM of operand traffic that the pair schedule cuts to 64 B/clk/SM.
+int g_conv_cta_pair = 1;
 
 int pick_bn(int cout) {
   if (cout <= 256) return (cout + 15) / 16 * 16;

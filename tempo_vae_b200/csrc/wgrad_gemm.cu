@@ -83,7 +83,7 @@ wgrad_gemm_kernel(const __grid_constant__ WgradMaps maps, const __grid_constant_
   const int total_units = units_per_split * p.splits;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {   // all lanes loop (warp-uniform control flow => uniform registers), one elected lane issues the TMA loads
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t tx_bytes = (uint32_t)(2 + p.nq) * CHUNK_BYTES;
@@ -107,18 +107,21 @@ wgrad_gemm_kernel(const __grid_constant__ WgradMaps maps, const __grid_constant_
           mbar_wait(&empty_bar[stage], phase ^ 1, 11);
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_STAGE_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
-          tma_load_4d(&maps.p, &full_bar[stage], sa, mt * BM, w0, h0, n0);
-          tma_load_4d(&maps.p, &full_bar[stage], sa + CHUNK_BYTES, mt * BM + 64, w0, h0, n0);
-          for (int j = 0; j < p.nq; ++j)
-            tma_load_4d(qm, &full_bar[stage], sb + j * CHUNK_BYTES, nt * p.bn + j * 64, w0 + p.dw[tap],
-                        h0 + p.dh[tap], n0);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+            tma_load_4d(&maps.p, &full_bar[stage], sa, mt * BM, w0, h0, n0);
+            tma_load_4d(&maps.p, &full_bar[stage], sa + CHUNK_BYTES, mt * BM + 64, w0, h0, n0);
+            for (int j = 0; j < p.nq; ++j)
+              tma_load_4d(qm, &full_bar[stage], sb + j * CHUNK_BYTES, nt * p.bn + j * 64, w0 + p.dw[tap],
+                          h0 + p.dh[tap], n0);
+          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // all lanes wait and count, one elected lane issues the MMAs and their commits (see conv_gemm.cu)
       const uint32_t idesc = make_idesc_bf16(BM, p.bn, 1, 1);
       int stage = 0;
       uint32_t phase = 0;
@@ -138,15 +141,18 @@ wgrad_gemm_kernel(const __grid_constant__ WgradMaps maps, const __grid_constant_
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
           const uint64_t da = make_smem_desc_sw128(sa, CHUNK_BYTES, 1024);
           const uint64_t db = make_smem_desc_sw128(sa + A_STAGE_BYTES, CHUNK_BYTES, 1024);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BKP / 16; ++k) {
-            // 16 pixels = two 8-row swizzle atoms = 2048 B further along K
-            umma_bf16(d_tmem, da + (uint64_t)(k * 128), db + (uint64_t)(k * 128), idesc, (kb > kb0) || (k > 0));
+            for (int k = 0; k < BKP / 16; ++k) {
+              // 16 pixels = two 8-row swizzle atoms = 2048 B further along K
+              umma_bf16(d_tmem, da + (uint64_t)(k * 128), db + (uint64_t)(k * 128), idesc, (kb > kb0) || (k > 0));
+            }
+            umma_commit(&empty_bar[stage]);
+            if (kb == kb1 - 1) umma_commit(&tfull_bar[as]);
           }
-          umma_commit(&empty_bar[stage]);
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[as]);
         as ^= 1;
         if (as == 0) aphase ^= 1;
       }

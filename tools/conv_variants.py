@@ -45,3 +45,27 @@ run("f32 out + stats, random weights", w_rand, x, want_f32=True, stats=(8, 1e-6)
 run("f32 out + residual, random weights", w_rand, x, want_f32=True, residual=res)
 run("f32 out only, low-entropy weights (+-1e-4)", w_low, x, want_f32=True)
 run("bf16 out only, zero activations", w_rand, torch.zeros_like(x), want_f32=False, want_bf16=True)
+
+# weight-gradient GEMM of the same layer, sustained (same flops as one conv launch)
+dy = torch.randn((B, 64, 64, 512), device="cuda", generator=g).to(torch.bfloat16)
+grad = torch.empty((512, 512, 3, 3), device="cuda")
+
+
+def run_wgrad(tag, p, q):
+    for _ in range(3):
+        o.wgrad_gemm(p, 512, q, 512, kind=0, R=3, grad=grad)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(10):
+        o.wgrad_gemm(p, 512, q, 512, kind=0, R=3, grad=grad)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    print(f"{tag:46s} {ms:6.3f} ms  {flops / ms / 1e9:7.1f} TFLOP/s", flush=True)
+
+
+for rep in range(2):
+    run_wgrad("wgrad 512x512x3x3, random dY / x", dy, x)
+    run("conv bf16 out only (same flops)", w_rand, x, want_f32=False, want_bf16=True)
+run_wgrad("wgrad, zero dY", torch.zeros_like(dy), x)

@@ -1,4 +1,5 @@
-"""Two launches for ncu: bf16-out-only and f32+bf16+residual+stats on the dominant conv shape."""
+"""Launches for one `ncu --set full` capture (-k regex:gemm_kernel): the dominant conv shape with three epilogues, its
+CTA-pair schedule, and the weight-gradient GEMM of the same layer."""
 import os, sys, math, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from tempo_vae_b200 import ops as o
@@ -14,3 +15,13 @@ o.conv_gemm(x, 512, wp, kind=0, R=3, Cout=512, bias=bias, want_f32=True)
 o.conv_gemm(x, 512, wp, kind=0, R=3, Cout=512, bias=bias, want_f32=True, want_bf16=True, residual=res, stats=(8, 1e-6))
 torch.cuda.synchronize()
 print("ok")
+# the CTA-pair schedule of the same bf16-out launch, and the weight-gradient GEMM of the same layer
+from tempo_vae_b200._lib import lib
+lib.tvae_conv_set_cta_pair(1)
+o.conv_gemm(x, 512, wp, kind=0, R=3, Cout=512, bias=bias, want_f32=False, want_bf16=True)
+lib.tvae_conv_set_cta_pair(0)
+dy = torch.randn((B, 64, 64, 512), device="cuda", generator=g).to(torch.bfloat16)
+grad = torch.empty((512, 512, 3, 3), device="cuda")
+o.wgrad_gemm(dy, 512, x, 512, kind=0, R=3, grad=grad)
+torch.cuda.synchronize()
+print("ok2")
