@@ -39,9 +39,10 @@ DEFAULT_MODEL = dict(
     optimizer_params=dict(lr=1e-4, betas=[0.9, 0.95], weight_decay=0.05),
 )
 FWD_GF, BWD_GF = 165.776, 292.746          # algorithmic conv GFLOP / sample
-# dram bytes of one 512->512 3x3 @64x64 launch at B=256 from the committed ncu capture (1.080 GB read + 2.098 GB
-# written; the launch reads a 1.07 GB bf16 activation + 4.7 MB of weights and writes a 2.15 GB fp32 tensor)
-NCU_CONV_TRAFFIC_BYTES = 3.178e9
+# dram bytes of one 512->512 3x3 @64x64 launch at B=256 from the committed ncu capture (profiles/ncu_gemm_r1.md,
+# launch 1: 1.084 GB read + 2.104 GB written; the launch reads a 1.07 GB bf16 activation + 4.7 MB of weights and
+# writes a 2.15 GB fp32 tensor)
+NCU_CONV_TRAFFIC_BYTES = 3.188e9
 
 
 def peaks():
@@ -339,8 +340,10 @@ def run_ours(args):
                      "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
                      "traffic": NCU_CONV_TRAFFIC_BYTES if B == 256 else None,
                      "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch "
-                                       "(profiles/ncu_conv_r1.md); algorithmic bytes per launch 3.22e9",
-                     "peak_source": pk["source"] + ", bf16_tflops_sustained",
+                                       "(profiles/ncu_gemm_r1.md); algorithmic bytes per launch 3.22e9",
+                     "peak_source": pk["source"] + ", bf16_tflops_sustained (cuBLAS back to back for 4 s: the figure "
+                                    "for a kernel timed inside a long step)",
+                     "frac_of_burst_peak": achieved / pk["burst"], "burst_peak": pk["burst"],
                      "launches_timed": len(conv_ms), "avg_ms": conv_avg,
                      "wgrad_kernel": {"avg_ms": wg_avg, "achieved": conv_flops / (wg_avg * 1e-3) / 1e12,
                                       "launches_timed": len(wg_ms)}},
