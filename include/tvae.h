@@ -135,11 +135,14 @@ int32_t tvae_gn_act_fwd(const float* x, const float* stats, const float* gamma, 
                         int32_t HW, int32_t C, int32_t G, int32_t act, void* out_bf16, void* out_lo,
                         tvae_stream_t stream);
 /* da: bf16 gradient wrt the activation output; gres (optional bf16) is added to dx (residual branch).
- * dgamma/dbeta are overwritten. workspace: tvae_gn_bwd_workspace_bytes(N, HW, C, G). */
+ * dgamma/dbeta are overwritten. dx_colsum (optional, float[C]): column sums of dx over all N*HW pixels, i.e. the bias
+ * gradient of the conv whose output x is -- produced by the same pass that writes dx.
+ * workspace: tvae_gn_bwd_workspace_bytes(N, HW, C, G). */
 int64_t tvae_gn_bwd_workspace_bytes(int32_t N, int32_t HW, int32_t C, int32_t G);
 int32_t tvae_gn_act_bwd(const float* x, const float* stats, const float* gamma, const float* beta, const void* da_bf16,
                         const void* gres_bf16, int32_t N, int32_t HW, int32_t C, int32_t G, int32_t act,
-                        void* dx_bf16, float* dgamma, float* dbeta, float* workspace, tvae_stream_t stream);
+                        void* dx_bf16, float* dgamma, float* dbeta, float* dx_colsum, float* workspace,
+                        tvae_stream_t stream);
 
 /* Column sums: out[c] = sum_rows x[row][c] (bias gradients). x bf16 [rows][pitch]; workspace rows_blocks*C floats:
  * tvae_colsum_workspace_bytes(rows, C). */

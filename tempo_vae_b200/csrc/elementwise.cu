@@ -578,12 +578,13 @@ extern "C" int32_t tvae_gn_act_fwd(const float* x, const float* stats, const flo
 
 extern "C" int64_t tvae_gn_bwd_workspace_bytes(int32_t N, int32_t HW, int32_t C, int32_t G) {
   if (gn_fast_ok(C, G)) return gn_bwd_fast_ws_floats(N, HW, C, G) * 4;
-  return (2ll * N * C + 2ll * N * G) * 4;
+  // generic kernels: sums + group means, then the partials of a column-sum pass over dx (dx_colsum)
+  return (2ll * N * C + 2ll * N * G) * 4 + (int64_t)colsum_blocks((long long)N * HW) * C * 4;
 }
 
 extern "C" int32_t tvae_gn_act_bwd(const float* x, const float* stats, const float* gamma, const float* beta,
                                    const void* da, const void* gres, int32_t N, int32_t HW, int32_t C, int32_t G,
-                                   int32_t act, void* dx, float* dgamma, float* dbeta, float* ws,
+                                   int32_t act, void* dx, float* dgamma, float* dbeta, float* dx_colsum, float* ws,
                                    cudaStream_t stream) {
   TVAE_ENTER(x);
   TVAE_CHECK(x && stats && gamma && beta && da && dx && dgamma && dbeta && ws, "tvae_gn_act_bwd: null pointer");
@@ -595,7 +596,7 @@ extern "C" int32_t tvae_gn_act_bwd(const float* x, const float* stats, const flo
   __nv_bfloat16* dxp = reinterpret_cast<__nv_bfloat16*>(dx);
   const float* gmeans = ws + 2ll * N * C;
   if (gn_fast_ok(C, G)) {
-    gn_act_bwd_fast(x, stats, gamma, beta, dap, grp, N, HW, C, G, act, dxp, dgamma, dbeta, ws, stream);
+    gn_act_bwd_fast(x, stats, gamma, beta, dap, grp, N, HW, C, G, act, dxp, dgamma, dbeta, dx_colsum, ws, stream);
     TVAE_CUDA(cudaGetLastError());
     return 0;
   }
@@ -618,6 +619,8 @@ extern "C" int32_t tvae_gn_act_bwd(const float* x, const float* stats, const flo
                                                                         HW, C, G, act, dxp);
   }
   TVAE_CUDA(cudaGetLastError());
+  if (dx_colsum)   // generic shapes: a separate pass over dx
+    return tvae_colsum_bf16(dx, rows, C, C, dx_colsum, ws + 2ll * N * C + 2ll * N * G, stream);
   return 0;
 }
 

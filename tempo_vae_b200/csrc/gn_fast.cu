@@ -77,22 +77,26 @@ gn_act_fwd_fast_kernel(const float* __restrict__ x, const float* __restrict__ st
 }
 
 // dx = rstd * (dy*gamma - m1 - xhat*m2) (+ gres), dy = da * act'(gamma*xhat + beta)
+// cs_part (optional): per-block column sums of the bf16 values written to dx, [n][chunk][C] -- dx is the output
+// gradient of the conv that produced x, so its column sums are that conv's bias gradient and the separate pass over
+// dx (tvae_colsum_bf16) disappears.
 __global__ void __launch_bounds__(256)
 gn_bwd_apply_fast_kernel(const float* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gamma,
                          const float* __restrict__ beta, const __nv_bfloat16* __restrict__ da,
                          const __nv_bfloat16* __restrict__ gres, const float* __restrict__ gmeans, int HW, int C, int G,
-                         int act, int rpb, __nv_bfloat16* __restrict__ dx) {
+                         int act, int rpb, __nv_bfloat16* __restrict__ dx, float* __restrict__ cs_part) {
+  __shared__ float cs_sm[256 * 8];
   const int U = C >> 3, lanes = 256 / U;
   const int u = threadIdx.x % U, lane = threadIdx.x / U;
   const int c = u << 3, n = blockIdx.y;
   const int sg = n * G + c / (C / G);
   const float mean = stats[2 * sg], rstd = stats[2 * sg + 1];
   const float m1r = gmeans[2 * sg] * rstd, m2r = gmeans[2 * sg + 1] * rstd;
-  float gm[8], bt[8], gr[8];
+  float gm[8], bt[8], gr[8], cs[8];
   load8(gamma + c, gm);
   load8(beta + c, bt);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) gr[j] = gm[j] * rstd;
+  for (int j = 0; j < 8; ++j) { gr[j] = gm[j] * rstd; cs[j] = 0.f; }
   const int r0 = blockIdx.x * rpb;
   const int r1 = min(r0 + rpb, HW);
   const long long base = (long long)n * HW * C + c;
@@ -114,9 +118,52 @@ gn_bwd_apply_fast_kernel(const float* __restrict__ x, const float* __restrict__ 
       float dy = dv[j];
       if (act) dy *= act_grad_fast(fmaf(xh, gm[j], bt[j]), act);
       o[j] = fmaf(dy, gr[j], rv[j]) - fmaf(xh, m2r, m1r);
+      cs[j] += __bfloat162float(__float2bfloat16(o[j]));   // what the consumers of dx will read
     }
     store8_bf16(dx + off, o);
   }
+  if (cs_part) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) cs_sm[threadIdx.x * 8 + j] = cs[j];
+    __syncthreads();
+    float* out = cs_part + ((long long)n * gridDim.x + blockIdx.x) * C;
+    for (int t = threadIdx.x; t < U * 8; t += 256) {
+      const int uu = t >> 3, k = t & 7;
+      float acc = 0.f;
+      for (int l = 0; l < lanes; ++l) acc += cs_sm[(l * U + uu) * 8 + k];   // fixed order
+      out[(uu << 3) + k] = acc;
+    }
+  }
+}
+
+// column sums of a [rows][C] fp32 matrix in two fixed-order stages: slice sums, then the sum of the slices
+constexpr int CS_SLICES = 32;
+__global__ void __launch_bounds__(256)
+colsum_rows_slice_kernel(const float* __restrict__ part, int rows, int C, float* __restrict__ slices) {
+  __shared__ float sa[8][33];
+  const int cx = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  const int per = (rows + CS_SLICES - 1) / CS_SLICES;
+  const int r0 = blockIdx.y * per, r1 = min(r0 + per, rows);
+  float a = 0.f;
+  if (c < C)
+    for (int r = r0 + rl; r < r1; r += 8) a += part[(long long)r * C + c];
+  sa[rl][cx] = a;
+  __syncthreads();
+  if (rl == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int l = 0; l < 8; ++l) t += sa[l][cx];
+    slices[(long long)blockIdx.y * C + c] = t;
+  }
+}
+__global__ void colsum_rows_final_kernel(const float* __restrict__ slices, int C, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float t = 0.f;
+#pragma unroll 8
+  for (int s = 0; s < CS_SLICES; ++s) t += slices[(long long)s * C + c];
+  out[c] = t;
 }
 
 // Stage A1: grid (row chunks, N) like the apply kernel (full 2 KB rows => long DRAM bursts): per-channel partial sums
@@ -257,12 +304,13 @@ int gn_act_fwd_fast(const float* x, const float* stats, const float* gamma, cons
 long long gn_bwd_fast_ws_floats(int N, int HW, int C, int G) {
   const int rpb = rows_per_block(HW);
   const long long chunks = (HW + rpb - 1) / rpb;
-  return 2ll * N * C + 2ll * N * G + (long long)N * chunks * 2 * C;
+  return 2ll * N * C + 2ll * N * G + (long long)N * chunks * 2 * C + (long long)CS_SLICES * C;
 }
 
 int gn_act_bwd_fast(const float* x, const float* stats, const float* gamma, const float* beta,
                     const __nv_bfloat16* da, const __nv_bfloat16* gres, int N, int HW, int C, int G, int act,
-                    __nv_bfloat16* dx, float* dgamma, float* dbeta, float* ws, cudaStream_t stream) {
+                    __nv_bfloat16* dx, float* dgamma, float* dbeta, float* dx_colsum, float* ws,
+                    cudaStream_t stream) {
   const int rpb = rows_per_block(HW);
   const int chunks = (HW + rpb - 1) / rpb;
   dim3 grid(chunks, N);
@@ -271,8 +319,14 @@ int gn_act_bwd_fast(const float* x, const float* stats, const float* gamma, cons
                                                                             rpb, part);
   gn_bwd_finalize_fast_kernel<<<N, 256, 2 * C * sizeof(float), stream>>>(part, gamma, chunks, HW, C, G, N, ws, nullptr);
   gn_bwd_param_fast_kernel<<<(C + 31) / 32, 256, 0, stream>>>(ws, N, C, dgamma, dbeta);
+  // the row-sum partials are consumed by now (stream order): their region is reused for the column sums of dx
   gn_bwd_apply_fast_kernel<<<grid, 256, 0, stream>>>(x, stats, gamma, beta, da, gres, ws + 2ll * N * C, HW, C, G, act,
-                                                     rpb, dx);
+                                                     rpb, dx, dx_colsum ? part : nullptr);
+  if (dx_colsum) {
+    float* slices = part + (long long)N * chunks * 2 * C;
+    colsum_rows_slice_kernel<<<dim3((C + 31) / 32, CS_SLICES), 256, 0, stream>>>(part, N * chunks, C, slices);
+    colsum_rows_final_kernel<<<(C + 127) / 128, 128, 0, stream>>>(slices, C, dx_colsum);
+  }
   return 0;
 }
 

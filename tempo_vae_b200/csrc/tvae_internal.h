@@ -33,6 +33,6 @@ int gn_act_fwd_fast(const float* x, const float* stats, const float* gamma, cons
                     int G, int act, __nv_bfloat16* out, cudaStream_t stream);
 int gn_act_bwd_fast(const float* x, const float* stats, const float* gamma, const float* beta, const __nv_bfloat16* da,
                     const __nv_bfloat16* gres, int N, int HW, int C, int G, int act, __nv_bfloat16* dx, float* dgamma,
-                    float* dbeta, float* ws, cudaStream_t stream);
+                    float* dbeta, float* dx_colsum, float* ws, cudaStream_t stream);
 
 }  // namespace tvae

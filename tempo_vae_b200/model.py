@@ -256,12 +256,16 @@ def conv_bwd(mod, dy_bf16, x_bf16, Cin, *, dgrad=None, dgrad_residual=None, bias
             if kind == 2:   # ConvTranspose2d [Cin][Cout][2][2]: P = x (coarse), Q = dy (fine)
                 ops.wgrad_gemm(x_bf16, Cin, dy_bf16, Cout, kind=1, R=2, grad=dst)
             elif kind == 0 and Cin > 256 and Cin % 256 and Cout % 128 == 0:
-                # a wide, awkward channel count (1028) goes on the GEMM's M side: operand roles exchanged
+                # a wide, awkward channel count (1028) goes on the GEMM's M side: operand roles exchanged. (Measured:
+                # the opposite choice, N = 1028 as 5 tiles of 208, pads less (1.2 % vs 12 %) but is 3 ms per launch
+                # SLOWER: a 208-wide tile still stages 256 channels per K block, and the kernel is operand-bound.)
                 ops.wgrad_gemm(x_bf16, Cin, dy_bf16, Cout, kind=0, R=R, grad=dst, flip=True)
             else:
                 ops.wgrad_gemm(dy_bf16, Cout, x_bf16, Cin, kind=kind, R=R, grad=dst)
         _write_grad(w, wg)
     if mod.bias is not None and mod.bias.requires_grad:
+        if bias_grad_from is None:
+            bias_grad_from = getattr(dy_bf16, "tvae_colsum", None)     # produced together with dy (norm_act_bwd)
         if bias_grad_from is not None:
             _write_grad(mod.bias, lambda dst: dst.copy_(bias_grad_from))
         else:
@@ -295,9 +299,12 @@ def norm_act_fwd(norm, h_f32, act_code, stats=None):
 
 
 def norm_act_bwd(norm, h_f32, stats, da_bf16, gres_bf16, act_code):
+    """Returns dx (bf16). dx is the output gradient of the conv(s) that produced h: its column sums (their bias
+    gradient) come out of the same pass and ride along as `dx.tvae_colsum`, which conv_bwd picks up."""
     gamma, beta = norm.affine_params()
     C = norm.num_channels
     dev = h_f32.device
+    cs = torch.empty((C,), dtype=torch.float32, device=dev)
     train_affine = norm.affine and gamma.requires_grad
     if train_affine:
         dg, acc_g = _grad_begin(gamma)
@@ -308,14 +315,15 @@ def norm_act_bwd(norm, h_f32, stats, da_bf16, gres_bf16, act_code):
         acc_g = acc_b = False
     if acc_g or acc_b:
         tg, tb = torch.empty_like(dg), torch.empty_like(db)
-        dx = ops.gn_act_bwd(h_f32, stats, gamma, beta, da_bf16, gres_bf16, norm.num_groups, act_code, tg, tb)
+        dx = ops.gn_act_bwd(h_f32, stats, gamma, beta, da_bf16, gres_bf16, norm.num_groups, act_code, tg, tb, cs)
         dg.add_(tg)
         db.add_(tb)
     else:
-        dx = ops.gn_act_bwd(h_f32, stats, gamma, beta, da_bf16, gres_bf16, norm.num_groups, act_code, dg, db)
+        dx = ops.gn_act_bwd(h_f32, stats, gamma, beta, da_bf16, gres_bf16, norm.num_groups, act_code, dg, db, cs)
     if train_affine:
         _grad_done(gamma)
         _grad_done(beta)
+    dx.tvae_colsum = cs
     return dx
 
 

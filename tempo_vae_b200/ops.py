@@ -33,7 +33,7 @@ KERNEL_LAUNCHES = [0]   # kernels of libtvae_b200.so enqueued through this modul
 _KERNELS_PER_CALL = {
     "tvae_pack_weight": 1, "tvae_conv_gemm": 1, "tvae_wgrad_gemm": 2, "tvae_nchw_f32_to_nhwc_bf16": 1,
     "tvae_nhwc_f32_to_nchw_f32": 1, "tvae_nhwc_bf16_to_nchw_f32": 1, "tvae_f32_to_bf16": 1, "tvae_gn_stats": 1,
-    "tvae_gn_act_fwd": 1, "tvae_gn_stats_finalize": 1, "tvae_gn_act_bwd": 3, "tvae_colsum_bf16": 2, "tvae_attn_fwd": 1, "tvae_attn_bwd": 2, "tvae_attn_fwd_tc": 1, "tvae_attn_bwd_tc": 2,
+    "tvae_gn_act_fwd": 1, "tvae_gn_stats_finalize": 1, "tvae_gn_act_bwd": 4, "tvae_colsum_bf16": 2, "tvae_attn_fwd": 1, "tvae_attn_bwd": 2, "tvae_attn_fwd_tc": 1, "tvae_attn_bwd_tc": 2,
     "tvae_reparam_fwd": 1, "tvae_reparam_bwd": 1, "tvae_nll_fwd": 2, "tvae_vae_loss_finalize": 1,
     "tvae_l2head_loss_fwd": 1, "tvae_l2head_loss_bwd": 1, "tvae_l2head_finalize": 1, "tvae_sumsq": 2, "tvae_adamw": 1,
 }
@@ -325,7 +325,8 @@ def gn_act_fwd(x, stats, gamma, beta, G, act):
     return _pair(out, lo)
 
 
-def gn_act_bwd(x, stats, gamma, beta, da, gres, G, act, dgamma, dbeta):
+def gn_act_bwd(x, stats, gamma, beta, da, gres, G, act, dgamma, dbeta, dx_colsum=None):
+    """dx_colsum (optional fp32 [C]): receives the column sums of dx (= bias gradient of the conv that produced x)."""
     N, H, W, Cc = x.shape
     da, gres = hi_of(da), hi_of(gres)
     assert da.shape[-1] == Cc and da.dtype == torch.bfloat16
@@ -333,7 +334,9 @@ def gn_act_bwd(x, stats, gamma, beta, da, gres, G, act, dgamma, dbeta):
     ws = _workspace(lib.tvae_gn_bwd_workspace_bytes(N, H * W, Cc, G), x.device, "gn")
     check(lib.tvae_gn_act_bwd(x.data_ptr(), stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), da.data_ptr(),
                               _ptr(gres), N, H * W, Cc, G, int(act), dx.data_ptr(), dgamma.data_ptr(),
-                              dbeta.data_ptr(), ws.data_ptr(), _stream()), "tvae_gn_act_bwd")
+                              dbeta.data_ptr(), _ptr(dx_colsum), ws.data_ptr(), _stream()), "tvae_gn_act_bwd")
+    if dx_colsum is not None:
+        KERNEL_LAUNCHES[0] += 2
     return dx
 
 

@@ -225,12 +225,21 @@ def test_groupnorm_gelu_fwd_bwd(N, H, W, C, G, act, eps):
     assert torch.allclose(stats[..., 0], ref_stats_mean, atol=1e-5)
     assert rel_err(a.float().permute(0, 3, 1, 2), y.detach()) < 1e-2  # bf16 output rounding
     dgamma = torch.empty((C,), device="cuda"); dbeta = torch.empty((C,), device="cuda")
+    colsum = torch.full((C,), float("nan"), device="cuda")
     dx = o.gn_act_bwd(xn, stats, gamma.detach(), beta.detach(), da.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16),
-                      gres.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16), G, act, dgamma, dbeta)
+                      gres.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16), G, act, dgamma, dbeta, colsum)
     torch.cuda.synchronize()
     assert rel_err(dx.float().permute(0, 3, 1, 2), x.grad + gres) < 1e-2
     assert rel_err(dgamma, gamma.grad) < 1e-3
     assert rel_err(dbeta, beta.grad) < 1e-3
+    # fused column sums of dx (bias gradient of the producing conv): exactly the sums of the stored bf16 values
+    ref_cs = dx.double().sum(dim=(0, 1, 2))
+    assert (colsum.double() - ref_cs).abs().max() <= 1e-5 * dx.double().abs().sum(dim=(0, 1, 2)).max() + 1e-6
+    # and the entry point still works without it
+    dx2 = o.gn_act_bwd(xn, stats, gamma.detach(), beta.detach(), da.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16),
+                       gres.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16), G, act, dgamma, dbeta)
+    torch.cuda.synchronize()
+    assert torch.equal(dx, dx2)
 
 
 @pytest.mark.parametrize("rows,C,pitch", [(4096, 512, 512), (8192, 1028, 1032), (512, 4, 8), (1000, 64, 64)])
