@@ -99,6 +99,10 @@ typedef struct {
   int32_t flip;
 } tvae_wgrad_args;
 int32_t tvae_wgrad_gemm(const tvae_wgrad_args* args, tvae_stream_t stream);
+/* Scheduling switch like tvae_conv_set_cta_pair: 1 (default) pairs adjacent 128-row M tiles on CTA pairs (cta_group::2);
+ * an odd last M tile runs as a second one-CTA-per-SM launch with its own split-K factor. Call before
+ * tvae_wgrad_splits / tvae_wgrad_workspace_bytes. Returns the previous setting. */
+int32_t tvae_wgrad_set_cta_pair(int32_t enable);
 int64_t tvae_wgrad_workspace_bytes(int32_t Cm, int32_t Cn, int32_t ntaps, int32_t splits);
 int32_t tvae_wgrad_splits(int32_t Cm, int32_t Cn, int32_t ntaps, int64_t pixels);
 

@@ -67,6 +67,7 @@ def _load():
         "tvae_conv_gemm": (i32, [C.POINTER(ConvArgs), vp]),
         "tvae_conv_set_cta_pair": (i32, [i32]),
         "tvae_wgrad_gemm": (i32, [C.POINTER(WgradArgs), vp]),
+        "tvae_wgrad_set_cta_pair": (i32, [i32]),
         "tvae_wgrad_workspace_bytes": (i64, [i32, i32, i32, i32]),
         "tvae_wgrad_splits": (i32, [i32, i32, i32, i64]),
         "tvae_pack_weight": (i32, [vp, vp, i32, i32, i32, i32, i32, i64, i64, i64, vp, vp]),
@@ -105,6 +106,8 @@ def _load():
 
 
 lib, EXPORTED = _load()
+if os.environ.get("TVAE_WGRAD_CTA_PAIR") in ("0", "1"):
+    lib.tvae_wgrad_set_cta_pair(int(os.environ["TVAE_WGRAD_CTA_PAIR"]))
 if os.environ.get("TVAE_CONV_CTA_PAIR") in ("0", "1"):     # A/B switch of the conv schedule (results are bit-identical)
     lib.tvae_conv_set_cta_pair(int(os.environ["TVAE_CONV_CTA_PAIR"]))
 

@@ -25,6 +25,11 @@ constexpr int A_STAGE_BYTES = 2 * CHUNK_BYTES;
 constexpr int B_STAGE_BYTES = 4 * CHUNK_BYTES;
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;  // 48 KB
 constexpr int STAGES = 4;
+// CTA-pair variant (cta_group::2, M = 256): each CTA stages its own 128 P channels and HALF of the Q tile
+constexpr int PAIR_STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES / 2;   // 32 KB
+constexpr int PAIR_STAGES = 6;
+static_assert(PAIR_STAGES * PAIR_STAGE_BYTES == STAGES * STAGE_BYTES, "same shared-memory budget");
+constexpr int MAX_REM_SPLITS = 16;            // split-K bound of the odd last M tile (runs as its own launch)
 constexpr int NTHREADS = 192;
 constexpr int TMEM_COLS = 512;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
@@ -40,13 +45,20 @@ struct WgradParams {
   int tiles_w, tiles_h, bw, bh, bnimg;
   int dh[9], dw[9], qmap[9];
   int cm, cn;                  // valid channels of P / Q
-  int nq;                      // 64-channel boxes of Q per stage
-  float* part;                 // [splits][cm][ntaps * cn_pitch]
+  int nq;                      // 64-channel boxes of Q per stage (per CTA)
+  float* part;                 // [splits][part_rows][ntaps * cn_pitch], row 0 = GEMM row part_row0
+  int part_rows, part_row0;
   int cn_pitch;
+  int mt0;                     // first M tile of this launch (m_tiles counts the tiles of this launch)
 };
 
+// PAIR: clusters of two CTAs, see conv_gemm.cu for the barrier topology (full/tmem-empty in the leader, empty/tmem-full
+// per CTA by multicast commit). The pair owns two adjacent M tiles (P channels) of one (N tile, tap, split) unit.
+template <bool PAIR>
 __global__ void __launch_bounds__(NTHREADS, 1)
 wgrad_gemm_kernel(const __grid_constant__ WgradMaps maps, const __grid_constant__ WgradParams p) {
+  constexpr int STAGES = PAIR ? PAIR_STAGES : tvae::STAGES;
+  constexpr int STAGE_BYTES = PAIR ? PAIR_STAGE_BYTES : tvae::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
@@ -69,30 +81,40 @@ wgrad_gemm_kernel(const __grid_constant__ WgradMaps maps, const __grid_constant_
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);
+      mbar_init(&tempty_bar[i], PAIR ? 8 : 4);
     }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+  if (warp == 1) {
+    if (PAIR) tmem_alloc_pair(tmem_ptr_smem, TMEM_COLS);
+    else tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  const int units_per_split = p.m_tiles * p.n_tiles * p.ntaps;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const int unit0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int nunits = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int mgroups = PAIR ? p.m_tiles / 2 : p.m_tiles;          // host launches an even tile count for pairs
+  const int units_per_split = mgroups * p.n_tiles * p.ntaps;
   const int total_units = units_per_split * p.splits;
+  auto m_tile_of = [&](int mg) { return p.mt0 + (PAIR ? 2 * mg + (int)rank : mg); };
 
   if (warp == 0) {
     {   // all lanes loop (warp-uniform control flow => uniform registers), one elected lane issues the TMA loads
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t tx_bytes = (uint32_t)(2 + p.nq) * CHUNK_BYTES;
-      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+      const uint32_t tx_bytes = (PAIR ? 2u : 1u) * (uint32_t)(2 + p.nq) * CHUNK_BYTES;
+      for (int u = unit0; u < total_units; u += nunits) {
         const int split = u / units_per_split;
         int r = u - split * units_per_split;
         const int tap = r % p.ntaps; r /= p.ntaps;
         const int nt = r % p.n_tiles;
-        const int mt = r / p.n_tiles;
+        const int mt = m_tile_of(r / p.n_tiles);
+        const int qch0 = nt * p.bn + (PAIR ? (int)rank * (p.bn >> 1) : 0);
         const int kb0 = (int)((long long)p.nblocks * split / p.splits);
         const int kb1 = (int)((long long)p.nblocks * (split + 1) / p.splits);
         const CUtensorMap* qm = &maps.q[p.qmap[tap]];
@@ -108,12 +130,21 @@ wgrad_gemm_kernel(const __grid_constant__ WgradMaps maps, const __grid_constant_
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_STAGE_BYTES;
           if (elect_one()) {
-            mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
-            tma_load_4d(&maps.p, &full_bar[stage], sa, mt * BM, w0, h0, n0);
-            tma_load_4d(&maps.p, &full_bar[stage], sa + CHUNK_BYTES, mt * BM + 64, w0, h0, n0);
-            for (int j = 0; j < p.nq; ++j)
-              tma_load_4d(qm, &full_bar[stage], sb + j * CHUNK_BYTES, nt * p.bn + j * 64, w0 + p.dw[tap],
-                          h0 + p.dh[tap], n0);
+            if (PAIR) {
+              const uint32_t fb = mapa_u32(smem_u32(&full_bar[stage]), 0);
+              if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+              tma_load_4d_pair(&maps.p, fb, sa, mt * BM, w0, h0, n0);
+              tma_load_4d_pair(&maps.p, fb, sa + CHUNK_BYTES, mt * BM + 64, w0, h0, n0);
+              for (int j = 0; j < p.nq; ++j)
+                tma_load_4d_pair(qm, fb, sb + j * CHUNK_BYTES, qch0 + j * 64, w0 + p.dw[tap], h0 + p.dh[tap], n0);
+            } else {
+              mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+              tma_load_4d(&maps.p, &full_bar[stage], sa, mt * BM, w0, h0, n0);
+              tma_load_4d(&maps.p, &full_bar[stage], sa + CHUNK_BYTES, mt * BM + 64, w0, h0, n0);
+              for (int j = 0; j < p.nq; ++j)
+                tma_load_4d(qm, &full_bar[stage], sb + j * CHUNK_BYTES, qch0 + j * 64, w0 + p.dw[tap],
+                            h0 + p.dh[tap], n0);
+            }
           }
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -121,13 +152,13 @@ wgrad_gemm_kernel(const __grid_constant__ WgradMaps maps, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    {   // all lanes wait and count, one elected lane issues the MMAs and their commits (see conv_gemm.cu)
-      const uint32_t idesc = make_idesc_bf16(BM, p.bn, 1, 1);
+    if (rank == 0) {   // all lanes wait and count, one elected lane issues the MMAs and their commits (see conv_gemm.cu)
+      const uint32_t idesc = make_idesc_bf16(PAIR ? 2 * BM : BM, p.bn, 1, 1);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+      for (int u = unit0; u < total_units; u += nunits) {
         const int split = u / units_per_split;
         const int kb0 = (int)((long long)p.nblocks * split / p.splits);
         const int kb1 = (int)((long long)p.nblocks * (split + 1) / p.splits);
@@ -145,10 +176,16 @@ wgrad_gemm_kernel(const __grid_constant__ WgradMaps maps, const __grid_constant_
 #pragma unroll
             for (int k = 0; k < BKP / 16; ++k) {
               // 16 pixels = two 8-row swizzle atoms = 2048 B further along K
-              umma_bf16(d_tmem, da + (uint64_t)(k * 128), db + (uint64_t)(k * 128), idesc, (kb > kb0) || (k > 0));
+              if (PAIR) umma_bf16_pair(d_tmem, da + (uint64_t)(k * 128), db + (uint64_t)(k * 128), idesc, (kb > kb0) || (k > 0));
+              else umma_bf16(d_tmem, da + (uint64_t)(k * 128), db + (uint64_t)(k * 128), idesc, (kb > kb0) || (k > 0));
             }
-            umma_commit(&empty_bar[stage]);
-            if (kb == kb1 - 1) umma_commit(&tfull_bar[as]);
+            if (PAIR) {
+              umma_commit_pair(&empty_bar[stage]);
+              if (kb == kb1 - 1) umma_commit_pair(&tfull_bar[as]);
+            } else {
+              umma_commit(&empty_bar[stage]);
+              if (kb == kb1 - 1) umma_commit(&tfull_bar[as]);
+            }
           }
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -163,16 +200,16 @@ wgrad_gemm_kernel(const __grid_constant__ WgradMaps maps, const __grid_constant_
     int as = 0;
     uint32_t aphase = 0;
     const long long row_pitch = (long long)p.ntaps * p.cn_pitch;
-    for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+    for (int u = unit0; u < total_units; u += nunits) {
       const int split = u / units_per_split;
       int r = u - split * units_per_split;
       const int tap = r % p.ntaps; r /= p.ntaps;
       const int nt = r % p.n_tiles;
-      const int mt = r / p.n_tiles;
+      const int mt = m_tile_of(r / p.n_tiles);
       const int kb0 = (int)((long long)p.nblocks * split / p.splits);
       const int kb1 = (int)((long long)p.nblocks * (split + 1) / p.splits);
       const int m = mt * BM + row;
-      float* orow = p.part + ((long long)split * p.cm + m) * row_pitch + (long long)tap * p.cn_pitch;
+      float* orow = p.part + ((long long)split * p.part_rows + (m - p.part_row0)) * row_pitch + (long long)tap * p.cn_pitch;
       if (kb1 > kb0) {
         mbar_wait(&tfull_bar[as], aphase, 14);
         tc_fence_after();
@@ -197,7 +234,10 @@ wgrad_gemm_kernel(const __grid_constant__ WgradMaps maps, const __grid_constant_
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        if (lane == 0) {
+          if (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[as]), 0));
+          else mbar_arrive(&tempty_bar[as]);
+        }
         as ^= 1;
         if (as == 0) aphase ^= 1;
       } else {
@@ -211,39 +251,60 @@ wgrad_gemm_kernel(const __grid_constant__ WgradMaps maps, const __grid_constant_
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (PAIR) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
-// grad[m][n][tap] (+)= sum_s part[s][m][tap][n]
-// grad[m][n][tap] (+)= sum_s part[s][m][tap][n]; with `swapped` the GEMM ran with the operand roles exchanged
-// (part[s][n'][tap][m'] with m' = n, n' = m of the parameter), which only changes where an element is read from
+int g_wgrad_cta_pair = 1;
+
+// grad[m][n][tap] (+)= sum_s part[s][m - row0][tap][n] for the GEMM rows m in [row0, row0 + nrows); with `swapped`
+// the GEMM ran with the operand roles exchanged (GEMM row = the parameter's second index): grad[n][m][tap].
 __global__ void wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ grad, int cm, int cn,
-                                    int ntaps, int cn_pitch, int splits, int accumulate, int swapped) {
-  // cm, cn, cn_pitch describe the GEMM (rows, columns, column pitch of the partials)
-  const long long total = (long long)cm * cn * ntaps;
-  const long long split_stride = (long long)cm * ntaps * cn_pitch;
+                                    int ntaps, int cn_pitch, int splits, int accumulate, int swapped, int row0,
+                                    int nrows, long long split_stride) {
+  const long long total = (long long)nrows * cn * ntaps;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int tap = (int)(i % ntaps);
     const long long rc = i / ntaps;
-    long long m;
-    int n;
-    if (!swapped) {            // parameter [cm][cn][tap]
+    int ml, n;
+    long long dst;
+    if (!swapped) {            // parameter [cm][cn][tap]: consecutive threads write consecutive elements
       n = (int)(rc % cn);
-      m = rc / cn;
+      ml = (int)(rc / cn);
+      dst = ((long long)(row0 + ml) * cn + n) * ntaps + tap;
     } else {                   // parameter [cn][cm][tap]
-      m = rc % cm;
-      n = (int)(rc / cm);
+      ml = (int)(rc % nrows);
+      n = (int)(rc / nrows);
+      dst = ((long long)n * cm + row0 + ml) * ntaps + tap;
     }
-    const float* src = part + (m * ntaps + tap) * cn_pitch + n;
+    const float* src = part + ((long long)ml * ntaps + tap) * cn_pitch + n;
     float s = 0.f;
     for (int k = 0; k < splits; ++k) s += src[k * split_stride];
-    grad[i] = accumulate ? grad[i] + s : s;
+    grad[dst] = accumulate ? grad[dst] + s : s;
   }
+}
+
+// split-K factor that fills `slots` (SMs, or CTA pairs) best with `base` units per split
+int pick_splits(int base, int slots, long long nblocks, int max_splits) {
+  int best = 1;
+  double best_eff = 0;
+  for (int s = 1; s <= max_splits; ++s) {
+    if (s > 1 && nblocks / s < 16) break;
+    const long long units = (long long)base * s;
+    const double eff = (double)units / (double)(((units + slots - 1) / slots) * slots);
+    if (eff > best_eff + 0.02) { best_eff = eff; best = s; }
+  }
+  return best;
+}
+
+int wgrad_bn(int cn) {
+  return cn <= 256 ? (cn + 15) / 16 * 16 : ((cn + (cn + 255) / 256 - 1) / ((cn + 255) / 256) + 15) / 16 * 16;
 }
 
 }  // namespace
@@ -252,25 +313,26 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, float* __res
 
 using namespace tvae;
 
+// Workspace: [splits][cm][ntaps * cn_pitch] for the main launch plus [MAX_REM_SPLITS][128][ntaps * cn_pitch] for the odd
+// last M tile, which runs as a second launch with its own split-K factor when the main launch uses CTA pairs.
 extern "C" int64_t tvae_wgrad_workspace_bytes(int32_t cm, int32_t cn, int32_t ntaps, int32_t splits) {
   const int64_t cn_pitch = (cn + 3) / 4 * 4;
-  return (int64_t)splits * cm * ntaps * cn_pitch * 4;
+  return ((int64_t)splits * cm + (int64_t)MAX_REM_SPLITS * BM) * ntaps * cn_pitch * 4;
 }
 
 extern "C" int32_t tvae_wgrad_splits(int32_t cm, int32_t cn, int32_t ntaps, int64_t pixels) {
-  const int bn = cn <= 256 ? (cn + 15) / 16 * 16 : ((cn + (cn + 255) / 256 - 1) / ((cn + 255) / 256) + 15) / 16 * 16;
-  const int base = ((cm + BM - 1) / BM) * ((cn + bn - 1) / bn) * ntaps;
-  const int sms = num_sms();
+  const int bn = wgrad_bn(cn);
+  const int m_tiles = (cm + BM - 1) / BM, n_tiles = (cn + bn - 1) / bn;
   const long long nblocks = (pixels + BKP - 1) / BKP;
-  int best = 1;
-  double best_eff = 0;
-  for (int s = 1; s <= 16; ++s) {
-    if (s > 1 && nblocks / s < 16) break;
-    const long long units = (long long)base * s;
-    const double eff = (double)units / (double)(((units + sms - 1) / sms) * sms);
-    if (eff > best_eff + 0.02) { best_eff = eff; best = s; }
-  }
-  return best;
+  if (g_wgrad_cta_pair && m_tiles >= 2)    // main launch: pairs of M tiles on pairs of SMs
+    return pick_splits((m_tiles / 2) * n_tiles * ntaps, num_sms() / 2, nblocks, 16);
+  return pick_splits(m_tiles * n_tiles * ntaps, num_sms(), nblocks, 16);
+}
+
+extern "C" int32_t tvae_wgrad_set_cta_pair(int32_t enable) {
+  const int prev = g_wgrad_cta_pair;
+  g_wgrad_cta_pair = enable ? 1 : 0;
+  return prev;
 }
 
 extern "C" int32_t tvae_wgrad_gemm(const tvae_wgrad_args* a, cudaStream_t stream) {
@@ -294,13 +356,9 @@ extern "C" int32_t tvae_wgrad_gemm(const tvae_wgrad_args* a, cudaStream_t stream
 
   p.cm = a->Cm; p.cn = a->Cn;
   p.m_tiles = (a->Cm + BM - 1) / BM;
-  p.bn = a->Cn <= 256 ? (a->Cn + 15) / 16 * 16
-                      : ((a->Cn + (a->Cn + 255) / 256 - 1) / ((a->Cn + 255) / 256) + 15) / 16 * 16;
+  p.bn = wgrad_bn(a->Cn);
   p.n_tiles = (a->Cn + p.bn - 1) / p.bn;
-  p.nq = (p.bn + 63) / 64;
-  p.splits = a->splits;
   p.cn_pitch = (a->Cn + 3) / 4 * 4;
-  p.part = a->workspace;
 
   const uint64_t pp = (uint64_t)a->p_pitch * 2, qp = (uint64_t)a->q_pitch * 2;
   uint32_t box[4] = {64, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bnimg};
@@ -334,18 +392,86 @@ extern "C" int32_t tvae_wgrad_gemm(const tvae_wgrad_args* a, cudaStream_t stream
     }
   }
 
-  TVAE_CUDA(cudaFuncSetAttribute(wgrad_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  const int total = p.m_tiles * p.n_tiles * p.ntaps * p.splits;
-  int grid = num_sms();
-  if (grid > total) grid = total;
-  wgrad_gemm_kernel<<<grid, NTHREADS, SMEM_BYTES, stream>>>(maps, p);
+  const int m_tiles = p.m_tiles;
+  const bool pair = g_wgrad_cta_pair != 0 && m_tiles >= 2;
+  const int main_tiles = pair ? (m_tiles & ~1) : m_tiles;      // the odd last tile becomes its own single-CTA launch
+  const int rem_tiles = m_tiles - main_tiles;
+  const long long row_elems = (long long)p.ntaps * p.cn_pitch;
+  auto reduce = [&](const float* part, int splits, int row0, int nrows, long long split_stride) {
+    const long long total_out = (long long)nrows * a->Cn * p.ntaps;
+    int rgrid = (int)((total_out + 255) / 256);
+    if (rgrid > 148 * 16) rgrid = 148 * 16;
+    wgrad_reduce_kernel<<<rgrid, 256, 0, stream>>>(part, a->grad, a->Cm, a->Cn, p.ntaps, p.cn_pitch, splits,
+                                                  a->accumulate, a->flip, row0, nrows, split_stride);
+  };
+
+  // ---- main launch
+  p.mt0 = 0;
+  p.m_tiles = main_tiles;
+  p.splits = a->splits;
+  p.part = a->workspace;
+  p.part_rows = a->Cm;
+  p.part_row0 = 0;
+  if (pair) {
+    p.nq = (p.bn / 2 + 63) / 64;
+    static bool attr_set = false;
+    if (!attr_set) {
+      TVAE_CUDA(cudaFuncSetAttribute(wgrad_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      attr_set = true;
+    }
+    const int total = (main_tiles / 2) * p.n_tiles * p.ntaps * p.splits;
+    int grid = num_sms() / 2;
+    if (grid > total) grid = total;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * grid);
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    TVAE_CUDA(cudaLaunchKernelEx(&cfg, wgrad_gemm_kernel<true>, maps, p));
+  } else {
+    p.nq = (p.bn + 63) / 64;
+    static bool attr_set = false;
+    if (!attr_set) {
+      TVAE_CUDA(cudaFuncSetAttribute(wgrad_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      attr_set = true;
+    }
+    const int total = main_tiles * p.n_tiles * p.ntaps * p.splits;
+    int grid = num_sms();
+    if (grid > total) grid = total;
+    wgrad_gemm_kernel<false><<<grid, NTHREADS, SMEM_BYTES, stream>>>(maps, p);
+  }
+  TVAE_CUDA(cudaGetLastError());
+  {
+    const int nrows = main_tiles * BM < a->Cm ? main_tiles * BM : a->Cm;
+    reduce(p.part, p.splits, 0, nrows, (long long)a->Cm * row_elems);
+  }
   TVAE_CUDA(cudaGetLastError());
 
-  const long long total_out = (long long)a->Cm * a->Cn * p.ntaps;
-  int rgrid = (int)((total_out + 255) / 256);
-  if (rgrid > 148 * 16) rgrid = 148 * 16;
-  wgrad_reduce_kernel<<<rgrid, 256, 0, stream>>>(p.part, a->grad, a->Cm, a->Cn, p.ntaps, p.cn_pitch, p.splits,
-                                                a->accumulate, a->flip);
+  // ---- odd last M tile: one CTA per SM, its own split-K factor and its own workspace region
+  if (rem_tiles) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      TVAE_CUDA(cudaFuncSetAttribute(wgrad_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      attr_set = true;
+    }
+    p.mt0 = main_tiles;
+    p.m_tiles = 1;
+    p.nq = (p.bn + 63) / 64;
+    p.splits = pick_splits(p.n_tiles * p.ntaps, num_sms(), p.nblocks, MAX_REM_SPLITS);
+    p.part = a->workspace + (long long)a->splits * a->Cm * row_elems;
+    p.part_rows = BM;
+    p.part_row0 = main_tiles * BM;
+    const int total = p.n_tiles * p.ntaps * p.splits;
+    int grid = num_sms();
+    if (grid > total) grid = total;
+    wgrad_gemm_kernel<false><<<grid, NTHREADS, SMEM_BYTES, stream>>>(maps, p);
+    TVAE_CUDA(cudaGetLastError());
+    reduce(p.part, p.splits, main_tiles * BM, a->Cm - main_tiles * BM, (long long)BM * row_elems);
+  }
   TVAE_CUDA(cudaGetLastError());
   return 0;
 }

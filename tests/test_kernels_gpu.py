@@ -33,6 +33,15 @@ def conv_sched(request):
     lib.tvae_conv_set_cta_pair(prev)
 
 
+@pytest.fixture(params=["cta_pair", "single_cta"])
+def wgrad_sched(request):
+    """Both schedules of tvae_wgrad_gemm (CTA pairs over M tiles + single-CTA remainder launch / one CTA per SM)."""
+    from tempo_vae_b200._lib import lib
+    prev = lib.tvae_wgrad_set_cta_pair(1 if request.param == "cta_pair" else 0)
+    yield request.param
+    lib.tvae_wgrad_set_cta_pair(prev)
+
+
 def bf16_round(t):
     return t.to(torch.bfloat16).float()
 
@@ -146,10 +155,12 @@ def test_convT_up_and_dgrad(N, H, W, Cin, Cout):
     assert rel_err(od[..., :Cin].permute(0, 3, 1, 2), refd) < 2e-3
 
 
+@pytest.mark.usefixtures("wgrad_sched")
 @pytest.mark.parametrize("N,H,W,Cin,Cout,R,splits", [
     (2, 16, 16, 64, 64, 3, 1), (2, 16, 16, 128, 128, 1, 0), (4, 32, 32, 256, 256, 3, 0), (2, 64, 64, 512, 512, 3, 0),
     (1, 64, 64, 1028, 512, 3, 0), (1, 64, 64, 512, 1028, 3, 3), (2, 16, 16, 128, 64, 3, 2), (2, 16, 16, 512, 4, 1, 0),
-    (6, 4, 4, 32, 32, 3, 0), (2, 16, 16, 32, 128, 3, 40)])
+    (6, 4, 4, 32, 32, 3, 0), (2, 16, 16, 32, 128, 3, 40), (2, 16, 16, 64, 384, 3, 0), (2, 16, 16, 96, 200, 3, 2),
+    (3, 8, 8, 48, 648, 1, 0)])
 def test_wgrad(N, H, W, Cin, Cout, R, splits):
     o = ops()
     g = torch.Generator(device="cuda").manual_seed(5)
@@ -167,6 +178,7 @@ def test_wgrad(N, H, W, Cin, Cout, R, splits):
     assert rel_err(grad, 2 * ref) < 2e-3
 
 
+@pytest.mark.usefixtures("wgrad_sched")
 @pytest.mark.parametrize("N,H,W,Cin,Cout", [(2, 16, 16, 64, 64), (2, 64, 64, 512, 512), (2, 8, 8, 32, 16)])
 def test_wgrad_strided(N, H, W, Cin, Cout):
     o = ops()
@@ -504,6 +516,7 @@ def test_conv_epilogue_writes_stay_in_bounds(N, H, W, Cin, Cout, kind):
     assert torch.isfinite(of[..., :Cout]).all() and (of[..., :Cout] != 12345.0).any()
 
 
+@pytest.mark.usefixtures("wgrad_sched")
 def test_wgrad_writes_stay_in_bounds():
     o = ops()
     g = torch.Generator(device="cuda").manual_seed(16)
@@ -520,6 +533,7 @@ def test_wgrad_writes_stay_in_bounds():
     assert rel_err(grad, ref) < 2e-3
 
 
+@pytest.mark.usefixtures("wgrad_sched")
 @pytest.mark.parametrize("N,H,W,Cin,Cout,R", [(2, 16, 16, 300, 128, 3), (1, 64, 64, 1028, 512, 3), (2, 16, 16, 260, 128, 1)])
 def test_wgrad_exchanged_operand_roles(N, H, W, Cin, Cout, R):
     o = ops()
@@ -558,3 +572,25 @@ def test_conv_cta_pair_is_bit_identical_to_single_cta(N, H, W, Cin, Cout, R):
         lib.tvae_conv_set_cta_pair(prev)
     assert torch.equal(outs[0][0], outs[1][0])
     assert torch.equal(outs[0][1], outs[1][1])
+
+
+@pytest.mark.parametrize("Cin,Cout,splits", [(256, 256, 2), (128, 512, 3)])
+def test_wgrad_cta_pair_is_bit_identical_to_single_cta(Cin, Cout, splits):
+    """Even M tile count and the same split-K factor: both schedules add the same K blocks in the same order."""
+    from tempo_vae_b200._lib import lib
+    o = ops()
+    g = torch.Generator(device="cuda").manual_seed(13)
+    x = nhwc_bf16(bf16_round(torch.randn((3, Cin, 32, 32), device="cuda", generator=g)), Cin)
+    dy = nhwc_bf16(bf16_round(torch.randn((3, Cout, 32, 32), device="cuda", generator=g)), Cout)
+    outs = []
+    prev = lib.tvae_wgrad_set_cta_pair(1)
+    try:
+        for mode in (1, 0):
+            lib.tvae_wgrad_set_cta_pair(mode)
+            grad = torch.full((Cout, Cin, 3, 3), float("nan"), device="cuda")
+            o.wgrad_gemm(dy, Cout, x, Cin, kind=0, R=3, grad=grad, splits=splits)
+            torch.cuda.synchronize()
+            outs.append(grad)
+    finally:
+        lib.tvae_wgrad_set_cta_pair(prev)
+    assert torch.equal(outs[0], outs[1])
