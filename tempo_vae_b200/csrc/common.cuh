@@ -315,19 +315,31 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
   return cdf + x * pdf;
 }
 
-// Fast exact-GELU pieces: Phi(y) = 0.5 (1 + erf(y / sqrt 2)) from Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7,
-// two orders below fp32 activations' own rounding here), sharing ONE exponential e = exp(-y^2/2) with the normal
-// density phi(y) that the derivative needs: ~12 FMA + 1 EX2 + 1 RCP instead of erff() + expf().
-__device__ __forceinline__ void gelu_phi(float y, float& Phi, float& e) {
-  const float ax = fabsf(y) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
-  e = __expf(-0.5f * y * y);
-  float poly = fmaf(t, 1.061405429f, -1.453152027f);
-  poly = fmaf(t, poly, 1.421413741f);
-  poly = fmaf(t, poly, -0.284496736f);
-  poly = fmaf(t, poly, 0.254829592f);
-  const float h = 0.5f * poly * t * e;      // = 0.5 * (1 - erf|x|)
-  Phi = (y >= 0.f) ? 1.0f - h : h;
+// Fast exact-GELU pieces: the normal CDF Phi(y) from Abramowitz-Stegun 26.2.17 (|error| < 7.5e-8, two orders below
+// fp32 activations' own rounding here), sharing ONE exponential e = exp(-y^2/2) with the normal density phi(y) that
+// the derivative needs. MUFU approximations (rcp.approx, ex2.approx: ~1-2 ulp) instead of the IEEE-rounded
+// __frcp_rn / range-checked __expf: 2 MUFU + ~14 FP32 instructions per element, where the first version spent 37
+// (10 of them on the reciprocal's slow-path check alone) and made the GroupNorm backward passes ALU-bound.
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// Phi = Phi(y); pe = phi(y) = exp(-y^2/2) / sqrt(2 pi)
+__device__ __forceinline__ void gelu_phi(float y, float& Phi, float& pe) {
+  const float t = rcp_approx(fmaf(0.2316419f, fabsf(y), 1.0f));
+  pe = 0.39894228040143267794f * ex2_approx(y * y * -0.72134752044448170368f);
+  float poly = fmaf(t, 1.330274429f, -1.821255978f);
+  poly = fmaf(t, poly, 1.781477937f);
+  poly = fmaf(t, poly, -0.356563782f);
+  poly = fmaf(t, poly, 0.319381530f);
+  const float q = poly * t * pe;            // = 1 - Phi(|y|)
+  Phi = (y >= 0.f) ? 1.0f - q : q;
 }
 __device__ __forceinline__ float gelu_fast(float y) {
   float Phi, e;
@@ -335,9 +347,9 @@ __device__ __forceinline__ float gelu_fast(float y) {
   return y * Phi;
 }
 __device__ __forceinline__ float gelu_grad_fast(float y) {
-  float Phi, e;
-  gelu_phi(y, Phi, e);
-  return fmaf(y * 0.39894228040143267794f, e, Phi);
+  float Phi, pe;
+  gelu_phi(y, Phi, pe);
+  return fmaf(y, pe, Phi);
 }
 
 // activation codes of the C ABI: 0 identity, 1 GELU (exact erf), 2 ReLU, 3 SiLU  (src/model.py:333-339)
