@@ -135,16 +135,18 @@ int32_t tvae_gn_stats(const float* x, int32_t N, int32_t HW, int32_t C, int32_t 
  * count = elements per (image, group). */
 int32_t tvae_gn_stats_finalize(const float* stats_part, int32_t slots_per_image, int32_t N, int32_t G, double count,
                                float eps, float* stats, tvae_stream_t stream);
-int32_t tvae_gn_act_fwd(const float* x, const float* stats, const float* gamma, const float* beta, int32_t N,
-                        int32_t HW, int32_t C, int32_t G, int32_t act, void* out_bf16, void* out_lo,
+/* x: the GroupNorm input, NHWC dense: fp32 (x_is_bf16 = 0), or bf16 (x_is_bf16 = 1; only for geometries of the
+ * vectorised kernels: C/8 divides 256 and groups are whole 8-channel octets -- every layer of the reference model). */
+int32_t tvae_gn_act_fwd(const void* x, int32_t x_is_bf16, const float* stats, const float* gamma, const float* beta,
+                        int32_t N, int32_t HW, int32_t C, int32_t G, int32_t act, void* out_bf16, void* out_lo,
                         tvae_stream_t stream);
 /* da: bf16 gradient wrt the activation output; gres (optional bf16) is added to dx (residual branch).
  * dgamma/dbeta are overwritten. dx_colsum (optional, float[C]): column sums of dx over all N*HW pixels, i.e. the bias
  * gradient of the conv whose output x is -- produced by the same pass that writes dx.
  * workspace: tvae_gn_bwd_workspace_bytes(N, HW, C, G). */
 int64_t tvae_gn_bwd_workspace_bytes(int32_t N, int32_t HW, int32_t C, int32_t G);
-int32_t tvae_gn_act_bwd(const float* x, const float* stats, const float* gamma, const float* beta, const void* da_bf16,
-                        const void* gres_bf16, int32_t N, int32_t HW, int32_t C, int32_t G, int32_t act,
+int32_t tvae_gn_act_bwd(const void* x, int32_t x_is_bf16, const float* stats, const float* gamma, const float* beta,
+                        const void* da_bf16, const void* gres_bf16, int32_t N, int32_t HW, int32_t C, int32_t G, int32_t act,
                         void* dx_bf16, float* dgamma, float* dbeta, float* dx_colsum, float* workspace,
                         tvae_stream_t stream);
 

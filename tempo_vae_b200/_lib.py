@@ -77,9 +77,9 @@ def _load():
         "tvae_f32_to_bf16": (i32, [vp, vp, i64, vp, vp]),
         "tvae_gn_stats": (i32, [vp, i32, i32, i32, i32, f32, vp, vp]),
         "tvae_gn_stats_finalize": (i32, [vp, i32, i32, i32, C.c_double, f32, vp, vp]),
-        "tvae_gn_act_fwd": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp]),
+        "tvae_gn_act_fwd": (i32, [vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp]),
         "tvae_gn_bwd_workspace_bytes": (i64, [i32, i32, i32, i32]),
-        "tvae_gn_act_bwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]),
+        "tvae_gn_act_bwd": (i32, [vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]),
         "tvae_colsum_workspace_bytes": (i64, [i64, i32]),
         "tvae_colsum_bf16": (i32, [vp, i64, i32, i32, vp, vp, vp]),
         "tvae_attn_fwd": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp]),

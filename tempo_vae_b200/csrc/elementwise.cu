@@ -551,19 +551,22 @@ extern "C" int32_t tvae_gn_stats_finalize(const float* part, int32_t spi, int32_
   return 0;
 }
 
-extern "C" int32_t tvae_gn_act_fwd(const float* x, const float* stats, const float* gamma, const float* beta,
-                                   int32_t N, int32_t HW, int32_t C, int32_t G, int32_t act, void* out, void* out_lo,
-                                   cudaStream_t stream) {
-  TVAE_ENTER(x);
-  TVAE_CHECK(x && stats && gamma && beta && out, "tvae_gn_act_fwd: null pointer");
+extern "C" int32_t tvae_gn_act_fwd(const void* xv, int32_t x_is_bf16, const float* stats, const float* gamma,
+                                   const float* beta, int32_t N, int32_t HW, int32_t C, int32_t G, int32_t act,
+                                   void* out, void* out_lo, cudaStream_t stream) {
+  TVAE_ENTER(xv);
+  TVAE_CHECK(xv && stats && gamma && beta && out, "tvae_gn_act_fwd: null pointer");
   TVAE_CHECK(G > 0 && C % G == 0, "tvae_gn_act_fwd: C %% G != 0");
   const long long rows = (long long)N * HW;
   const int gs = C / G;
   if (gn_fast_ok(C, G) && out_lo == nullptr) {   // the split-bf16 ("fp32 mode") output uses the generic kernel
-    gn_act_fwd_fast(x, stats, gamma, beta, N, HW, C, G, act, reinterpret_cast<__nv_bfloat16*>(out), stream);
+    gn_act_fwd_fast(xv, x_is_bf16 != 0, stats, gamma, beta, N, HW, C, G, act, reinterpret_cast<__nv_bfloat16*>(out),
+                    stream);
     TVAE_CUDA(cudaGetLastError());
     return 0;
   }
+  TVAE_CHECK(!x_is_bf16, "tvae_gn_act_fwd: a bf16 input needs the fast-path geometry (C/8 dividing 256, groups of whole octets)");
+  const float* x = reinterpret_cast<const float*>(xv);
   if (gs % 8 == 0)
     gn_act_fwd_kernel<8><<<ew_grid(rows * (C / 8)), EW_THREADS, 0, stream>>>(
         x, stats, gamma, beta, rows, HW, C, G, act, reinterpret_cast<__nv_bfloat16*>(out),
@@ -582,12 +585,12 @@ extern "C" int64_t tvae_gn_bwd_workspace_bytes(int32_t N, int32_t HW, int32_t C,
   return (2ll * N * C + 2ll * N * G) * 4 + (int64_t)colsum_blocks((long long)N * HW) * C * 4;
 }
 
-extern "C" int32_t tvae_gn_act_bwd(const float* x, const float* stats, const float* gamma, const float* beta,
-                                   const void* da, const void* gres, int32_t N, int32_t HW, int32_t C, int32_t G,
+extern "C" int32_t tvae_gn_act_bwd(const void* xv, int32_t x_is_bf16, const float* stats, const float* gamma,
+                                   const float* beta, const void* da, const void* gres, int32_t N, int32_t HW, int32_t C, int32_t G,
                                    int32_t act, void* dx, float* dgamma, float* dbeta, float* dx_colsum, float* ws,
                                    cudaStream_t stream) {
-  TVAE_ENTER(x);
-  TVAE_CHECK(x && stats && gamma && beta && da && dx && dgamma && dbeta && ws, "tvae_gn_act_bwd: null pointer");
+  TVAE_ENTER(xv);
+  TVAE_CHECK(xv && stats && gamma && beta && da && dx && dgamma && dbeta && ws, "tvae_gn_act_bwd: null pointer");
   TVAE_CHECK(G > 0 && C % G == 0, "tvae_gn_act_bwd: C %% G != 0");
   const int gs = C / G;
   const long long rows = (long long)N * HW;
@@ -596,10 +599,13 @@ extern "C" int32_t tvae_gn_act_bwd(const float* x, const float* stats, const flo
   __nv_bfloat16* dxp = reinterpret_cast<__nv_bfloat16*>(dx);
   const float* gmeans = ws + 2ll * N * C;
   if (gn_fast_ok(C, G)) {
-    gn_act_bwd_fast(x, stats, gamma, beta, dap, grp, N, HW, C, G, act, dxp, dgamma, dbeta, dx_colsum, ws, stream);
+    gn_act_bwd_fast(xv, x_is_bf16 != 0, stats, gamma, beta, dap, grp, N, HW, C, G, act, dxp, dgamma, dbeta, dx_colsum,
+                    ws, stream);
     TVAE_CUDA(cudaGetLastError());
     return 0;
   }
+  TVAE_CHECK(!x_is_bf16, "tvae_gn_act_bwd: a bf16 input needs the fast-path geometry");
+  const float* x = reinterpret_cast<const float*>(xv);
   if (gs % 8 == 0 && gs / 8 <= 256) {
     const int threads = 256;
     gn_bwd_reduce_kernel<8><<<N * G, threads, threads * 16 * sizeof(float), stream>>>(x, stats, gamma, beta, dap, HW, C,

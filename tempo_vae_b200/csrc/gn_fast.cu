@@ -26,6 +26,9 @@ __device__ __forceinline__ void load8_bf16(const __nv_bfloat16* p, float (&v)[8]
     v[2 * j + 1] = bf16_bits_to_f(w[j] >> 16);
   }
 }
+// 8 consecutive channels of the GroupNorm input: fp32 (residual stream) or bf16 (a conv output that only feeds a norm)
+__device__ __forceinline__ void load8x(const float* p, float (&v)[8]) { load8(p, v); }
+__device__ __forceinline__ void load8x(const __nv_bfloat16* p, float (&v)[8]) { load8_bf16(p, v); }
 __device__ __forceinline__ void store8_bf16(__nv_bfloat16* p, const float (&v)[8]) {
   uint4 o;
   o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]);
@@ -34,8 +37,9 @@ __device__ __forceinline__ void store8_bf16(__nv_bfloat16* p, const float (&v)[8
 }
 
 // grid (row chunks, N); 256 threads = (256/U) row lanes x U channel-octets, U = C/8
+template <typename TX>
 __global__ void __launch_bounds__(256)
-gn_act_fwd_fast_kernel(const float* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gamma,
+gn_act_fwd_fast_kernel(const TX* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gamma,
                        const float* __restrict__ beta, int HW, int C, int G, int act, int rpb,
                        __nv_bfloat16* __restrict__ out) {
   const int U = C >> 3, lanes = 256 / U;
@@ -57,8 +61,8 @@ gn_act_fwd_fast_kernel(const float* __restrict__ x, const float* __restrict__ st
   int r = r0 + lane;
   for (; r + lanes < r1; r += 2 * lanes) {
     float a[8], b[8];
-    load8(x + base + (long long)r * C, a);
-    load8(x + base + (long long)(r + lanes) * C, b);
+    load8x(x + base + (long long)r * C, a);
+    load8x(x + base + (long long)(r + lanes) * C, b);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       a[j] = act_fast(fmaf(a[j], sc[j], sh[j]), act);
@@ -69,7 +73,7 @@ gn_act_fwd_fast_kernel(const float* __restrict__ x, const float* __restrict__ st
   }
   if (r < r1) {
     float a[8];
-    load8(x + base + (long long)r * C, a);
+    load8x(x + base + (long long)r * C, a);
 #pragma unroll
     for (int j = 0; j < 8; ++j) a[j] = act_fast(fmaf(a[j], sc[j], sh[j]), act);
     store8_bf16(out + base + (long long)r * C, a);
@@ -80,8 +84,9 @@ gn_act_fwd_fast_kernel(const float* __restrict__ x, const float* __restrict__ st
 // cs_part (optional): per-block column sums of the bf16 values written to dx, [n][chunk][C] -- dx is the output
 // gradient of the conv that produced x, so its column sums are that conv's bias gradient and the separate pass over
 // dx (tvae_colsum_bf16) disappears.
+template <typename TX>
 __global__ void __launch_bounds__(256)
-gn_bwd_apply_fast_kernel(const float* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gamma,
+gn_bwd_apply_fast_kernel(const TX* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gamma,
                          const float* __restrict__ beta, const __nv_bfloat16* __restrict__ da,
                          const __nv_bfloat16* __restrict__ gres, const float* __restrict__ gmeans, int HW, int C, int G,
                          int act, int rpb, __nv_bfloat16* __restrict__ dx, float* __restrict__ cs_part) {
@@ -103,7 +108,7 @@ gn_bwd_apply_fast_kernel(const float* __restrict__ x, const float* __restrict__ 
   for (int r = r0 + lane; r < r1; r += lanes) {
     const long long off = base + (long long)r * C;
     float xv[8], dv[8], rv[8];
-    load8(x + off, xv);
+    load8x(x + off, xv);
     load8_bf16(da + off, dv);
     if (gres) {
       load8_bf16(gres + off, rv);
@@ -168,8 +173,9 @@ __global__ void colsum_rows_final_kernel(const float* __restrict__ slices, int C
 
 // Stage A1: grid (row chunks, N) like the apply kernel (full 2 KB rows => long DRAM bursts): per-channel partial sums
 // of dy and dy*xhat over the chunk's rows -> part[n][chunk][2][C].
+template <typename TX>
 __global__ void __launch_bounds__(256, 4)
-gn_bwd_rowsum_fast_kernel(const float* __restrict__ x, const float* __restrict__ stats,
+gn_bwd_rowsum_fast_kernel(const TX* __restrict__ x, const float* __restrict__ stats,
                           const float* __restrict__ gamma, const float* __restrict__ beta,
                           const __nv_bfloat16* __restrict__ da, int HW, int C, int G, int act, int rpb,
                           float* __restrict__ part) {
@@ -195,7 +201,7 @@ gn_bwd_rowsum_fast_kernel(const float* __restrict__ x, const float* __restrict__
   const long long base = (long long)n * HW * C + c;
   for (int r = r0 + lane; r < r1; r += lanes) {
     float xa[8], da_[8];
-    load8(x + base + (long long)r * C, xa);
+    load8x(x + base + (long long)r * C, xa);
     load8_bf16(da + base + (long long)r * C, da_);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -293,11 +299,16 @@ bool gn_fast_ok(int C, int G) {
   return U >= 1 && U <= 256 && (256 % U) == 0 && (256 % (gs / 8)) == 0;
 }
 
-int gn_act_fwd_fast(const float* x, const float* stats, const float* gamma, const float* beta, int N, int HW, int C,
-                    int G, int act, __nv_bfloat16* out, cudaStream_t stream) {
+int gn_act_fwd_fast(const void* x, bool x_bf16, const float* stats, const float* gamma, const float* beta, int N,
+                    int HW, int C, int G, int act, __nv_bfloat16* out, cudaStream_t stream) {
   const int rpb = rows_per_block(HW);
   dim3 grid((HW + rpb - 1) / rpb, N);
-  gn_act_fwd_fast_kernel<<<grid, 256, 0, stream>>>(x, stats, gamma, beta, HW, C, G, act, rpb, out);
+  if (x_bf16)
+    gn_act_fwd_fast_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), stats, gamma, beta, HW,
+                                                     C, G, act, rpb, out);
+  else
+    gn_act_fwd_fast_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const float*>(x), stats, gamma, beta, HW, C, G,
+                                                     act, rpb, out);
   return 0;
 }
 
@@ -307,7 +318,7 @@ long long gn_bwd_fast_ws_floats(int N, int HW, int C, int G) {
   return 2ll * N * C + 2ll * N * G + (long long)N * chunks * 2 * C + (long long)CS_SLICES * C;
 }
 
-int gn_act_bwd_fast(const float* x, const float* stats, const float* gamma, const float* beta,
+int gn_act_bwd_fast(const void* xv, bool x_bf16, const float* stats, const float* gamma, const float* beta,
                     const __nv_bfloat16* da, const __nv_bfloat16* gres, int N, int HW, int C, int G, int act,
                     __nv_bfloat16* dx, float* dgamma, float* dbeta, float* dx_colsum, float* ws,
                     cudaStream_t stream) {
@@ -315,13 +326,23 @@ int gn_act_bwd_fast(const float* x, const float* stats, const float* gamma, cons
   const int chunks = (HW + rpb - 1) / rpb;
   dim3 grid(chunks, N);
   float* part = ws + 2ll * N * C + 2ll * N * G;
-  gn_bwd_rowsum_fast_kernel<<<grid, 256, 256 * 16 * sizeof(float), stream>>>(x, stats, gamma, beta, da, HW, C, G, act,
-                                                                            rpb, part);
+  const float* x = reinterpret_cast<const float*>(xv);
+  const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(xv);
+  if (x_bf16)
+    gn_bwd_rowsum_fast_kernel<<<grid, 256, 256 * 16 * sizeof(float), stream>>>(xb, stats, gamma, beta, da, HW, C, G,
+                                                                              act, rpb, part);
+  else
+    gn_bwd_rowsum_fast_kernel<<<grid, 256, 256 * 16 * sizeof(float), stream>>>(x, stats, gamma, beta, da, HW, C, G,
+                                                                              act, rpb, part);
   gn_bwd_finalize_fast_kernel<<<N, 256, 2 * C * sizeof(float), stream>>>(part, gamma, chunks, HW, C, G, N, ws, nullptr);
   gn_bwd_param_fast_kernel<<<(C + 31) / 32, 256, 0, stream>>>(ws, N, C, dgamma, dbeta);
   // the row-sum partials are consumed by now (stream order): their region is reused for the column sums of dx
-  gn_bwd_apply_fast_kernel<<<grid, 256, 0, stream>>>(x, stats, gamma, beta, da, gres, ws + 2ll * N * C, HW, C, G, act,
-                                                     rpb, dx, dx_colsum ? part : nullptr);
+  if (x_bf16)
+    gn_bwd_apply_fast_kernel<<<grid, 256, 0, stream>>>(xb, stats, gamma, beta, da, gres, ws + 2ll * N * C, HW, C, G, act,
+                                                       rpb, dx, dx_colsum ? part : nullptr);
+  else
+    gn_bwd_apply_fast_kernel<<<grid, 256, 0, stream>>>(x, stats, gamma, beta, da, gres, ws + 2ll * N * C, HW, C, G, act,
+                                                       rpb, dx, dx_colsum ? part : nullptr);
   if (dx_colsum) {
     float* slices = part + (long long)N * chunks * 2 * C;
     colsum_rows_slice_kernel<<<dim3((C + 31) / 32, CS_SLICES), 256, 0, stream>>>(part, N * chunks, C, slices);

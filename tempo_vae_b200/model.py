@@ -18,6 +18,7 @@ decode. Weight gradients are written straight into `param.grad` (a view of the o
 when FusedAdamW owns the parameter).
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -40,6 +41,9 @@ class _Engine:
         self.rng_offset = 0           # global sample counter (keyed RNG => world-size invariant draws)
         self.grad_ready_hook = None   # set by parallel.DataParallel: called as hook(param) when param.grad is final
         self.unit_loss_grad = False   # Trainer sets this: loss.backward() is called with grad 1 (skips a sync)
+        # conv outputs that only feed a GroupNorm (the h between the two convs of a ResNet block) are stored as bf16;
+        # the fp32 residual stream is untouched. False restores fp32 storage for them (A/B and parity experiments).
+        self.bf16_norm_inputs = os.environ.get("TVAE_BF16_NORM_INPUTS", "1") != "0"
 
     def params_changed(self):
         self.param_epoch += 1
@@ -234,7 +238,7 @@ def conv_fwd(mod, x_bf16, Cin, *, residual=None, want_f32=True, want_bf16=False,
     Cout = mod.out_channels
     mode = "up_fwd" if kind == 2 else "fwd"
     spec = None
-    if stats_for is not None and want_f32 and out_f32 is None and stats_for.num_channels == Cout:
+    if stats_for is not None and out_f32 is None and stats_for.num_channels == Cout:
         spec = (stats_for.num_groups, stats_for.eps)
     r = ops.conv_gemm(x_bf16, Cin, mod.packed(mode), kind=kind, R=R, Cout=Cout, bias=mod.bias, residual=residual,
                       want_f32=want_f32, want_bf16=want_bf16, out_f32=out_f32, stats=spec)
@@ -293,6 +297,8 @@ def norm_act_fwd(norm, h_f32, act_code, stats=None):
     if stats is not None and stats[0] == norm.num_groups and stats[1] == norm.eps:
         st = stats[2]
     else:
+        if h_f32.dtype != torch.float32:
+            raise RuntimeError("a bf16 GroupNorm input needs statistics from the producing conv's epilogue")
         st = ops.gn_stats(h_f32, C, norm.num_groups, norm.eps)
     a = ops.gn_act_fwd(h_f32, st, gamma, beta, norm.num_groups, act_code)
     return a, st
@@ -468,9 +474,16 @@ class ResNetBlock(nn.Module):
     def fwd(self, h, save, want_bf16=False, next_norm=None):
         act = self.net1[1].code
         a1, st1 = norm_act_fwd(self.net1[0], h.f32, act, h.stats)
-        r1 = conv_fwd(self.net1[2], a1, self.ch_in, stats_for=self.net2[0])
-        h1 = r1[0]
-        a2, st2 = norm_act_fwd(self.net2[0], h1, self.net2[1].code, r1.stats)
+        # h1 only feeds net2's GroupNorm (it is not on the fp32 residual stream): when its statistics come out of the
+        # conv epilogue (taken from the fp32 accumulators) it is stored as bf16 -- half the bytes for the conv
+        # epilogue, the norm's forward and both passes of its backward
+        n2 = self.net2[0]
+        N_, H_, W_ = a1.shape[0], a1.shape[1], a1.shape[2]
+        h1_bf16 = (ENGINE.bf16_norm_inputs and not ops.SPLIT_BF16[0] and ops.gn_fast_ok(self.ch_out, n2.num_groups)
+                   and ops.fused_stats_ok(N_, H_, W_, self.ch_out, n2.num_groups, 0, H_, W_))
+        r1 = conv_fwd(self.net1[2], a1, self.ch_in, stats_for=n2, want_f32=not h1_bf16, want_bf16=h1_bf16)
+        h1 = r1[1] if h1_bf16 else r1[0]
+        a2, st2 = norm_act_fwd(n2, h1, self.net2[1].code, r1.stats)
         if self.ch_in != self.ch_out:
             xb = h.as_bf16()
             res, _ = conv_fwd(self.skip_conv, xb, self.ch_in)

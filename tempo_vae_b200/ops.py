@@ -316,12 +316,23 @@ def gn_stats(x, Cc, G, eps):
     return stats
 
 
+def gn_fast_ok(Cc, G):
+    """Geometry of the vectorised GroupNorm kernels (gn_fast.cu); only these accept a bf16 input."""
+    if G <= 0 or Cc % G or (Cc // G) % 8:
+        return False
+    U = Cc // 8
+    return 1 <= U <= 256 and 256 % U == 0 and 256 % (Cc // G // 8) == 0
+
+
 def gn_act_fwd(x, stats, gamma, beta, G, act):
+    """x: the GroupNorm input, dense NHWC, fp32 or bf16 (see tvae_gn_act_fwd)."""
     N, H, W, Cc = x.shape
+    assert x.is_contiguous() and x.dtype in (torch.float32, torch.bfloat16)
     out = torch.empty((N, H, W, Cc), dtype=torch.bfloat16, device=x.device)
     lo = _lo_like(out)
-    check(lib.tvae_gn_act_fwd(x.data_ptr(), stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), N, H * W, Cc, G,
-                              int(act), out.data_ptr(), _ptr(lo), _stream()), "tvae_gn_act_fwd")
+    check(lib.tvae_gn_act_fwd(x.data_ptr(), int(x.dtype == torch.bfloat16), stats.data_ptr(), gamma.data_ptr(),
+                              beta.data_ptr(), N, H * W, Cc, G, int(act), out.data_ptr(), _ptr(lo), _stream()),
+          "tvae_gn_act_fwd")
     return _pair(out, lo)
 
 
@@ -332,8 +343,9 @@ def gn_act_bwd(x, stats, gamma, beta, da, gres, G, act, dgamma, dbeta, dx_colsum
     assert da.shape[-1] == Cc and da.dtype == torch.bfloat16
     dx = torch.empty((N, H, W, Cc), dtype=torch.bfloat16, device=x.device)
     ws = _workspace(lib.tvae_gn_bwd_workspace_bytes(N, H * W, Cc, G), x.device, "gn")
-    check(lib.tvae_gn_act_bwd(x.data_ptr(), stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), da.data_ptr(),
-                              _ptr(gres), N, H * W, Cc, G, int(act), dx.data_ptr(), dgamma.data_ptr(),
+    assert x.is_contiguous() and x.dtype in (torch.float32, torch.bfloat16)
+    check(lib.tvae_gn_act_bwd(x.data_ptr(), int(x.dtype == torch.bfloat16), stats.data_ptr(), gamma.data_ptr(),
+                              beta.data_ptr(), da.data_ptr(), _ptr(gres), N, H * W, Cc, G, int(act), dx.data_ptr(), dgamma.data_ptr(),
                               dbeta.data_ptr(), _ptr(dx_colsum), ws.data_ptr(), _stream()), "tvae_gn_act_bwd")
     if dx_colsum is not None:
         KERNEL_LAUNCHES[0] += 2
