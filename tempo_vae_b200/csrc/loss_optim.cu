@@ -111,10 +111,16 @@ __global__ void nll_fwd_kernel(const __nv_bfloat16* __restrict__ x, int x_pitch,
   double a_rec = 0.0, a_sq = 0.0;
   float f_rec = 0.f, f_sq = 0.f;
   int cnt = 0;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long p = i / U;
-    const int c = (int)(i - p * U) * VEC;
+  // (pixel, channel-vector) advance incrementally by the grid stride: no 64-bit division per element
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long sp = stride / U;
+  const int sc = (int)(stride - sp * U);
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  long long p = i / U;
+  int cu = (int)(i - p * U);
+  for (; i < total; i += stride, p += sp, cu += sc) {
+    if (cu >= U) { cu -= U; ++p; }
+    const int c = cu * VEC;
     float xv[VEC], hv[VEC], g[VEC];
     if (VEC == 4) {
       const uint2 d = *reinterpret_cast<const uint2*>(x + p * x_pitch + c);
