@@ -100,6 +100,9 @@ class GradBucketer:
         s, e = self.buckets[b]
         self.launched[b] = True
         if self.world > 1:
+            if self.flat.is_cuda:   # weight gradients are produced on a second stream (model.ENGINE.wgrad_overlap)
+                from .model import ENGINE
+                ENGINE.sync_streams_for_collective(self.flat.device)
             self.works.append(dist.all_reduce(self.flat[s:e], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
     def finish(self):

@@ -456,3 +456,31 @@ def test_unsupported_geometry_and_inputs_raise():
         model.vae.encode(torch.zeros(2, 20, 12, 12, device="cuda"))         # 12 is not a power of two / multiple of 128
     z = torch.zeros(1, 4, 4, 4, device="cuda")
     assert model.vae.decode(z).shape == (1, 20, 16, 16)                     # batch of one works
+
+
+def test_wgrad_stream_overlap_gives_identical_gradients():
+    """ENGINE.wgrad_overlap moves the weight-gradient GEMMs to a second stream; the kernels and their inputs are the
+    same, so every gradient must be bit-identical to the single-stream run."""
+    from tempo_vae_b200.model import ENGINE
+    cfg = orc.TINY_CFG
+    x = orc.structured_batch(6, cfg, seed=5).cuda()
+    eps = torch.randn((6, cfg["embed_dim"], cfg["shape"][1] // 4, cfg["shape"][2] // 4),
+                      generator=torch.Generator().manual_seed(3)).cuda()
+    grads = []
+    prev = ENGINE.wgrad_overlap
+    try:
+        for mode in (False, True, True):
+            ENGINE.wgrad_overlap = mode
+            model = build(cfg, seed=7)
+            sd = orc.rerandomize_zero_init({k: v.detach().cpu().clone() for k, v in model.state_dict().items()})
+            model.load_state_dict(sd)
+            loss, _ = model.vae.get_loss(x, eps=eps)
+            loss.backward()
+            torch.cuda.synchronize()
+            grads.append({k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None})
+    finally:
+        ENGINE.wgrad_overlap = prev
+    assert grads[0].keys() == grads[1].keys() and len(grads[0]) > 20
+    for k in grads[0]:
+        assert torch.equal(grads[0][k], grads[1][k]), k
+        assert torch.equal(grads[1][k], grads[2][k]), k
