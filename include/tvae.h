@@ -118,6 +118,18 @@ int32_t tvae_pack_weight(const float* w, void* out_bf16, int32_t Crow, int32_t T
  */
 int32_t tvae_nchw_f32_to_nhwc_bf16(const float* x, void* out_bf16, int32_t N, int32_t C, int32_t HW,
                                    int32_t out_pitch, void* out_lo, tvae_stream_t stream);
+/* Radiance normalisation of the data preparation / analysis scripts (src/scripts/prepare_tempo_tiles.py:67-79 with
+ * global statistics): z[r][c] = clamp((log(max(rad[r][c], min_radiance)) - mean[c]) / (std[c] + 1e-8), clip_min, clip_max)
+ * for raw radiance rows [rows][C] (a granule is [mirror][track][C]). Writes fp32 rows (out_f32, pitch C) and/or the bf16
+ * channels-last operand rows (out_bf16, pitch out_pitch, pad lanes zeroed) in one pass. */
+int32_t tvae_normalize_radiance(const float* rad, const float* mean, const float* std, int64_t rows, int32_t C,
+                                float min_radiance, float clip_min, float clip_max, float* out_f32, void* out_bf16,
+                                int32_t out_pitch, tvae_stream_t stream);
+/* Channels-last fp32 pixels (row pitch in_pitch elements, e.g. the reference's on-disk [H][W][1028] tiles or a
+ * torch.channels_last tensor) -> channels-last bf16 operand rows (pitch out_pitch, pad lanes zeroed): the layout the
+ * conv kernels read, without the NCHW detour of src/tempo_data.py:98-99 + the transpose above. */
+int32_t tvae_nhwc_f32_to_nhwc_bf16(const float* x, int64_t in_pitch, int64_t rows, int32_t C, void* out_bf16,
+                                   int32_t out_pitch, void* out_lo, tvae_stream_t stream);
 int32_t tvae_nhwc_f32_to_nchw_f32(const float* x, float* out, int32_t N, int32_t C, int32_t HW, int32_t in_pitch,
                                   tvae_stream_t stream);
 int32_t tvae_nhwc_bf16_to_nchw_f32(const void* x_bf16, float* out, int32_t N, int32_t C, int32_t HW,

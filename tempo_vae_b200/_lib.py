@@ -72,6 +72,8 @@ def _load():
         "tvae_wgrad_splits": (i32, [i32, i32, i32, i64]),
         "tvae_pack_weight": (i32, [vp, vp, i32, i32, i32, i32, i32, i64, i64, i64, vp, vp]),
         "tvae_nchw_f32_to_nhwc_bf16": (i32, [vp, vp, i32, i32, i32, i32, vp, vp]),
+        "tvae_normalize_radiance": (i32, [vp, vp, vp, i64, i32, f32, f32, f32, vp, vp, i32, vp]),
+        "tvae_nhwc_f32_to_nhwc_bf16": (i32, [vp, i64, i64, i32, vp, i32, vp, vp]),
         "tvae_nhwc_f32_to_nchw_f32": (i32, [vp, vp, i32, i32, i32, i32, vp]),
         "tvae_nhwc_bf16_to_nchw_f32": (i32, [vp, vp, i32, i32, i32, i32, vp]),
         "tvae_f32_to_bf16": (i32, [vp, vp, i64, vp, vp]),

@@ -527,6 +527,97 @@ extern "C" int32_t tvae_f32_to_bf16(const float* x, void* out, int64_t n, void* 
   return 0;
 }
 
+// channels-last fp32 rows (pitch in_pitch) -> channels-last bf16 rows (pitch out_pitch), pad lanes [C, out_pitch) zeroed;
+// a pair of channels per thread (out_pitch is even), 64-bit loads when the input rows allow it
+__global__ void nhwc_f32_to_bf16_kernel(const float* __restrict__ x, long long in_pitch, long long rows, int C,
+                                        __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ out_lo,
+                                        int out_pitch, int vec2) {
+  const int U = out_pitch >> 1;
+  const long long total = rows * U;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long sp = stride / U;
+  const int su = (int)(stride - sp * U);
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  long long r = i / U;
+  int u = (int)(i - r * U);
+  for (; i < total; i += stride, r += sp, u += su) {
+    if (u >= U) { u -= U; ++r; }
+    const int c = u << 1;
+    float v0 = 0.f, v1 = 0.f;
+    const float* src = x + r * in_pitch + c;
+    if (c + 1 < C) {
+      if (vec2) {
+        const float2 t = *reinterpret_cast<const float2*>(src);
+        v0 = t.x; v1 = t.y;
+      } else {
+        v0 = src[0]; v1 = src[1];
+      }
+    } else if (c < C) {
+      v0 = src[0];
+    }
+    *reinterpret_cast<uint32_t*>(out + r * out_pitch + c) = pack_bf16(v0, v1);
+    if (out_lo)
+      *reinterpret_cast<uint32_t*>(out_lo + r * out_pitch + c) = pack_bf16(bf16_residual(v0), bf16_residual(v1));
+  }
+}
+
+// z = clamp((log(max(rad, min_rad)) - mean[c]) / (std[c] + 1e-8), lo, hi): raw radiance rows [rows][C] -> z-scored
+// log-radiance, as fp32 rows (same pitch C) and/or as the bf16 operand rows the conv kernels read (pitch out_pitch)
+__global__ void normalize_radiance_kernel(const float* __restrict__ rad, const float* __restrict__ mean,
+                                          const float* __restrict__ stdv, long long rows, int C, float min_rad,
+                                          float lo, float hi, float* __restrict__ out_f32,
+                                          __nv_bfloat16* __restrict__ out_bf16, int out_pitch) {
+  const int U = (out_bf16 ? out_pitch : C + (C & 1)) >> 1;     // channel pairs per row (pad lanes of the bf16 rows incl.)
+  const long long total = rows * U;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long sp = stride / U;
+  const int su = (int)(stride - sp * U);
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  long long r = i / U;
+  int u = (int)(i - r * U);
+  for (; i < total; i += stride, r += sp, u += su) {
+    if (u >= U) { u -= U; ++r; }
+    const int c = u << 1;
+    float z[2] = {0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      if (c + j < C) {
+        const float v = logf(fmaxf(rad[r * C + c + j], min_rad));
+        z[j] = fminf(fmaxf((v - mean[c + j]) / (stdv[c + j] + 1e-8f), lo), hi);
+        if (out_f32) out_f32[r * C + c + j] = z[j];
+      }
+    }
+    if (out_bf16) *reinterpret_cast<uint32_t*>(out_bf16 + r * out_pitch + c) = pack_bf16(z[0], z[1]);
+  }
+}
+
+extern "C" int32_t tvae_normalize_radiance(const float* rad, const float* mean, const float* stdv, int64_t rows,
+                                           int32_t C, float min_radiance, float clip_min, float clip_max,
+                                           float* out_f32, void* out_bf16, int32_t out_pitch, cudaStream_t stream) {
+  TVAE_ENTER(rad);
+  TVAE_CHECK(rad && mean && stdv && (out_f32 || out_bf16), "tvae_normalize_radiance: null pointer");
+  TVAE_CHECK(!out_bf16 || (out_pitch >= C && out_pitch % 2 == 0), "tvae_normalize_radiance: bad out_pitch");
+  const long long pairs = rows * ((out_bf16 ? out_pitch : C + 1) / 2);
+  normalize_radiance_kernel<<<ew_grid(pairs), EW_THREADS, 0, stream>>>(
+      rad, mean, stdv, rows, C, min_radiance, clip_min, clip_max, out_f32, reinterpret_cast<__nv_bfloat16*>(out_bf16),
+      out_pitch);
+  TVAE_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int32_t tvae_nhwc_f32_to_nhwc_bf16(const float* x, int64_t in_pitch, int64_t rows, int32_t C, void* out,
+                                              int32_t out_pitch, void* out_lo, cudaStream_t stream) {
+  TVAE_ENTER(x);
+  TVAE_CHECK(x && out, "tvae_nhwc_f32_to_nhwc_bf16: null pointer");
+  TVAE_CHECK(in_pitch >= C && out_pitch >= C && out_pitch % 2 == 0, "tvae_nhwc_f32_to_nhwc_bf16: bad pitch");
+  const int vec2 = (in_pitch % 2 == 0) && ((reinterpret_cast<uintptr_t>(x) & 7) == 0);
+  nhwc_f32_to_bf16_kernel<<<ew_grid(rows * (out_pitch / 2)), EW_THREADS, 0, stream>>>(
+      x, in_pitch, rows, C, reinterpret_cast<__nv_bfloat16*>(out), reinterpret_cast<__nv_bfloat16*>(out_lo), out_pitch,
+      vec2);
+  TVAE_CUDA(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int32_t tvae_gn_stats(const float* x, int32_t N, int32_t HW, int32_t C, int32_t G, float eps, float* stats,
                                  cudaStream_t stream) {
   TVAE_ENTER(x);

@@ -20,12 +20,18 @@ from .model import TvaeError
 
 
 def normalize_radiance(rad: torch.Tensor, mean_spectrum: torch.Tensor, std_spectrum: torch.Tensor,
-                       min_radiance: float = 1.0, clip: float = 10.0) -> torch.Tensor:
-    """[mirror, track, C] raw radiance -> z-scored log-radiance clipped to [-clip, clip] (same formula as the
-    reference's data preparation and analysis scripts)."""
-    log_rad = torch.log(torch.clamp(rad, min_radiance, float("inf")))
-    z = (log_rad - mean_spectrum) / (std_spectrum + 1e-8)
-    return torch.clamp(z, -clip, clip)
+                       min_radiance: float = 1.0, clip: float = 10.0, device=None) -> torch.Tensor:
+    """[mirror, track, C] raw radiance -> z-scored log-radiance clipped to [-clip, clip] (the formula of the
+    reference's data preparation and analysis scripts, src/scripts/prepare_tempo_tiles.py:67-79), computed in one
+    fused pass on the GPU (`tvae_normalize_radiance`). A host tensor is copied to `device` (default: the current
+    CUDA device) first; the result lives on the device."""
+    from . import ops
+    if not rad.is_cuda:
+        if not torch.cuda.is_available():
+            raise TvaeError("normalize_radiance runs on CUDA only (there is no CPU fallback)")
+        rad = rad.to(device if device is not None else torch.device("cuda", torch.cuda.current_device()),
+                     non_blocking=True)
+    return ops.normalize_radiance(rad, mean_spectrum, std_spectrum, min_radiance, -clip, clip)[0]
 
 
 def granule_to_patches(z_rad: torch.Tensor, tile: int = 64) -> torch.Tensor:

@@ -851,7 +851,7 @@ class _ModuleFn(torch.autograd.Function):
     def forward(ctx, x, mod, *params):
         _check_input(x, mod.in_channels_api())
         save = any(ctx.needs_input_grad)
-        xb = ops.nchw_to_nhwc_bf16(x)
+        xb = ops.input_nhwc_bf16(x)
         out, saved = mod.program_fwd(xb, save)
         ctx.mod, ctx.saved = mod, saved
         ctx.x_needs_grad = x.requires_grad
@@ -945,7 +945,7 @@ class _VAELossFn(torch.autograd.Function):
         train = any(ctx.needs_input_grad)
         C = vae.encoder.in_channels
         Z = vae.embed_dim
-        xb = ops.nchw_to_nhwc_bf16(x)
+        xb = ops.input_nhwc_bf16(x)
         enc, dec = _EncodeProgram(vae), _DecodeProgram(vae)
         mom, enc_saved = enc.program_fwd(xb, train)
         if eps is None:

@@ -32,7 +32,7 @@ KERNEL_LAUNCHES = [0]   # kernels of libtvae_b200.so enqueued through this modul
 # kernels launched by one call of each C-ABI entry point
 _KERNELS_PER_CALL = {
     "tvae_pack_weight": 1, "tvae_conv_gemm": 1, "tvae_wgrad_gemm": 2, "tvae_nchw_f32_to_nhwc_bf16": 1,
-    "tvae_nhwc_f32_to_nchw_f32": 1, "tvae_nhwc_bf16_to_nchw_f32": 1, "tvae_f32_to_bf16": 1, "tvae_gn_stats": 1,
+    "tvae_nhwc_f32_to_nchw_f32": 1, "tvae_nhwc_f32_to_nhwc_bf16": 1, "tvae_normalize_radiance": 1, "tvae_nhwc_bf16_to_nchw_f32": 1, "tvae_f32_to_bf16": 1, "tvae_gn_stats": 1,
     "tvae_gn_act_fwd": 1, "tvae_gn_stats_finalize": 1, "tvae_gn_act_bwd": 4, "tvae_colsum_bf16": 2, "tvae_attn_fwd": 1, "tvae_attn_bwd": 2, "tvae_attn_fwd_tc": 1, "tvae_attn_bwd_tc": 2,
     "tvae_reparam_fwd": 1, "tvae_reparam_bwd": 1, "tvae_nll_fwd": 2, "tvae_vae_loss_finalize": 1,
     "tvae_l2head_loss_fwd": 1, "tvae_l2head_loss_bwd": 1, "tvae_l2head_finalize": 1, "tvae_sumsq": 2, "tvae_adamw": 1,
@@ -287,6 +287,48 @@ def nchw_to_nhwc_bf16(x, pitch=None):
     return _pair(out, lo)
 
 
+def input_nhwc_bf16(x):
+    """The engine's bf16 channels-last operand for an NCHW-SHAPED input tensor [N, C, H, W], whatever its memory
+    layout: (a) bf16 with channels-last strides and a row pitch that is a multiple of 8 (what DeviceTileCache
+    yields) is used in place, no kernel; (b) fp32 with channels-last strides (torch.channels_last, or a permuted
+    view of [N, H, W, C] tiles) is cast row by row; (c) anything else goes through the NCHW transpose."""
+    require_cuda(x, "input")
+    N, Cc, H, W = x.shape
+    pitch = round_up(Cc, 8)
+    cl = x.stride(1) == 1 and x.stride(2) == W * x.stride(3) and x.stride(0) == H * x.stride(2) and x.stride(3) >= Cc
+    if cl and x.dtype == torch.bfloat16 and not SPLIT_BF16[0] and x.stride(3) % 8 == 0 and x.data_ptr() % 16 == 0:
+        p = x.stride(3)
+        need = ((N * H * W - 1) * p + Cc) * 2                    # bytes actually addressed (pad lanes are never read)
+        if x.untyped_storage().nbytes() - x.storage_offset() * 2 >= need:
+            return x.permute(0, 2, 3, 1)                          # [N, H, W, C] view, pixel pitch p: zero copy
+    if cl and x.dtype == torch.float32:
+        out = torch.empty((N, H, W, pitch), dtype=torch.bfloat16, device=x.device)
+        lo = _lo_like(out)
+        check(lib.tvae_nhwc_f32_to_nhwc_bf16(x.data_ptr(), x.stride(3), N * H * W, Cc, out.data_ptr(), pitch,
+                                             _ptr(lo), _stream()), "tvae_nhwc_f32_to_nhwc_bf16")
+        return _pair(out, lo)
+    return nchw_to_nhwc_bf16(x)
+
+
+def normalize_radiance(rad, mean, std, min_radiance, clip_min, clip_max, want_f32=True, want_bf16=False):
+    """rad [..., C] fp32 on the device -> (z fp32 [..., C] or None, z bf16 [..., pitch] operand rows or None)."""
+    require_cuda(rad, "radiance")
+    rad = rad.contiguous().float()
+    Cc = rad.shape[-1]
+    rows = rad.numel() // Cc
+    mean = mean.to(rad.device, torch.float32).contiguous()
+    std = std.to(rad.device, torch.float32).contiguous()
+    if mean.numel() != Cc or std.numel() != Cc:
+        raise _lib.TvaeError(f"mean/std spectra must have {Cc} channels")
+    zf = torch.empty_like(rad) if want_f32 else None
+    pitch = round_up(Cc, 8)
+    zb = torch.empty(rad.shape[:-1] + (pitch,), dtype=torch.bfloat16, device=rad.device) if want_bf16 else None
+    check(lib.tvae_normalize_radiance(rad.data_ptr(), mean.data_ptr(), std.data_ptr(), rows, Cc, float(min_radiance),
+                                      float(clip_min), float(clip_max), _ptr(zf), _ptr(zb), pitch, _stream()),
+          "tvae_normalize_radiance")
+    return zf, zb
+
+
 def nhwc_to_nchw_f32(x, Cc):
     x = hi_of(x)
     N, H, W, pitch = x.shape
@@ -433,14 +475,14 @@ def reparam_bwd(moments, Z, dz1, eps1, dz2, eps2, kl_scale):
 def nll_fwd(x_bf16, xhat, Cc, loss_type, logvar, batch, want_grad):
     """x_bf16 [N,H,W,xp] bf16; xhat [N,H,W,hp] fp32. Returns (sums fp64[3], dxhat bf16 or None)."""
     x_bf16 = hi_of(x_bf16)
-    P = x_bf16.numel() // x_bf16.shape[-1]
+    P = x_bf16.numel() // x_bf16.shape[-1]          # pixels (the last dim may be a channel-slice view of pitched rows)
     dev = xhat.device
     sums = torch.empty((3,), dtype=torch.float64, device=dev)
     ws = _workspace(lib.tvae_nll_workspace_bytes(), dev, "nll")
     dx = None
     if want_grad:
         dx = torch.empty(x_bf16.shape[:-1] + (round_up(Cc, 8),), dtype=torch.bfloat16, device=dev)
-    check(lib.tvae_nll_fwd(x_bf16.data_ptr(), x_bf16.shape[-1], xhat.data_ptr(), xhat.shape[-1], P, Cc, loss_type,
+    check(lib.tvae_nll_fwd(x_bf16.data_ptr(), pitch_of(x_bf16), xhat.data_ptr(), pitch_of(xhat), P, Cc, loss_type,
                            _ptr(logvar), batch, _ptr(dx), dx.shape[-1] if dx is not None else 0, sums.data_ptr(),
                            ws.data_ptr(), _stream()), "tvae_nll_fwd")
     return sums, dx

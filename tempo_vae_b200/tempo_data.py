@@ -155,3 +155,88 @@ class DevicePrefetcher:
             self._record(cur)
             nxt, ev = fetch()
             yield cur
+
+
+class DeviceTileCache:
+    """The tile set resident in HBM in the layout the conv kernels read.
+
+    The reference streams fp32 tiles from worker processes, permutes HWC -> CHW, collates and copies 4.3 GB per
+    256-sample step to the GPU (src/tempo_data.py:34-146). The whole January train split is 18 GB as bf16, a tenth of
+    one B200's HBM: here every tile is cast ONCE to channels-last bf16 rows (`tvae_nhwc_f32_to_nhwc_bf16`, pitch
+    rounded up to 8 channels for TMA) and batches are gathered on the device. A batch is yielded as an NCHW-SHAPED
+    `[B, C, H, W]` bf16 view with channels-last strides, which `get_loss` / `encode` consume in place (no transpose,
+    no host->device traffic in the step):
+
+        cache = DeviceTileCache.from_dir(train_dir, device)
+        for x in cache.batches(256, seed=0, rank=rank, world=world):
+            trainer.train_step_device(x)
+
+    Sampling: epoch-wise random permutation without replacement (the reference draws without replacement from a pool
+    refilled file by file; both visit every tile equally often). `rank/world` shard each epoch's permutation.
+    """
+
+    def __init__(self, device, H: int, W: int, C: int, capacity: int):
+        from . import ops
+        self.device = torch.device(device)
+        self.H, self.W, self.C = H, W, C
+        self.pitch = ops.round_up(C, 8)
+        self.data = torch.zeros((capacity, H, W, self.pitch), dtype=torch.bfloat16, device=self.device)
+        self.n = 0
+
+    def __len__(self):
+        return self.n
+
+    def add(self, tiles: torch.Tensor, chunk: int = 64):
+        """tiles: [n, H, W, C] or [H, W, C] fp32, channels last (the on-disk format), on the host or the device."""
+        from . import ops
+        from ._lib import lib
+        if tiles.dim() == 3:
+            tiles = tiles.unsqueeze(0)
+        if tuple(tiles.shape[1:]) != (self.H, self.W, self.C):
+            raise ValueError(f"tile shape {tuple(tiles.shape[1:])} does not match the cache ({self.H}, {self.W}, {self.C})")
+        if self.n + tiles.shape[0] > self.data.shape[0]:
+            raise ValueError("DeviceTileCache capacity exceeded")
+        for i in range(0, tiles.shape[0], chunk):
+            t = tiles[i:i + chunk].to(self.device, dtype=torch.float32, non_blocking=True).contiguous()
+            dst = self.data[self.n:self.n + t.shape[0]]
+            ops.check(lib.tvae_nhwc_f32_to_nhwc_bf16(t.data_ptr(), self.C, t.shape[0] * self.H * self.W, self.C,
+                                                     dst.data_ptr(), self.pitch, None, ops._stream()),
+                      "tvae_nhwc_f32_to_nhwc_bf16")
+            self.n += t.shape[0]
+
+    @classmethod
+    def from_dir(cls, data_dir: str, device, max_tiles=None, verbose: bool = False):
+        files = sorted(glob.glob(str(Path(data_dir) / "*.pt")))
+        if not files:
+            raise ValueError(f"No .pt files found in {data_dir}")
+        first = torch.load(files[0], weights_only=False)
+        if first.dim() == 3:
+            first = first.unsqueeze(0)
+        per_file, H, W, C = first.shape
+        cap = per_file * len(files) if max_tiles is None else min(max_tiles, per_file * len(files))
+        cache = cls(device, H, W, C, cap)
+        for i, f in enumerate(tqdm(files, desc="Caching tiles on the device") if verbose else files):
+            t = first if i == 0 else torch.load(f, weights_only=False)
+            if t.dim() == 3:
+                t = t.unsqueeze(0)
+            room = cap - cache.n
+            if room <= 0:
+                break
+            if t.shape[0] > per_file and max_tiles is None:
+                raise ValueError(f"{f} holds {t.shape[0]} tiles, more than the first file ({per_file})")
+            cache.add(t[:room])
+        return cache
+
+    def batches(self, batch_size: int, seed: int = 0, epochs=None, rank: int = 0, world: int = 1):
+        """Yields [batch_size, C, H, W] bf16 channels-last views; the last partial batch of an epoch is dropped.
+        Each yielded batch owns its memory (a device-side gather), so it may be kept across iterations."""
+        if self.n < batch_size * world:
+            raise ValueError(f"{self.n} cached tiles cannot fill a batch of {batch_size} on {world} ranks")
+        g = torch.Generator().manual_seed(seed)
+        epoch = 0
+        while epochs is None or epoch < epochs:
+            perm = torch.randperm(self.n, generator=g)[rank::world].to(self.device)
+            for i in range(0, perm.numel() - batch_size + 1, batch_size):
+                x = torch.index_select(self.data, 0, perm[i:i + batch_size])
+                yield x[..., :self.C].permute(0, 3, 1, 2)
+            epoch += 1

@@ -202,6 +202,30 @@ def test_wgrad_strided(N, H, W, Cin, Cout):
     assert rel_err(gradt, wt.grad) < 2e-3
 
 
+@pytest.mark.parametrize("rows,C,in_pitch", [(4096, 1028, 1028), (1000, 20, 24), (257, 7, 7), (64, 512, 640)])
+def test_channels_last_cast_and_radiance_normalisation(rows, C, in_pitch):
+    o = ops()
+    from tempo_vae_b200._lib import lib
+    g = torch.Generator(device="cuda").manual_seed(23)
+    buf = torch.randn((rows, in_pitch), device="cuda", generator=g)
+    pitch = o.round_up(C, 8)
+    out = torch.full((rows, pitch), float("nan"), device="cuda", dtype=torch.bfloat16)
+    o.check(lib.tvae_nhwc_f32_to_nhwc_bf16(buf.data_ptr(), in_pitch, rows, C, out.data_ptr(), pitch, None, None),
+            "tvae_nhwc_f32_to_nhwc_bf16")
+    torch.cuda.synchronize()
+    assert torch.equal(out[:, :C], buf[:, :C].to(torch.bfloat16)) and (out[:, C:] == 0).all()
+    # z-scored log radiance, fp32 and bf16-operand outputs from one pass
+    rad = torch.exp(torch.randn((rows, C), device="cuda", generator=g) * 2.0 + 1.0)
+    mean = torch.randn((C,), device="cuda", generator=g) + 1.0
+    std = torch.rand((C,), device="cuda", generator=g) + 0.5
+    zf, zb = o.normalize_radiance(rad, mean, std, 1.0, -3.0, 3.0, want_f32=True, want_bf16=True)
+    ref = torch.clamp((torch.log(torch.clamp(rad, 1.0, float("inf"))) - mean) / (std + 1e-8), -3.0, 3.0)
+    torch.cuda.synchronize()
+    assert (zf - ref).abs().max() < 1e-5
+    assert torch.equal(zb[:, :C], zf.to(torch.bfloat16)) and (zb[:, C:] == 0).all()
+    assert float(zf.max()) <= 3.0 and float(zf.min()) >= -3.0
+
+
 def test_layout_roundtrip():
     o = ops()
     x = torch.randn((3, 1028, 16, 16), device="cuda")

@@ -349,8 +349,10 @@ def test_inference_patch_sweep_and_whole_granule_vs_oracle(capsys):
     g = torch.Generator().manual_seed(21)
     rad = torch.exp(torch.randn((131, 256, C), generator=g) * 0.5 + 3.0)
     mean_s, std_s = torch.full((C,), 3.0), torch.full((C,), 0.5)
-    z = t.normalize_radiance(rad, mean_s, std_s)
-    assert float(z.abs().max()) <= 10.0
+    z = t.normalize_radiance(rad, mean_s, std_s)             # fused CUDA kernel; host input is copied over
+    z_ref = torch.clamp((torch.log(torch.clamp(rad, 1.0, float("inf"))) - mean_s) / (std_s + 1e-8), -10.0, 10.0)
+    assert z.is_cuda and float((z.cpu() - z_ref).abs().max()) < 1e-5     # src/scripts/prepare_tempo_tiles.py:67-79
+    z = z.cpu()
     patches = t.granule_to_patches(z)                       # 2 x 4 patches of [C, 64, 64]
     assert patches.shape == (8, C, 64, 64)
     lat = torch.cat([t.encode_patches(model, patches, batch_size=3, rank=r, world=2).cpu() for r in range(2)])
@@ -484,3 +486,56 @@ def test_wgrad_stream_overlap_gives_identical_gradients():
     for k in grads[0]:
         assert torch.equal(grads[0][k], grads[1][k]), k
         assert torch.equal(grads[1][k], grads[2][k]), k
+
+
+def test_channels_last_inputs_are_consumed_without_the_nchw_detour(tmp_path):
+    """"accept channels_last strides without copying". The same values fed as (a) NCHW fp32, (b) fp32
+    with channels-last strides, (c) a permuted view of [N, H, W, C] tiles and (d) the bf16 channels-last view that
+    DeviceTileCache yields give bit-identical losses and gradients."""
+    import tempo_vae_b200 as t
+    cfg = orc.TINY_CFG
+    C, H, W = cfg["shape"]
+    tiles = orc.structured_batch(8, cfg, seed=11).permute(0, 2, 3, 1).contiguous()          # [8, H, W, C] as on disk
+    tiles = tiles.to(torch.bfloat16).float()                                                 # bf16-representable
+    torch.save(tiles[:5].clone(), tmp_path / "a.pt")
+    torch.save(tiles[5:].clone(), tmp_path / "b.pt")
+    cache = t.DeviceTileCache.from_dir(str(tmp_path), torch.device("cuda"))
+    assert len(cache) == 8 and cache.pitch % 8 == 0
+    assert torch.equal(cache.data[:8, :, :, :C].float().cpu(), tiles)
+    # one epoch visits every tile exactly once
+    seen = torch.cat([x.float().permute(0, 2, 3, 1).cpu() for x in cache.batches(4, seed=1, epochs=1)], 0)
+    assert seen.shape[0] == 8
+    key = lambda z: sorted(round(float(v), 4) for v in z.reshape(z.shape[0], -1).sum(1))      # noqa: E731
+    assert key(seen) == key(tiles)
+    # rank sharding: disjoint halves
+    halves = [torch.cat([x.float().cpu() for x in cache.batches(2, seed=2, epochs=1, rank=r, world=2)], 0) for r in (0, 1)]
+    assert halves[0].shape[0] == halves[1].shape[0] == 4
+    assert key(torch.cat(halves, 0).permute(0, 2, 3, 1)) == key(tiles)
+
+    eps = torch.randn((4, cfg["embed_dim"], H // 4, W // 4), generator=torch.Generator().manual_seed(3)).cuda()
+    x_nchw = tiles[:4].permute(0, 3, 1, 2).contiguous().cuda()
+    variants = {
+        "nchw_f32": x_nchw,
+        "channels_last_f32": x_nchw.contiguous(memory_format=torch.channels_last),
+        "tile_view_f32": tiles[:4].cuda().permute(0, 3, 1, 2),
+        "cache_bf16": cache.data[:4, :, :, :C].permute(0, 3, 1, 2),
+    }
+    assert variants["cache_bf16"].dtype == torch.bfloat16 and not variants["cache_bf16"].is_contiguous()
+    results = {}
+    for name, xin in variants.items():
+        model = build(cfg, seed=7)
+        sd = orc.rerandomize_zero_init({k: v.detach().cpu().clone() for k, v in model.state_dict().items()})
+        model.load_state_dict(sd)
+        loss, _ = model.vae.get_loss(xin, eps=eps)
+        loss.backward()
+        torch.cuda.synchronize()
+        results[name] = (loss.detach().clone(), {k: p.grad.detach().clone() for k, p in model.named_parameters()
+                                                 if p.grad is not None})
+        post = model.vae.encode(xin)
+        results[name] += (post.mean.detach().clone(),)
+    base = results["nchw_f32"]
+    for name, r in results.items():
+        assert torch.equal(r[0], base[0]), name
+        assert torch.equal(r[2], base[2]), name
+        for k in base[1]:
+            assert torch.equal(r[1][k], base[1][k]), (name, k)
