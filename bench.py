@@ -418,6 +418,28 @@ def run_extra(args):
                "metric": "train samples/sec (fwd+bwd+AdamW)", "value": world * B / ms * 1e3, "unit": "samples/s",
                "ms_per_step": ms, "n_gpus": world, "batch_per_gpu": B,
                "final_metrics": {k: float(v.detach()) for k, v in m.items()}}
+    elif args.workload == "train_cached":
+        # the train step fed from a device-resident channels-last bf16 tile cache
+        trainer = t.Trainer(model, model.optimizer, dev, tempfile.mkdtemp(prefix="tvae_bench_"))
+        trainer.step = 1
+        n_tiles = 4 * B
+        cache = t.DeviceTileCache(dev, 64, 64, 1028, n_tiles)
+        g = torch.Generator(device=dev).manual_seed(7 + rank)
+        for _ in range(n_tiles // 64):
+            cache.add(torch.randn((64, 64, 64, 1028), device=dev, generator=g).clamp_(-10, 10))
+        it = cache.batches(B, seed=rank)
+        for _ in range(args.warmup):
+            trainer.train_step_device(next(it))
+        sync(); e0.record()
+        for _ in range(args.steps):
+            m = trainer.train_step_device(next(it))
+        e1.record(); sync()
+        ms = e0.elapsed_time(e1) / args.steps
+        out = {"workload": "train step fed from DeviceTileCache (tiles resident in HBM as channels-last bf16, batches "
+                           "gathered on the device and consumed without a layout pass)",
+               "metric": "train samples/sec (fwd+bwd+AdamW)", "value": world * B / ms * 1e3, "unit": "samples/s",
+               "ms_per_step": ms, "n_gpus": world, "batch_per_gpu": B, "cached_tiles_per_gpu": n_tiles,
+               "final_metrics": {k: float(v.detach()) for k, v in m.items()}}
     else:
         # synthetic granules [131, 2048, 1028] -> normalise -> crop [128, 2048] -> 64 patches of [1028, 64, 64] each
         n_gran = 4
@@ -463,9 +485,10 @@ def main():
                     help="--impl reference only: cpu = the contract's reference arm; cuda = same-box PyTorch-eager comparator")
     ap.add_argument("--ref-precision", default="tf32", choices=["fp32", "tf32", "bf16"])
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: skip the host-fed leg")
-    ap.add_argument("--workload", default="train", choices=["train", "train_l2", "encode"],
+    ap.add_argument("--workload", default="train", choices=["train", "train_l2", "train_cached", "encode"],
                     help="train = headline (BASELINE config 2/4); train_l2 = L2-supervised variant (config 3); "
-                         "encode = inference-only patch sweep of synthetic granules (config 5). The extra workloads "
+                         "encode = inference-only patch sweep of synthetic granules (config 5); train_cached = train step "
+                         "fed from the device-resident tile cache (SURVEY 8f). The extra workloads "
                          "print their own JSON line and are not the headline metric.")
     args = ap.parse_args()
     if args.impl == "reference" and args.ref_device == "cuda":
