@@ -25,3 +25,13 @@ grad = torch.empty((512, 512, 3, 3), device="cuda")
 o.wgrad_gemm(dy, 512, x, 512, kind=0, R=3, grad=grad)
 torch.cuda.synchronize()
 print("ok2")
+# GroupNorm + GELU forward / backward on the same tensor size (fp32 residual-stream input), for the HBM-bound roofline
+C, G = 512, 8
+xf = torch.randn((B, 64, 64, C), device="cuda", generator=g)
+gamma = torch.ones(C, device="cuda"); beta = torch.zeros(C, device="cuda")
+stats = o.gn_stats(xf, C, G, 1e-6)
+o.gn_act_fwd(xf, stats, gamma, beta, G, 1)
+dg, db, cs = (torch.empty(C, device="cuda") for _ in range(3))
+o.gn_act_bwd(xf, stats, gamma, beta, dy, res.to(torch.bfloat16), G, 1, dg, db, cs)
+torch.cuda.synchronize()
+print("ok3")
