@@ -216,6 +216,12 @@ int32_t tvae_reparam_bwd(const float* moments, const float* dz1, const float* ep
  *  grad_scale = exp(-logvar) / B (read from the device scalar `logvar`): dxhat = sign(xhat - x)*s or 2(xhat-x)*s.
  *  workspace: tvae_nll_workspace_bytes().
  */
+/* Per-sample reconstruction metrics (src/scripts/evaluate_reconstruction.py:23-42): out[n] = (MAE, MSE) between the
+ * bf16 input rows x and the fp32 reconstruction xhat (both channels-last, [N][HW][pitch]); PSNR follows from the MSE.
+ * Fixed-order reductions. workspace: tvae_recon_metrics_workspace_bytes(N). */
+int64_t tvae_recon_metrics_workspace_bytes(int32_t N);
+int32_t tvae_recon_metrics(const void* x_bf16, int32_t x_pitch, const float* xhat, int32_t xh_pitch, int32_t N,
+                           int32_t HW, int32_t C, float* out, double* workspace, tvae_stream_t stream);
 int64_t tvae_nll_workspace_bytes(void);
 int32_t tvae_nll_fwd(const void* x_bf16, int32_t x_pitch, const float* xhat, int32_t xh_pitch, int64_t P, int32_t C,
                      int32_t loss_type, const float* logvar, int32_t batch, void* dxhat_bf16, int32_t dx_pitch,

@@ -174,6 +174,43 @@ __global__ void nll_final_kernel(const double* __restrict__ ws, int nblocks, dou
   if (threadIdx.x == 0) { sums[0] = t1; sums[1] = t2; sums[2] = 0.0; }
 }
 
+// Per-sample reconstruction error sums (evaluation metrics of src/scripts/evaluate_reconstruction.py:23-42):
+// part[n][chunk] = (sum |x - xhat|, sum (x - xhat)^2) over the chunk's pixels; recon_metrics_final adds the chunks.
+constexpr int RM_CHUNKS = 16;
+__global__ void __launch_bounds__(256)
+recon_metrics_kernel(const __nv_bfloat16* __restrict__ x, int x_pitch, const float* __restrict__ xh, int xh_pitch,
+                     int HW, int C, double* __restrict__ part) {
+  __shared__ double red[32];
+  const int n = blockIdx.y;
+  const int per = (HW + RM_CHUNKS - 1) / RM_CHUNKS;
+  const int p0 = blockIdx.x * per, p1 = min(p0 + per, HW);
+  double a1 = 0.0, a2 = 0.0;
+  for (int p = p0; p < p1; ++p) {
+    const long long row = (long long)n * HW + p;
+    float f1 = 0.f, f2 = 0.f;
+    for (int c = threadIdx.x; c < C; c += 256) {
+      const float d = xh[row * xh_pitch + c] - __bfloat162float(x[row * x_pitch + c]);
+      f1 += fabsf(d);
+      f2 = fmaf(d, d, f2);
+    }
+    a1 += f1; a2 += f2;
+  }
+  const double t1 = block_sum(a1, red);
+  const double t2 = block_sum(a2, red);
+  if (threadIdx.x == 0) {
+    part[2 * (n * RM_CHUNKS + blockIdx.x)] = t1;
+    part[2 * (n * RM_CHUNKS + blockIdx.x) + 1] = t2;
+  }
+}
+__global__ void recon_metrics_final_kernel(const double* __restrict__ part, int N, double count, float* __restrict__ out) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  double a = 0.0, b = 0.0;
+  for (int k = 0; k < RM_CHUNKS; ++k) { a += part[2 * (n * RM_CHUNKS + k)]; b += part[2 * (n * RM_CHUNKS + k) + 1]; }
+  out[2 * n] = (float)(a / count);       // MAE
+  out[2 * n + 1] = (float)(b / count);   // MSE
+}
+
 // loss / metric scalars of AutoencoderKL.get_loss (src/model.py:660-668), one thread:
 //   out[0] = loss, out[1] = nll_loss, out[2] = kl_loss (already * kl_weight), out[3] = pixel_mse,
 //   out[4] = d(loss)/d(logvar)
@@ -386,6 +423,21 @@ extern "C" int32_t tvae_nll_fwd(const void* x, int32_t x_pitch, const float* xha
                                                      dx_pitch, ws);
   TVAE_CUDA(cudaGetLastError());
   nll_final_kernel<<<1, 256, 0, stream>>>(ws, NLL_BLOCKS, sums);
+  TVAE_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int64_t tvae_recon_metrics_workspace_bytes(int32_t N) { return (int64_t)N * RM_CHUNKS * 2 * sizeof(double); }
+
+extern "C" int32_t tvae_recon_metrics(const void* x, int32_t x_pitch, const float* xhat, int32_t xh_pitch, int32_t N,
+                                      int32_t HW, int32_t C, float* out, double* ws, cudaStream_t stream) {
+  TVAE_ENTER(x);
+  TVAE_CHECK(x && xhat && out && ws, "tvae_recon_metrics: null pointer");
+  TVAE_CHECK(N > 0 && HW > 0 && C > 0 && x_pitch >= C && xh_pitch >= C, "tvae_recon_metrics: bad shape");
+  recon_metrics_kernel<<<dim3(RM_CHUNKS, N), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), x_pitch, xhat,
+                                                              xh_pitch, HW, C, ws);
+  TVAE_CUDA(cudaGetLastError());
+  recon_metrics_final_kernel<<<(N + 127) / 128, 128, 0, stream>>>(ws, N, (double)HW * C, out);
   TVAE_CUDA(cudaGetLastError());
   return 0;
 }

@@ -72,3 +72,33 @@ def encode_granule_whole(model, z_rad: torch.Tensor, tile: int = 64) -> torch.Te
     M, T, C = z_rad.shape
     x = z_rad[:(M // tile) * tile, :(T // tile) * tile, :].permute(2, 0, 1).unsqueeze(0)
     return vae.encode(x.to(dev, dtype=torch.float32)).mean
+
+
+@torch.no_grad()
+def evaluate_reconstruction(model, x: torch.Tensor, eps: Optional[torch.Tensor] = None,
+                            sample_posterior: bool = True, max_val: float = 20.0) -> dict:
+    """Per-sample reconstruction metrics of src/scripts/evaluate_reconstruction.py:23-42 for a batch x [B, C, H, W]:
+    {"mse": [B], "mae": [B], "psnr": [B]} on the device (PSNR = 10 log10(max_val^2 / (mse + 1e-10)), max_val = 20 for
+    data clipped to [-10, 10]). One stochastic forward like the reference's `model(x)` (or the posterior mode with
+    sample_posterior=False; `eps` injects the noise); the errors are reduced by `tvae_recon_metrics` straight from the
+    channels-last reconstruction, which is never converted back to NCHW."""
+    from . import ops
+    from .model import ENGINE, _DecodeProgram, _EncodeProgram, _check_input
+    vae = model.vae if hasattr(model, "vae") else model
+    C, Z = vae.encoder.in_channels, vae.embed_dim
+    _check_input(x, C)
+    B = x.shape[0]
+    xb = ops.input_nhwc_bf16(x)
+    mom, _ = _EncodeProgram(vae).program_fwd(xb, False)
+    if not sample_posterior:
+        eps = torch.zeros((B, Z, mom.f32.shape[1], mom.f32.shape[2]), device=x.device)
+    if eps is None:
+        off = ENGINE.rng_offset
+        ENGINE.rng_offset += B
+        z = ops.reparam_fwd(mom.f32, Z, seed=ENGINE.rng_seed, sample_offset=off)[0]
+    else:
+        z = ops.reparam_fwd(mom.f32, Z, eps=eps)[0]
+    xhat, _ = _DecodeProgram(vae).program_fwd(z, False)
+    m = ops.recon_metrics(xb, xhat.f32, C)
+    mse = m[:, 1]
+    return {"mse": mse, "mae": m[:, 0], "psnr": 10.0 * torch.log10(max_val ** 2 / (mse + 1e-10))}

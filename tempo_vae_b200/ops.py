@@ -32,7 +32,7 @@ KERNEL_LAUNCHES = [0]   # kernels of libtvae_b200.so enqueued through this modul
 # kernels launched by one call of each C-ABI entry point
 _KERNELS_PER_CALL = {
     "tvae_pack_weight": 1, "tvae_conv_gemm": 1, "tvae_wgrad_gemm": 2, "tvae_nchw_f32_to_nhwc_bf16": 1,
-    "tvae_nhwc_f32_to_nchw_f32": 1, "tvae_nhwc_f32_to_nhwc_bf16": 1, "tvae_normalize_radiance": 1, "tvae_nhwc_bf16_to_nchw_f32": 1, "tvae_f32_to_bf16": 1, "tvae_gn_stats": 1,
+    "tvae_nhwc_f32_to_nchw_f32": 1, "tvae_nhwc_f32_to_nhwc_bf16": 1, "tvae_normalize_radiance": 1, "tvae_recon_metrics": 2, "tvae_nhwc_bf16_to_nchw_f32": 1, "tvae_f32_to_bf16": 1, "tvae_gn_stats": 1,
     "tvae_gn_act_fwd": 1, "tvae_gn_stats_finalize": 1, "tvae_gn_act_bwd": 4, "tvae_colsum_bf16": 2, "tvae_attn_fwd": 1, "tvae_attn_bwd": 2, "tvae_attn_fwd_tc": 1, "tvae_attn_bwd_tc": 2,
     "tvae_reparam_fwd": 1, "tvae_reparam_bwd": 1, "tvae_nll_fwd": 2, "tvae_vae_loss_finalize": 1,
     "tvae_l2head_loss_fwd": 1, "tvae_l2head_loss_bwd": 1, "tvae_l2head_finalize": 1, "tvae_sumsq": 2, "tvae_adamw": 1,
@@ -486,6 +486,17 @@ def nll_fwd(x_bf16, xhat, Cc, loss_type, logvar, batch, want_grad):
                            _ptr(logvar), batch, _ptr(dx), dx.shape[-1] if dx is not None else 0, sums.data_ptr(),
                            ws.data_ptr(), _stream()), "tvae_nll_fwd")
     return sums, dx
+
+
+def recon_metrics(x_bf16, xhat, Cc):
+    """x_bf16 [N,H,W,xp] bf16, xhat [N,H,W,hp] fp32 -> fp32 [N, 2] = per-sample (MAE, MSE)."""
+    x_bf16 = hi_of(x_bf16)
+    N, H, W = xhat.shape[0], xhat.shape[1], xhat.shape[2]
+    out = torch.empty((N, 2), dtype=torch.float32, device=xhat.device)
+    ws = _workspace(lib.tvae_recon_metrics_workspace_bytes(N), xhat.device, "recon_metrics")
+    check(lib.tvae_recon_metrics(x_bf16.data_ptr(), pitch_of(x_bf16), xhat.data_ptr(), pitch_of(xhat), N, H * W, Cc,
+                                 out.data_ptr(), ws.data_ptr(), _stream()), "tvae_recon_metrics")
+    return out
 
 
 def vae_loss_finalize(sums, kl, logvar, n_elem, kl_weight):

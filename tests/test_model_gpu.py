@@ -576,3 +576,28 @@ def test_full_size_step_properties():
     assert abs(0.5 * (h0[0] + h1[0]) - a[0]) / a[0] < 1e-6
     assert abs(0.5 * (h0[1] + h1[1]) - a[1]) / max(a[1], 1e-12) < 1e-4
     assert math.isfinite(a[3]) and a[3] > 0
+
+
+def test_evaluate_reconstruction_metrics_vs_oracle():
+    """src/scripts/evaluate_reconstruction.py:23-42: per-sample MSE / MAE / PSNR of a stochastic reconstruction, against the
+    same quantities computed from the oracle's reconstruction with the same injected noise."""
+    import tempo_vae_b200 as t
+    cfg = orc.TINY_CFG
+    fx = gold("tiny_train.pt")
+    model = build(cfg, fx["state_dict"])
+    x = orc.structured_batch(5, cfg, seed=31)
+    eps = torch.randn((5, cfg["embed_dim"], cfg["shape"][1] // 4, cfg["shape"][2] // 4),
+                      generator=torch.Generator().manual_seed(9))
+    got = t.evaluate_reconstruction(model, x.cuda(), eps=eps.cuda())
+    with torch.no_grad():
+        mean, logvar, _ = orc.encode(fx["state_dict"], x, cfg)
+        z = mean + torch.exp(0.5 * torch.clamp(logvar, -30.0, 20.0)) * eps
+        recon = orc.decode(fx["state_dict"], z, cfg)
+    d = (x - recon).reshape(5, -1)
+    ref_mse, ref_mae = (d ** 2).mean(1), d.abs().mean(1)
+    ref_psnr = 10.0 * torch.log10(20.0 ** 2 / (ref_mse + 1e-10))
+    assert got["mse"].shape == (5,) and got["mse"].is_cuda
+    assert rel(got["mse"], ref_mse) < 2e-2 and rel(got["mae"], ref_mae) < 2e-2
+    assert (got["psnr"].cpu() - ref_psnr).abs().max() < 0.1          # dB
+    mode = t.evaluate_reconstruction(model, x.cuda(), sample_posterior=False)
+    assert torch.isfinite(mode["psnr"]).all()
