@@ -81,7 +81,7 @@ gn_act_fwd_fast_kernel(const TX* __restrict__ x, const float* __restrict__ stats
 }
 
 // dx = rstd * (dy*gamma - m1 - xhat*m2) (+ gres), dy = da * act'(gamma*xhat + beta)
-// cs_part (optional): per-block column sums of the bf16 values written to dx, [n][chunk][C] -- dx is the output
+// cs_part (optional): per-block column sums of dx (before its bf16 rounding), [n][chunk][C] -- dx is the output
 // gradient of the conv that produced x, so its column sums are that conv's bias gradient and the separate pass over
 // dx (tvae_colsum_bf16) disappears.
 template <typename TX>
@@ -96,12 +96,20 @@ gn_bwd_apply_fast_kernel(const TX* __restrict__ x, const float* __restrict__ sta
   const int c = u << 3, n = blockIdx.y;
   const int sg = n * G + c / (C / G);
   const float mean = stats[2 * sg], rstd = stats[2 * sg + 1];
-  const float m1r = gmeans[2 * sg] * rstd, m2r = gmeans[2 * sg + 1] * rstd;
-  float gm[8], bt[8], gr[8], cs[8];
-  load8(gamma + c, gm);
-  load8(beta + c, bt);
+  // everything that multiplies x is folded into per-thread constants, so an element costs one FMA for the activation
+  // argument y = x*sc + sh, one for the mean terms t = x*ta + tb (= rstd*(m1 + xhat*m2)), act', and two for dx
+  const float ta = gmeans[2 * sg + 1] * rstd * rstd;
+  const float tb = gmeans[2 * sg] * rstd - mean * ta;
+  float sc[8], sh[8], gr[8], cs[8];
+  load8(gamma + c, sc);
+  load8(beta + c, sh);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { gr[j] = gm[j] * rstd; cs[j] = 0.f; }
+  for (int j = 0; j < 8; ++j) {
+    gr[j] = sc[j] * rstd;
+    sc[j] = gr[j];
+    sh[j] = fmaf(-mean, sc[j], sh[j]);
+    cs[j] = 0.f;
+  }
   const int r0 = blockIdx.x * rpb;
   const int r1 = min(r0 + rpb, HW);
   const long long base = (long long)n * HW * C + c;
@@ -119,11 +127,10 @@ gn_bwd_apply_fast_kernel(const TX* __restrict__ x, const float* __restrict__ sta
     float o[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float xh = (xv[j] - mean) * rstd;
       float dy = dv[j];
-      if (act) dy *= act_grad_fast(fmaf(xh, gm[j], bt[j]), act);
-      o[j] = fmaf(dy, gr[j], rv[j]) - fmaf(xh, m2r, m1r);
-      cs[j] += __bfloat162float(__float2bfloat16(o[j]));   // what the consumers of dx will read
+      if (act) dy *= act_grad_fast(fmaf(xv[j], sc[j], sh[j]), act);
+      o[j] = fmaf(dy, gr[j], rv[j]) - fmaf(xv[j], ta, tb);
+      cs[j] += o[j];
     }
     store8_bf16(dx + off, o);
   }

@@ -268,9 +268,13 @@ def test_groupnorm_gelu_fwd_bwd(N, H, W, C, G, act, eps):
     assert rel_err(dx.float().permute(0, 3, 1, 2), x.grad + gres) < 1e-2
     assert rel_err(dgamma, gamma.grad) < 1e-3
     assert rel_err(dbeta, beta.grad) < 1e-3
-    # fused column sums of dx (bias gradient of the producing conv): exactly the sums of the stored bf16 values
-    ref_cs = dx.double().sum(dim=(0, 1, 2))
-    assert (colsum.double() - ref_cs).abs().max() <= 1e-5 * dx.double().abs().sum(dim=(0, 1, 2)).max() + 1e-6
+    # fused column sums of dx (bias gradient of the producing conv), accumulated before dx is rounded to bf16:
+    # against the fp32 reference, and within bf16 rounding noise of the sums of the stored values
+    ref_cs = (x.grad + gres).double().sum(dim=(0, 2, 3))
+    scale = (x.grad + gres).double().abs().sum(dim=(0, 2, 3)).max()
+    tol = 1e-4 if o.gn_fast_ok(C, G) else 4e-3        # generic geometries sum the stored (bf16-rounded) dx instead
+    assert (colsum.double() - ref_cs).abs().max() <= tol * scale + 1e-6
+    assert (colsum.double() - dx.double().sum(dim=(0, 1, 2))).abs().max() <= 4e-3 * scale
     # and the entry point still works without it
     dx2 = o.gn_act_bwd(xn, stats, gamma.detach(), beta.detach(), da.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16),
                        gres.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16), G, act, dgamma, dbeta)
