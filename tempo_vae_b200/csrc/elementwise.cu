@@ -77,6 +77,50 @@ __global__ void nchw_to_nhwc_bf16_kernel(const float* __restrict__ x, __nv_bfloa
   }
 }
 
+// Same transpose with 16-byte accesses on both sides (HW % 4 == 0, pitch % 8 == 0, no split-bf16 output): float4 loads
+// along pixels, 8-channel bf16 stores along channels; 64 channels x 64 pixels per block.
+__global__ void __launch_bounds__(256)
+nchw_to_nhwc_bf16_vec_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int C, int HW, int pitch) {
+  __shared__ float tile[64][65];
+  const int n = blockIdx.z;
+  const int c0 = blockIdx.y * 64, p0 = blockIdx.x * 64;
+  const float* xn = x + (long long)n * C * HW;
+  {
+    const int pq = (threadIdx.x & 15) << 2, cr = threadIdx.x >> 4;
+    float4 v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = c0 + cr + 16 * i, p = p0 + pq;
+      v[i] = (c < C && p < HW) ? *reinterpret_cast<const float4*>(xn + (long long)c * HW + p)
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float* t = &tile[cr + 16 * i][pq];
+      t[0] = v[i].x; t[1] = v[i].y; t[2] = v[i].z; t[3] = v[i].w;
+    }
+  }
+  __syncthreads();
+  {
+    const int c8 = (threadIdx.x & 7) << 3, pr = threadIdx.x >> 3;
+    const int c = c0 + c8;
+    if (c < pitch) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int pl = pr + 32 * i, p = p0 + pl;
+        if (p < HW) {
+          uint4 o;
+          o.x = pack_bf16(tile[c8][pl], tile[c8 + 1][pl]);
+          o.y = pack_bf16(tile[c8 + 2][pl], tile[c8 + 3][pl]);
+          o.z = pack_bf16(tile[c8 + 4][pl], tile[c8 + 5][pl]);
+          o.w = pack_bf16(tile[c8 + 6][pl], tile[c8 + 7][pl]);
+          *reinterpret_cast<uint4*>(out + ((long long)n * HW + p) * pitch + c) = o;   // lanes >= C were loaded as 0
+        }
+      }
+    }
+  }
+}
+
 // NHWC (fp32 or bf16, pitch) -> NCHW fp32
 template <typename T>
 __global__ void nhwc_to_nchw_kernel(const T* __restrict__ x, float* __restrict__ out, int C, int HW, int pitch) {
@@ -494,8 +538,12 @@ extern "C" int32_t tvae_nchw_f32_to_nhwc_bf16(const float* x, void* out, int32_t
   TVAE_CHECK(x && out, "tvae_nchw_f32_to_nhwc_bf16: null pointer");
   TVAE_CHECK(pitch >= C && pitch % 2 == 0, "tvae_nchw_f32_to_nhwc_bf16: bad pitch");
   dim3 grid((HW + 63) / 64, (pitch + 63) / 64, N);
-  nchw_to_nhwc_bf16_kernel<<<grid, 256, 0, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(out),
-                                                     reinterpret_cast<__nv_bfloat16*>(out_lo), C, HW, pitch);
+  if (!out_lo && HW % 4 == 0 && pitch % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(out) & 15) == 0)
+    nchw_to_nhwc_bf16_vec_kernel<<<grid, 256, 0, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(out), C, HW, pitch);
+  else
+    nchw_to_nhwc_bf16_kernel<<<grid, 256, 0, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(out),
+                                                       reinterpret_cast<__nv_bfloat16*>(out_lo), C, HW, pitch);
   TVAE_CUDA(cudaGetLastError());
   return 0;
 }

@@ -237,6 +237,14 @@ def test_layout_roundtrip():
     f = torch.randn((3, 16, 16, 1028), device="cuda")
     assert torch.equal(o.nhwc_to_nchw_f32(f, 1028), f.permute(0, 3, 1, 2))
     assert torch.equal(o.f32_to_bf16(f), f.to(torch.bfloat16))
+    # vectorised and scalar transpose paths, partial tiles, pad lanes
+    for (N, C, H, W) in [(1, 1028, 64, 64), (2, 20, 16, 16), (2, 70, 12, 12), (3, 7, 5, 5), (2, 130, 4, 8)]:
+        x = torch.randn((N, C, H, W), device="cuda")
+        pitch = o.round_up(C, 8)
+        y = o.nchw_to_nhwc_bf16(x)
+        assert y.shape == (N, H, W, pitch)
+        assert torch.equal(y[..., :C], x.permute(0, 2, 3, 1).to(torch.bfloat16)), (N, C, H, W)
+        assert (y[..., C:] == 0).all()
 
 
 @pytest.mark.parametrize("N,H,W,C,G,act,eps", [(3, 16, 16, 128, 8, 1, 1e-6), (2, 64, 64, 512, 8, 1, 1e-6), (2, 16, 16, 128, 8, 0, 1e-6),
