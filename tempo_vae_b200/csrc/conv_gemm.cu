@@ -75,7 +75,9 @@ struct ConvParams {
 // accumulator rows into that CTA's own TMEM. Barrier topology: "full" lives in the leader (both producers' TMA
 // bytes are counted there), "empty" and "tmem full" are per CTA and signalled by a multicast commit, "tmem empty"
 // lives in the leader and collects the 16 epilogue warps of both CTAs.
-template <bool PAIR>
+// LEAN = true: the epilogue of the data-gradient launches (bf16 output only: no fp32 output, residual, statistics,
+// split-bf16 half or pixel-shuffle scatter) with those feature paths compiled out.
+template <bool PAIR, bool LEAN>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ ConvParams p) {
   constexpr int STAGES = PAIR ? PAIR_STAGES : tvae::STAGES;
@@ -241,7 +243,7 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
       const bool row_ok = pix < p.m_total;
       int col0 = nt * p.bn;   // column in the (tap, cout) / cout space
       long long opix = pix;
-      if (p.up_mode) {
+      if (!LEAN && p.up_mode) {
         const int tap = col0 / p.cout_per_tap;
         col0 -= tap * p.cout_per_tap;
         const int hw = p.up_H * p.up_W;
@@ -251,9 +253,9 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
         opix = ((long long)n * (2 * p.up_H) + (2 * h + (tap >> 1))) * (2 * p.up_W) + (2 * w + (tap & 1));
       }
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * 256u;
-      const bool do_stats = p.stats_part != nullptr;
+      const bool do_stats = !LEAN && p.stats_part != nullptr;
       float st1 = 0.f, st2 = 0.f;
-      const float* res_row = p.res ? p.res + opix * p.ld_res : nullptr;
+      const float* res_row = (!LEAN && p.res) ? p.res + opix * p.ld_res : nullptr;
 
       uint32_t r[16];
       float rs[16];
@@ -319,7 +321,7 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
               st2 = fmaf(v[j], v[j], st2);
             }
           }
-          if (p.out_f32) {
+          if (!LEAN && p.out_f32) {
             float* op = p.out_f32 + opix * p.ld_f32 + col;
             if (full && (p.wide & 1)) {
               st_global_v8(op, v, 0);
@@ -333,7 +335,7 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
                 if (col + j < p.n_valid) op[j] = v[j];
             }
           }
-          if (p.out_bf16) {
+          if (LEAN || p.out_bf16) {
             __nv_bfloat16* op = p.out_bf16 + opix * p.ld_bf16 + col;
             if (full) {
               uint32_t w8[8];
@@ -349,7 +351,7 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
               for (int j = 0; j < 16; ++j)
                 if (col + j < p.n_valid) op[j] = __float2bfloat16(v[j]);
             }
-            if (p.out_bf16_lo) {     // residual of the bf16 rounding, for split-bf16 consumers
+            if (!LEAN && p.out_bf16_lo) {     // residual of the bf16 rounding, for split-bf16 consumers
               __nv_bfloat16* ol = p.out_bf16_lo + opix * p.ld_bf16 + col;
               for (int j = 0; j < 16; ++j)
                 if (col + j < p.n_valid) ol[j] = __float2bfloat16(v[j] - __bfloat162float(__float2bfloat16(v[j])));
@@ -408,6 +410,7 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
 // at 1.64 PFLOP/s (3.01 ms) against 1.1-1.2 PFLOP/s for the single-CTA schedule, which is then limited by the
 // 96 B/clk/SM of operand traffic that the pair schedule cuts to 64 B/clk/SM.
 int g_conv_cta_pair = 1;
+int g_conv_lean_epilogue = 1;
 
 int pick_bn(int cout) {
   if (cout <= 256) return (cout + 15) / 16 * 16;
@@ -570,10 +573,21 @@ extern "C" int32_t tvae_conv_gemm(const tvae_conv_args* a, cudaStream_t stream) 
   if (p.bias) TVAE_CHECK((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0, "bias must be 16-byte aligned");
   if (p.res) TVAE_CHECK(p.ld_res % 4 == 0 && (reinterpret_cast<uintptr_t>(p.res) & 15) == 0, "residual alignment");
 
+  {
+    static bool env_read = false;            // TVAE_CONV_LEAN=0 keeps the generic epilogue (A/B measurements)
+    if (!env_read) {
+      const char* e = getenv("TVAE_CONV_LEAN");
+      if (e) g_conv_lean_epilogue = atoi(e) != 0;
+      env_read = true;
+    }
+  }
+  const bool lean = g_conv_lean_epilogue && p.out_bf16 && !p.out_f32 && !p.res && !p.stats_part && !p.out_bf16_lo &&
+                    !p.up_mode;
   if (pair) {
     static bool attr_set = false;
     if (!attr_set) {
-      TVAE_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      TVAE_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      TVAE_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
       attr_set = true;
     }
     const int total = (p.m_tiles + 1) / 2 * p.n_tiles;
@@ -588,17 +602,20 @@ extern "C" int32_t tvae_conv_gemm(const tvae_conv_args* a, cudaStream_t stream) 
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    TVAE_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<true>, maps, p));
+    if (lean) TVAE_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<true, true>, maps, p));
+    else TVAE_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<true, false>, maps, p));
   } else {
     static bool attr_set = false;
     if (!attr_set) {
-      TVAE_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      TVAE_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      TVAE_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
       attr_set = true;
     }
     const int total = p.m_tiles * p.n_tiles;
     int grid = num_sms();
     if (grid > total) grid = total;
-    conv_gemm_kernel<false><<<grid, NTHREADS, SMEM_BYTES, stream>>>(maps, p);
+    if (lean) conv_gemm_kernel<false, true><<<grid, NTHREADS, SMEM_BYTES, stream>>>(maps, p);
+    else conv_gemm_kernel<false, false><<<grid, NTHREADS, SMEM_BYTES, stream>>>(maps, p);
   }
   TVAE_CUDA(cudaGetLastError());
   return 0;
