@@ -39,6 +39,10 @@ _KERNELS_PER_CALL = {
 }
 
 
+# mirror of the library's wgrad scheduling switch (only used to count launches correctly)
+WGRAD_CTA_PAIR = [__import__("os").environ.get("TVAE_WGRAD_CTA_PAIR", "1") != "0"]
+
+
 def _ptr(t):
     return 0 if t is None else t.data_ptr()
 
@@ -261,6 +265,9 @@ def wgrad_gemm(p, Cm, q, Cn, *, kind, R, grad, accumulate=False, splits=0, flip=
     a.N, a.H, a.W = N, H, W
     a.kind, a.R, a.splits = kind, R, splits
     a.workspace = ws.data_ptr(); a.grad = grad.data_ptr(); a.accumulate = int(accumulate); a.flip = int(flip)
+    m_tiles = (Cm + 127) // 128
+    if WGRAD_CTA_PAIR[0] and m_tiles >= 3 and m_tiles % 2 == 1:
+        KERNEL_LAUNCHES[0] += 2       # the odd last M tile runs as its own GEMM + reduce launch (see tvae_wgrad_gemm)
     prof = PROFILE.get("wgrad")
     if prof is not None and prof["match"](N * H * W, Cm, Cn, kind, R):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
