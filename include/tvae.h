@@ -212,20 +212,23 @@ int32_t tvae_reparam_bwd(const float* moments, const float* dz1, const float* ep
  * Reconstruction NLL. Replaces F.l1_loss / F.mse_loss + the logvar scaling (src/model.py:656-663).
  *  x: bf16 NHWC [P][x_pitch]; xhat: fp32 NHWC [P][xh_pitch]; C valid channels; loss_type 0 = l1, 1 = l2.
  *  sums[3] (fp64) = { sum rec, sum (x - xhat)^2, unused }; written by the kernel (no pre-zeroing needed).
- *  dxhat (optional bf16 [P][dx_pitch], pad lanes zeroed) = d(rec)/d(xhat) * grad_scale, where the caller passes
+ *  dxhat (optional bf16 [P][dx_pitch]; pad lanes are never read by the consumers) = d(rec)/d(xhat) * grad_scale, where the caller passes
  *  grad_scale = exp(-logvar) / B (read from the device scalar `logvar`): dxhat = sign(xhat - x)*s or 2(xhat-x)*s.
- *  workspace: tvae_nll_workspace_bytes().
+ *  dx_colsum (optional fp32 [C], needs dxhat): column sums of dxhat over all P pixels = the bias gradient of the
+ *  last decoder conv, produced by the same pass.
+ *  workspace: tvae_nll_workspace_bytes(C).
  */
+int64_t tvae_nll_workspace_bytes(int32_t C);
+int32_t tvae_nll_fwd(const void* x_bf16, int32_t x_pitch, const float* xhat, int32_t xh_pitch, int64_t P, int32_t C,
+                     int32_t loss_type, const float* logvar, int32_t batch, void* dxhat_bf16, int32_t dx_pitch,
+                     float* dx_colsum, double* sums, double* workspace, tvae_stream_t stream);
+
 /* Per-sample reconstruction metrics (src/scripts/evaluate_reconstruction.py:23-42): out[n] = (MAE, MSE) between the
  * bf16 input rows x and the fp32 reconstruction xhat (both channels-last, [N][HW][pitch]); PSNR follows from the MSE.
  * Fixed-order reductions. workspace: tvae_recon_metrics_workspace_bytes(N). */
 int64_t tvae_recon_metrics_workspace_bytes(int32_t N);
 int32_t tvae_recon_metrics(const void* x_bf16, int32_t x_pitch, const float* xhat, int32_t xh_pitch, int32_t N,
                            int32_t HW, int32_t C, float* out, double* workspace, tvae_stream_t stream);
-int64_t tvae_nll_workspace_bytes(void);
-int32_t tvae_nll_fwd(const void* x_bf16, int32_t x_pitch, const float* xhat, int32_t xh_pitch, int64_t P, int32_t C,
-                     int32_t loss_type, const float* logvar, int32_t batch, void* dxhat_bf16, int32_t dx_pitch,
-                     double* sums, double* workspace, tvae_stream_t stream);
 
 /* Scalars of AutoencoderKL.get_loss (src/model.py:660-668) from the reductions above, on the device:
  *  out[0] = loss = nll + kl, out[1] = nll = (sums[0]*exp(-logvar) + logvar*n_elem)/B,

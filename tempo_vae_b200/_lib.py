@@ -92,8 +92,8 @@ def _load():
         "tvae_reparam_bwd": (i32, [vp, vp, vp, vp, vp, f32, i32, i32, i32, vp, vp]),
         "tvae_recon_metrics_workspace_bytes": (i64, [i32]),
         "tvae_recon_metrics": (i32, [vp, i32, vp, i32, i32, i32, i32, vp, vp, vp]),
-        "tvae_nll_workspace_bytes": (i64, []),
-        "tvae_nll_fwd": (i32, [vp, i32, vp, i32, i64, i32, i32, vp, i32, vp, i32, vp, vp, vp]),
+        "tvae_nll_workspace_bytes": (i64, [i32]),
+        "tvae_nll_fwd": (i32, [vp, i32, vp, i32, i64, i32, i32, vp, i32, vp, i32, vp, vp, vp, vp]),
         "tvae_vae_loss_finalize": (i32, [vp, vp, i32, vp, C.c_double, f32, vp, vp]),
         "tvae_l2head_loss_fwd": (i32, [vp, i32, C.POINTER(vp), i32, i32, i32, i32, vp, vp]),
         "tvae_l2head_loss_bwd": (i32, [vp, i32, C.POINTER(vp), i32, i32, i32, i32, vp, vp, f32, vp, i32, vp]),

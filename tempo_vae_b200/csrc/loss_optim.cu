@@ -165,6 +165,94 @@ __global__ void nll_fwd_kernel(const __nv_bfloat16* __restrict__ x, int x_pitch,
     ws[2 * blockIdx.x + 1] = t2;
   }
 }
+// Row-structured variant (C % 4 == 0): thread u of a block owns channel vector u (4 channels) and walks the block's
+// pixel rows, so the per-channel sums of the gradient (= the bias gradient of the conv that produced xhat) fall out of
+// the same pass: csp[block][C]. blockDim.x >= dx_pitch/4 (a multiple of 32); threads past C/4 zero the pad lanes.
+__global__ void nll_fwd_rows_kernel(const __nv_bfloat16* __restrict__ x, int x_pitch, const float* __restrict__ xh,
+                                    int xh_pitch, long long P, int C, int loss_type, const float* __restrict__ logvar,
+                                    int batch, __nv_bfloat16* __restrict__ dxh, int dx_pitch, double* __restrict__ ws,
+                                    float* __restrict__ csp) {
+  __shared__ double red[32];
+  const int U = C >> 2, u = threadIdx.x, c = u << 2;
+  const bool live = u < U;
+  const float gs = dxh ? expf(-logvar[0]) / (float)batch : 0.f;
+  const long long per = (P + gridDim.x - 1) / gridDim.x;
+  const long long r0 = blockIdx.x * per, r1 = min(r0 + per, P);
+  double a_rec = 0.0, a_sq = 0.0;
+  float cs[4] = {0.f, 0.f, 0.f, 0.f};
+  constexpr int RU = 4;      // rows in flight per thread
+  for (long long r = r0; r < r1; r += RU) {
+    float f_rec = 0.f, f_sq = 0.f;
+    const int nr = (int)min((long long)RU, r1 - r);
+    if (live) {
+      uint2 d[RU];
+      float4 h[RU];
+#pragma unroll
+      for (int k = 0; k < RU; ++k)
+        if (k < nr) {
+          d[k] = *reinterpret_cast<const uint2*>(x + (r + k) * x_pitch + c);
+          h[k] = *reinterpret_cast<const float4*>(xh + (r + k) * xh_pitch + c);
+        }
+#pragma unroll
+      for (int k = 0; k < RU; ++k)
+        if (k < nr) {
+          const float xv[4] = {bf16_bits_to_f(d[k].x & 0xffffu), bf16_bits_to_f(d[k].x >> 16),
+                               bf16_bits_to_f(d[k].y & 0xffffu), bf16_bits_to_f(d[k].y >> 16)};
+          const float hv[4] = {h[k].x, h[k].y, h[k].z, h[k].w};
+          float g[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float df = hv[j] - xv[j];
+            const float sq = df * df;
+            f_sq += sq;
+            if (loss_type == 0) {
+              f_rec += fabsf(df);
+              g[j] = (df > 0.f) ? gs : ((df < 0.f) ? -gs : 0.f);
+            } else {
+              f_rec += sq;
+              g[j] = 2.0f * df * gs;
+            }
+            cs[j] += g[j];
+          }
+          if (dxh) {
+            uint2 o;
+            o.x = pack_bf16(g[0], g[1]);
+            o.y = pack_bf16(g[2], g[3]);
+            *reinterpret_cast<uint2*>(dxh + (r + k) * dx_pitch + c) = o;
+          }
+        }
+    } else if (dxh && c + 4 <= dx_pitch) {
+      for (int k = 0; k < nr; ++k) *reinterpret_cast<uint2*>(dxh + (r + k) * dx_pitch + c) = make_uint2(0u, 0u);
+    }
+    a_rec += f_rec; a_sq += f_sq;
+  }
+  if (csp && live)
+    *reinterpret_cast<float4*>(csp + (long long)blockIdx.x * C + c) = make_float4(cs[0], cs[1], cs[2], cs[3]);
+  const double t1 = block_sum(a_rec, red);
+  const double t2 = block_sum(a_sq, red);
+  if (threadIdx.x == 0) {
+    ws[2 * blockIdx.x] = t1;
+    ws[2 * blockIdx.x + 1] = t2;
+  }
+}
+// out[c] = sum over blocks of csp[block][c], fixed order: 32 channels x 8 block lanes per CTA
+__global__ void __launch_bounds__(256)
+nll_colsum_final_kernel(const float* __restrict__ csp, int nblocks, int C, float* __restrict__ out) {
+  __shared__ float sa[8][33];
+  const int cx = threadIdx.x & 31, bl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  float a = 0.f;
+  if (c < C)
+    for (int b = bl; b < nblocks; b += 8) a += csp[(long long)b * C + c];
+  sa[bl][cx] = a;
+  __syncthreads();
+  if (bl == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int l = 0; l < 8; ++l) t += sa[l][cx];
+    out[c] = t;
+  }
+}
 __global__ void nll_final_kernel(const double* __restrict__ ws, int nblocks, double* __restrict__ sums) {
   __shared__ double red[32];
   double a = 0.0, b = 0.0;
@@ -403,24 +491,43 @@ extern "C" int32_t tvae_reparam_bwd(const float* moments, const float* dz1, cons
   return 0;
 }
 
-extern "C" int64_t tvae_nll_workspace_bytes(void) { return (int64_t)NLL_BLOCKS * 2 * sizeof(double); }
+extern "C" int64_t tvae_nll_workspace_bytes(int32_t C) {
+  return (int64_t)NLL_BLOCKS * 2 * sizeof(double) + (int64_t)NLL_BLOCKS * (C > 0 ? (C + 3) / 4 * 4 : 0) * sizeof(float);
+}
 
 extern "C" int32_t tvae_nll_fwd(const void* x, int32_t x_pitch, const float* xhat, int32_t xh_pitch, int64_t P,
                                 int32_t C, int32_t loss_type, const float* logvar, int32_t batch, void* dxhat,
-                                int32_t dx_pitch, double* sums, double* ws, cudaStream_t stream) {
+                                int32_t dx_pitch, float* dx_colsum, double* sums, double* ws, cudaStream_t stream) {
   TVAE_ENTER(x);
   TVAE_CHECK(x && xhat && sums && ws, "tvae_nll_fwd: null pointer");
   TVAE_CHECK(!dxhat || logvar, "tvae_nll_fwd: dxhat needs logvar");
+  TVAE_CHECK(!dx_colsum || dxhat, "tvae_nll_fwd: dx_colsum needs dxhat");
   TVAE_CHECK(loss_type == 0 || loss_type == 1, "tvae_nll_fwd: loss_type must be 0 (l1) or 1 (l2)");
   const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x);
   __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(dxhat);
   const bool vec = (C % 4 == 0) && (x_pitch % 4 == 0) && (xh_pitch % 4 == 0) && (!dxhat || dx_pitch % 4 == 0);
-  if (vec)
-    nll_fwd_kernel<4><<<NLL_BLOCKS, 256, 0, stream>>>(xp, x_pitch, xhat, xh_pitch, P, C, loss_type, logvar, batch, dp,
-                                                     dx_pitch, ws);
-  else
-    nll_fwd_kernel<1><<<NLL_BLOCKS, 256, 0, stream>>>(xp, x_pitch, xhat, xh_pitch, P, C, loss_type, logvar, batch, dp,
-                                                     dx_pitch, ws);
+  float* csp = reinterpret_cast<float*>(ws + 2 * NLL_BLOCKS);
+  const int threads = ((dxhat ? dx_pitch : C) / 4 + 31) / 32 * 32;
+  if (vec && threads <= 1024 && P >= NLL_BLOCKS && (reinterpret_cast<uintptr_t>(xhat) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(x) & 7) == 0 && (reinterpret_cast<uintptr_t>(dxhat) & 7) == 0) {
+    nll_fwd_rows_kernel<<<NLL_BLOCKS, threads, 0, stream>>>(xp, x_pitch, xhat, xh_pitch, P, C, loss_type, logvar, batch,
+                                                           dp, dx_pitch, ws, dx_colsum ? csp : nullptr);
+    TVAE_CUDA(cudaGetLastError());
+    if (dx_colsum) nll_colsum_final_kernel<<<(C + 31) / 32, 256, 0, stream>>>(csp, NLL_BLOCKS, C, dx_colsum);
+  } else {
+    if (vec)
+      nll_fwd_kernel<4><<<NLL_BLOCKS, 256, 0, stream>>>(xp, x_pitch, xhat, xh_pitch, P, C, loss_type, logvar, batch, dp,
+                                                       dx_pitch, ws);
+    else
+      nll_fwd_kernel<1><<<NLL_BLOCKS, 256, 0, stream>>>(xp, x_pitch, xhat, xh_pitch, P, C, loss_type, logvar, batch, dp,
+                                                       dx_pitch, ws);
+    TVAE_CUDA(cudaGetLastError());
+    if (dx_colsum) {   // generic shapes: a separate pass over the gradient just written (workspace: colsum partials)
+      TVAE_CHECK(tvae_colsum_workspace_bytes(P, C) <= (int64_t)NLL_BLOCKS * ((C + 3) / 4 * 4) * 4,
+                 "tvae_nll_fwd: workspace too small for the column sums");
+      if (tvae_colsum_bf16(dxhat, P, C, dx_pitch, dx_colsum, csp, stream) != 0) return -1;
+    }
+  }
   TVAE_CUDA(cudaGetLastError());
   nll_final_kernel<<<1, 256, 0, stream>>>(ws, NLL_BLOCKS, sums);
   TVAE_CUDA(cudaGetLastError());

@@ -480,18 +480,23 @@ def reparam_bwd(moments, Z, dz1, eps1, dz2, eps2, kl_scale):
 
 
 def nll_fwd(x_bf16, xhat, Cc, loss_type, logvar, batch, want_grad):
-    """x_bf16 [N,H,W,xp] bf16; xhat [N,H,W,hp] fp32. Returns (sums fp64[3], dxhat bf16 or None)."""
+    """x_bf16 [N,H,W,xp] bf16; xhat [N,H,W,hp] fp32. Returns (sums fp64[3], dxhat bf16 or None); dxhat carries its
+    column sums (the bias gradient of the conv that produced xhat) as `dxhat.tvae_colsum`."""
     x_bf16 = hi_of(x_bf16)
     P = x_bf16.numel() // x_bf16.shape[-1]          # pixels (the last dim may be a channel-slice view of pitched rows)
     dev = xhat.device
     sums = torch.empty((3,), dtype=torch.float64, device=dev)
-    ws = _workspace(lib.tvae_nll_workspace_bytes(), dev, "nll")
-    dx = None
+    ws = _workspace(lib.tvae_nll_workspace_bytes(Cc), dev, "nll")
+    dx = cs = None
     if want_grad:
         dx = torch.empty(x_bf16.shape[:-1] + (round_up(Cc, 8),), dtype=torch.bfloat16, device=dev)
+        cs = torch.empty((Cc,), dtype=torch.float32, device=dev)
     check(lib.tvae_nll_fwd(x_bf16.data_ptr(), pitch_of(x_bf16), xhat.data_ptr(), pitch_of(xhat), P, Cc, loss_type,
-                           _ptr(logvar), batch, _ptr(dx), dx.shape[-1] if dx is not None else 0, sums.data_ptr(),
-                           ws.data_ptr(), _stream()), "tvae_nll_fwd")
+                           _ptr(logvar), batch, _ptr(dx), dx.shape[-1] if dx is not None else 0, _ptr(cs),
+                           sums.data_ptr(), ws.data_ptr(), _stream()), "tvae_nll_fwd")
+    if dx is not None:
+        dx.tvae_colsum = cs
+        KERNEL_LAUNCHES[0] += 1
     return sums, dx
 
 

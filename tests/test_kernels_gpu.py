@@ -404,10 +404,14 @@ def test_reparam_kl_fwd_bwd():
     assert abs(e1.mean().item()) < 0.02 and abs(e1.std().item() - 1.0) < 0.02
 
 
+@pytest.mark.parametrize("HW,C", [(16, 1028), (32, 1028), (32, 20), (40, 7)])
 @pytest.mark.parametrize("loss_type", [0, 1])
-def test_nll(loss_type):
+def test_nll(loss_type, HW, C):
+    """Small pixel counts / odd channel counts take the generic kernels, [2,32,32,1028] the row-structured kernel that
+    also produces the column sums of the gradient (bias gradient of the last decoder conv)."""
     o = ops()
-    N, H, W, C = 2, 16, 16, 1028
+    N, H, W = 2, HW, HW
+    pitch = o.round_up(C, 8)
     g = torch.Generator(device="cuda").manual_seed(10)
     x = bf16_round(torch.randn((N, C, H, W), device="cuda", generator=g))
     xh = torch.randn((N, C, H, W), device="cuda", generator=g).requires_grad_(True)
@@ -415,13 +419,22 @@ def test_nll(loss_type):
     rec = (x - xh).abs() if loss_type == 0 else (x - xh) ** 2
     nll = torch.sum(rec / torch.exp(logvar) + logvar) / N
     nll.backward()
-    xb = nhwc_bf16(x, 1032)
+    xb = nhwc_bf16(x, pitch)
     xhn = xh.detach().permute(0, 2, 3, 1).contiguous()
     sums, dx = o.nll_fwd(xb, xhn, C, loss_type, logvar.detach(), N, True)
     torch.cuda.synchronize()
     assert abs(sums[0].item() - rec.sum().item()) / rec.sum().item() < 1e-6
     assert abs(sums[1].item() - ((x - xh) ** 2).sum().item()) / ((x - xh) ** 2).sum().item() < 1e-6
     assert rel_err(dx[..., :C].float().permute(0, 3, 1, 2), xh.grad) < 1e-2
+    assert dx.shape[-1] == pitch
+    if C % 4 == 0 and N * H * W >= 148 * 8:          # row-structured kernel: pad lanes are zeroed as well
+        assert (dx[..., C:] == 0).all()
+    ref_cs = xh.grad.double().sum(dim=(0, 2, 3))
+    scale = xh.grad.double().abs().sum(dim=(0, 2, 3)).max()
+    assert (dx.tvae_colsum.double() - ref_cs).abs().max() <= 4e-3 * scale
+    sums2, none = o.nll_fwd(xb, xhn, C, loss_type, logvar.detach(), N, False)       # forward only (validation)
+    torch.cuda.synchronize()
+    assert none is None and torch.equal(sums2[:2], sums[:2])
 
 
 def test_l2head_loss():
