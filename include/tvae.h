@@ -109,6 +109,18 @@ int32_t tvae_wgrad_splits(int32_t Cm, int32_t Cn, int32_t ntaps, int64_t pixels)
 /* out[(tr*Crow + cr)][tk*c_pad + c] = bf16(w[cr*s_row + c*s_col + (tr+tk)*s_tap]), zero for c in [C, c_pad).
  * One of TR, TK is 1. Row pitch of `out` is TK*c_pad. out_lo (optional, same layout) = bf16(w - out): the low-order
  * half for the split-bf16 "fp32 mode" (every *_lo argument below has the same meaning; NULL = not produced). */
+/* All packs that went stale in an optimiser step, in ONE launch. `descs` (device memory) holds one descriptor per pack
+ * with the arguments of tvae_pack_weight; block_start (device, n + 1 entries) is the exclusive prefix sum of
+ * ceil(elements_i / tvae_pack_chunk_elems()) and total_blocks its last entry. */
+typedef struct {
+  const float* w;
+  void* out_bf16;
+  int32_t Crow, TR, TK, C, c_pad, reserved;
+  int64_t s_row, s_col, s_tap;
+} tvae_pack_desc;
+int32_t tvae_pack_chunk_elems(void);
+int32_t tvae_pack_weights_batched(const tvae_pack_desc* descs, const int64_t* block_start, int32_t n,
+                                  int64_t total_blocks, tvae_stream_t stream);
 int32_t tvae_pack_weight(const float* w, void* out_bf16, int32_t Crow, int32_t TR, int32_t TK, int32_t C,
                          int32_t c_pad, int64_t s_row, int64_t s_col, int64_t s_tap, void* out_lo,
                          tvae_stream_t stream);

@@ -70,6 +70,8 @@ def _load():
         "tvae_wgrad_set_cta_pair": (i32, [i32]),
         "tvae_wgrad_workspace_bytes": (i64, [i32, i32, i32, i32]),
         "tvae_wgrad_splits": (i32, [i32, i32, i32, i64]),
+        "tvae_pack_chunk_elems": (i32, []),
+        "tvae_pack_weights_batched": (i32, [vp, vp, i32, i64, vp]),
         "tvae_pack_weight": (i32, [vp, vp, i32, i32, i32, i32, i32, i64, i64, i64, vp, vp]),
         "tvae_nchw_f32_to_nhwc_bf16": (i32, [vp, vp, i32, i32, i32, i32, vp, vp]),
         "tvae_normalize_radiance": (i32, [vp, vp, vp, i64, i32, f32, f32, f32, vp, vp, i32, vp]),

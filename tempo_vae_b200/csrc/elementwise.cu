@@ -36,6 +36,38 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* _
   }
 }
 
+// Every stale pack of a train step in ONE launch: work block wb (PACK_CHUNK elements) belongs to descriptor d with
+// block_start[d] <= wb < block_start[d + 1] (binary search), then the same element mapping as above.
+constexpr int PACK_CHUNK = 2048;
+__global__ void __launch_bounds__(256)
+pack_weights_batched_kernel(const tvae_pack_desc* __restrict__ descs, const long long* __restrict__ block_start, int n,
+                            long long total_blocks) {
+  for (long long wb = blockIdx.x; wb < total_blocks; wb += gridDim.x) {
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (block_start[mid] <= wb) lo = mid; else hi = mid - 1;
+    }
+    const tvae_pack_desc d = descs[lo];
+    const long long kp = (long long)d.TK * d.c_pad;
+    const long long total = (long long)d.TR * d.Crow * kp;
+    const long long e0 = (wb - block_start[lo]) * PACK_CHUNK;
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(d.out_bf16);
+#pragma unroll 2
+    for (int k = threadIdx.x; k < PACK_CHUNK; k += 256) {
+      const long long i = e0 + k;
+      if (i >= total) break;
+      const long long row = i / kp;
+      const int kk = (int)(i - row * kp);
+      const int tk = kk / d.c_pad, c = kk - tk * d.c_pad;
+      const int tr = (int)(row / d.Crow), cr = (int)(row - (long long)tr * d.Crow);
+      float v = 0.f;
+      if (c < d.C) v = d.w[cr * d.s_row + c * d.s_col + (tr + tk) * d.s_tap];
+      out[i] = __float2bfloat16(v);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- transposes
 // NCHW fp32 -> NHWC bf16 (pad lanes [C, pitch) zeroed). Tile: 64 channels x 64 pixels.
 __global__ void nchw_to_nhwc_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
@@ -528,6 +560,21 @@ extern "C" int32_t tvae_pack_weight(const float* w, void* out, int32_t Crow, int
   pack_weight_kernel<<<ew_grid(total), EW_THREADS, 0, stream>>>(w, reinterpret_cast<__nv_bfloat16*>(out),
                                                                reinterpret_cast<__nv_bfloat16*>(out_lo), Crow, TR, TK, C,
                                                                c_pad, s_row, s_col, s_tap);
+  TVAE_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int32_t tvae_pack_chunk_elems(void) { return PACK_CHUNK; }
+
+extern "C" int32_t tvae_pack_weights_batched(const tvae_pack_desc* descs_device, const int64_t* block_start_device,
+                                             int32_t n, int64_t total_blocks, cudaStream_t stream) {
+  TVAE_ENTER(descs_device);
+  TVAE_CHECK(descs_device && block_start_device && n > 0 && total_blocks > 0, "tvae_pack_weights_batched: bad arguments");
+  long long grid = total_blocks;
+  if (grid > 148 * 16) grid = 148 * 16;
+  pack_weights_batched_kernel<<<(int)grid, 256, 0, stream>>>(descs_device,
+                                                            reinterpret_cast<const long long*>(block_start_device), n,
+                                                            total_blocks);
   TVAE_CUDA(cudaGetLastError());
   return 0;
 }

@@ -51,9 +51,41 @@ class _Engine:
         # power-capped, so co-scheduling does not buy the time it would on an unconstrained part. Off by default.
         self.wgrad_overlap = os.environ.get("TVAE_WGRAD_OVERLAP", "0") == "1"
         self._side, self._main, self._side_busy = {}, {}, set()
+        # every weight pack that an optimiser step made stale is rebuilt by ONE launch (TVAE_BATCHED_PACKING=0: one
+        # launch per pack, on first use)
+        self.batched_packing = os.environ.get("TVAE_BATCHED_PACKING", "1") != "0"
+        self._packs = []
 
     def params_changed(self):
         self.param_epoch += 1
+
+    def register_pack(self, module, mode, ent):
+        import weakref
+        self._packs.append((weakref.ref(module), mode, ent))
+
+    def repack_stale(self, device):
+        """Rebuild, in ONE kernel launch, every registered bf16 weight pack on `device` whose parameter changed since
+        it was packed (after an optimiser step: all of them -- ~80 launches become one)."""
+        items, keys = [], []
+        alive = []
+        for ref, mode, ent in self._packs:
+            mod = ref()
+            if mod is None or mod.__dict__.get("_packs", {}).get(mode) is not ent:
+                continue
+            alive.append((ref, mode, ent))
+            w = mod.weight
+            if w.device != device or ent.data.device != device or not w.is_contiguous():
+                continue
+            key = (w.data_ptr(), w._version, self.param_epoch, False)
+            if ent.version != key:
+                items.append((w.detach(), mode, ent))
+                keys.append((ent, key))
+        self._packs = alive
+        if len(items) < 2:
+            return
+        ops.pack_weights_batched(items)
+        for ent, key in keys:
+            ent.version = key
 
     def side_stream(self, device):
         """The weight-gradient stream of `device`, made to wait for everything enqueued so far on the current one."""
@@ -150,8 +182,12 @@ class _PackedMixin:
         if ent is None or ent.data.device != w.device:
             ent = ops.pack_weight(w, mode)
             packs[mode] = ent
+            ENGINE.register_pack(self, mode, ent)
         elif ent.version != key:
-            ops.pack_weight(w, mode, out=ent)
+            if ENGINE.batched_packing and not ops.SPLIT_BF16[0]:
+                ENGINE.repack_stale(w.device)          # one launch for every pack the optimiser step invalidated
+            if ent.version != key:
+                ops.pack_weight(w, mode, out=ent)
         ent.version = key
         return ent
 

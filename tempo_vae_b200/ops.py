@@ -31,7 +31,7 @@ KERNEL_LAUNCHES = [0]   # kernels of libtvae_b200.so enqueued through this modul
 
 # kernels launched by one call of each C-ABI entry point
 _KERNELS_PER_CALL = {
-    "tvae_pack_weight": 1, "tvae_conv_gemm": 1, "tvae_wgrad_gemm": 2, "tvae_nchw_f32_to_nhwc_bf16": 1,
+    "tvae_pack_weight": 1, "tvae_pack_weights_batched": 1, "tvae_conv_gemm": 1, "tvae_wgrad_gemm": 2, "tvae_nchw_f32_to_nhwc_bf16": 1,
     "tvae_nhwc_f32_to_nchw_f32": 1, "tvae_nhwc_f32_to_nhwc_bf16": 1, "tvae_normalize_radiance": 1, "tvae_recon_metrics": 2, "tvae_nhwc_bf16_to_nchw_f32": 1, "tvae_f32_to_bf16": 1, "tvae_gn_stats": 1,
     "tvae_gn_act_fwd": 1, "tvae_gn_stats_finalize": 1, "tvae_gn_act_bwd": 4, "tvae_colsum_bf16": 2, "tvae_attn_fwd": 1, "tvae_attn_bwd": 2, "tvae_attn_fwd_tc": 1, "tvae_attn_bwd_tc": 2,
     "tvae_reparam_fwd": 1, "tvae_reparam_bwd": 1, "tvae_nll_fwd": 2, "tvae_vae_loss_finalize": 1,
@@ -154,6 +154,43 @@ def pack_weight(w, mode, out=None):
                                g["s_row"], g["s_col"], g["s_tap"], _ptr(out.lo) if SPLIT_BF16[0] else 0, _stream()),
           "tvae_pack_weight")
     return out
+
+
+class PackDesc(C.Structure):      # tvae_pack_desc
+    _fields_ = [("w", C.c_void_p), ("out_bf16", C.c_void_p), ("Crow", C.c_int32), ("TR", C.c_int32), ("TK", C.c_int32),
+                ("C", C.c_int32), ("c_pad", C.c_int32), ("reserved", C.c_int32), ("s_row", C.c_int64),
+                ("s_col", C.c_int64), ("s_tap", C.c_int64)]
+
+
+_pack_tables = {}      # signature of (weight ptr, pack ptr, mode) triples -> (descs tensor, block_start tensor, n, total)
+
+
+def pack_weights_batched(items):
+    """items: list of (weight parameter, mode, PackedWeight). Rebuilds every pack with ONE kernel launch
+    (tvae_pack_weights_batched). The descriptor table lives on the device and is reused while the pointers stay the
+    same (they do: parameters sit in FusedAdamW's flat buffer, packs are persistent)."""
+    dev = items[0][0].device
+    sig = tuple((w.data_ptr(), ent.data.data_ptr(), mode) for w, mode, ent in items)
+    tab = _pack_tables.get(dev)
+    if tab is None or tab[0] != sig:
+        chunk = lib.tvae_pack_chunk_elems()
+        descs = (PackDesc * len(items))()
+        starts = [0]
+        for i, (w, mode, ent) in enumerate(items):
+            g = pack_geometry(tuple(w.shape), mode)
+            assert w.is_contiguous() and w.dtype == torch.float32
+            d = descs[i]
+            d.w, d.out_bf16 = w.data_ptr(), ent.data.data_ptr()
+            d.Crow, d.TR, d.TK, d.C, d.c_pad = g["Crow"], g["TR"], g["TK"], g["C"], ent.c_pad
+            d.s_row, d.s_col, d.s_tap = g["s_row"], g["s_col"], g["s_tap"]
+            total = g["TR"] * g["Crow"] * g["TK"] * ent.c_pad
+            starts.append(starts[-1] + (total + chunk - 1) // chunk)
+        raw = torch.frombuffer(bytearray(bytes(descs)), dtype=torch.uint8).to(dev)
+        bs = torch.tensor(starts, dtype=torch.int64).to(dev)
+        tab = _pack_tables[dev] = (sig, raw, bs, len(items), starts[-1])
+    _, raw, bs, n, total_blocks = tab
+    check(lib.tvae_pack_weights_batched(raw.data_ptr(), bs.data_ptr(), n, total_blocks, _stream()),
+          "tvae_pack_weights_batched")
 
 
 # ----------------------------------------------------------------------------------------------- conv GEMM

@@ -673,3 +673,24 @@ def test_wgrad_cta_pair_is_bit_identical_to_single_cta(Cin, Cout, splits):
     finally:
         lib.tvae_wgrad_set_cta_pair(prev)
     assert torch.equal(outs[0], outs[1])
+
+
+def test_batched_weight_packing_matches_single_packs():
+    """tvae_pack_weights_batched (one launch for all packs of a step) against tvae_pack_weight, every pack mode."""
+    o = ops()
+    g = torch.Generator(device="cuda").manual_seed(29)
+    specs = [((512, 1028, 3, 3), "fwd"), ((512, 1028, 3, 3), "dgrad"), ((64, 128, 1, 1), "fwd"), ((48, 20, 3, 3), "dgrad"),
+             ((256, 256, 2, 2), "fwd"), ((256, 256, 2, 2), "down_dgrad"), ((128, 256, 2, 2), "up_fwd"),
+             ((128, 256, 2, 2), "up_dgrad"), ((4, 512, 1, 1), "fwd")]
+    items, refs = [], []
+    for shape, mode in specs:
+        w = torch.randn(shape, device="cuda", generator=g)
+        ref = o.pack_weight(w, mode)
+        ent = o.pack_weight(torch.zeros_like(w), mode)        # same geometry, different content
+        items.append((w, mode, ent))
+        refs.append(ref)
+    o.pack_weights_batched(items)
+    o.pack_weights_batched(items)                              # second call reuses the cached descriptor table
+    torch.cuda.synchronize()
+    for (w, mode, ent), ref in zip(items, refs):
+        assert torch.equal(ent.data, ref.data), (tuple(w.shape), mode)
