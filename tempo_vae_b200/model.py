@@ -17,10 +17,8 @@ torch.autograd.Function nodes expose it to autograd: the whole get_loss (the tra
 decode. Weight gradients are written straight into `param.grad` (a view of the optimiser's flat gradient buffer
 when FusedAdamW owns the parameter).
 """
-import math
 import os
 
-import numpy as np
 import torch
 import torch.nn as nn
 

@@ -5,7 +5,7 @@ libtvae_b200.so on torch's current CUDA stream. Activations are NHWC tensors `[N
 fp32 residual stream); `C` (the number of valid channels, <= pitch) travels next to them.
 """
 import ctypes as C
-import math
+import os
 
 import torch
 
@@ -40,7 +40,7 @@ _KERNELS_PER_CALL = {
 
 
 # mirror of the library's wgrad scheduling switch (only used to count launches correctly)
-WGRAD_CTA_PAIR = [__import__("os").environ.get("TVAE_WGRAD_CTA_PAIR", "1") != "0"]
+WGRAD_CTA_PAIR = [os.environ.get("TVAE_WGRAD_CTA_PAIR", "1") != "0"]
 
 
 def _ptr(t):
