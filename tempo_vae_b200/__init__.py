@@ -20,7 +20,7 @@ from .model_with_l2 import L2PredictionHead, VAEWithL2Supervision  # noqa: F401
 from .optim import FusedAdamW  # noqa: F401
 from .tempo_data import (DevicePrefetcher, DeviceTileCache, RandomBuffer, TEMPODataLoader, TEMPODataset,  # noqa: F401
                          load_normalization_stats)
-from .tempo_data_with_l2 import TEMPODataLoaderWithL2, TEMPODatasetWithL2  # noqa: F401
+from .tempo_data_with_l2 import DeviceTileCacheWithL2, TEMPODataLoaderWithL2, TEMPODatasetWithL2  # noqa: F401
 from .train_utils import L2SupervisedTrainer, Trainer, get_device, get_sqrt_schedule, seed_all  # noqa: F401
 
 __version__ = "0.1.0"

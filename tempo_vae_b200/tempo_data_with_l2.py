@@ -88,3 +88,64 @@ class TEMPODataLoaderWithL2:
         dataset = TEMPODatasetWithL2(data_dir=data_dir, split=split, min_buffer_size=min_buffer_size, verbose=verbose)
         return DataLoader(dataset, batch_size=batch_size, num_workers=num_workers, pin_memory=True,
                           persistent_workers=(num_workers > 0))
+
+
+class DeviceTileCacheWithL2:
+    """`tempo_data.DeviceTileCache` for the L2-supervised variant: the spectral tiles resident in HBM as channels-last
+    bf16, the four product targets next to them as fp32 `[n, 64, 64]` (NaN = invalid pixel, kept as is). Batches are the
+    dicts `L2SupervisedTrainer.train_step` / `VAEWithL2Supervision.compute_loss` take:
+    `{'spectral': [B, C, H, W] bf16 channels-last view, 'NO2': [B, H, W], ...}`.
+
+        cache = DeviceTileCacheWithL2.from_dir(data_dir, 'train', device)
+        for batch in cache.batches(256, seed=0, rank=rank, world=world):
+            trainer.train_step_device(batch)
+    """
+
+    def __init__(self, spectral_cache, targets: Dict[str, torch.Tensor]):
+        self.spectral = spectral_cache
+        self.targets = targets
+
+    def __len__(self):
+        return len(self.spectral)
+
+    @classmethod
+    def from_dir(cls, data_dir: str, split: str, device, max_tiles=None):
+        from .tempo_data import DeviceTileCache
+        root = Path(data_dir) / split
+        files = sorted(root.glob("*.pt"))
+        if not files:
+            raise ValueError(f"FATAL: No .pt files found in {root}")
+        spectral = DeviceTileCache.from_dir(str(root), device, max_tiles=max_tiles)
+        targets = {}
+        for product in L2_PRODUCTS:
+            d = root / f'l2_{product}'
+            if not d.exists():
+                raise FileNotFoundError(f"FATAL: L2 directory not found: {d}")
+            parts = []
+            for f in files:
+                p = d / f.name
+                if not p.exists():
+                    raise FileNotFoundError(f"FATAL: L2 file not found: {p}")
+                t = torch.load(p, weights_only=True)
+                parts.append(t.unsqueeze(0) if t.dim() == 2 else t)
+            tg = torch.cat(parts, 0)[:len(spectral)].to(device, dtype=torch.float32)
+            if tg.shape[0] != len(spectral):
+                raise ValueError(f"{product}: {tg.shape[0]} targets for {len(spectral)} spectral tiles")
+            targets[product] = tg.contiguous()
+        return cls(spectral, targets)
+
+    def batches(self, batch_size: int, seed: int = 0, epochs=None, rank: int = 0, world: int = 1):
+        sp = self.spectral
+        if sp.n < batch_size * world:
+            raise ValueError(f"{sp.n} cached tiles cannot fill a batch of {batch_size} on {world} ranks")
+        g = torch.Generator().manual_seed(seed)
+        epoch = 0
+        while epochs is None or epoch < epochs:
+            perm = torch.randperm(sp.n, generator=g)[rank::world].to(sp.device)
+            for i in range(0, perm.numel() - batch_size + 1, batch_size):
+                idx = perm[i:i + batch_size]
+                batch = {'spectral': torch.index_select(sp.data, 0, idx)[..., :sp.C].permute(0, 3, 1, 2)}
+                for product, tg in self.targets.items():
+                    batch[product] = torch.index_select(tg, 0, idx)
+                yield batch
+            epoch += 1

@@ -131,7 +131,10 @@ class Trainer:
     # ------------------------------------------------------------------------------------------------ one step
     def _loss_and_metrics(self, batch):
         """(loss, metrics-with-device-scalars) for one batch; overridden by the L2 trainer."""
-        batch = batch.to(self.device, dtype=torch.float32, non_blocking=True)
+        if batch.dtype != torch.bfloat16:      # bf16 batches (DeviceTileCache views) are consumed in place by the engine
+            batch = batch.to(self.device, dtype=torch.float32, non_blocking=True)
+        elif batch.device != self.device:
+            batch = batch.to(self.device, non_blocking=True)
         if self.step == 0 and torch.is_grad_enabled():
             print(f"Batch stats - min: {batch.min():.3f}, max: {batch.max():.3f}, "
                   f"mean: {batch.mean():.3f}, std: {batch.std():.3f}")

@@ -601,3 +601,55 @@ def test_evaluate_reconstruction_metrics_vs_oracle():
     assert (got["psnr"].cpu() - ref_psnr).abs().max() < 0.1          # dB
     mode = t.evaluate_reconstruction(model, x.cuda(), sample_posterior=False)
     assert torch.isfinite(mode["psnr"]).all()
+
+
+def test_l2_device_tile_cache_batches_match_host_batches(tmp_path):
+    """DeviceTileCacheWithL2: dict batches gathered on the device give the same loss, bit for bit, as the same samples
+    fed the reference way (fp32 NCHW spectral tensor + [B, H, W] targets with NaN holes)."""
+    import tempo_vae_b200 as t
+    fx = gold("tiny_l2.pt")
+    cfg = fx["cfg"]
+    C, H, W = cfg["shape"]
+    n = 6
+    tiles = orc.structured_batch(n, cfg, seed=41).permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).float()
+    gen = torch.Generator().manual_seed(43)
+    split = tmp_path / "train"
+    split.mkdir()
+    torch.save(tiles[:4].clone(), split / "g0.pt")
+    torch.save(tiles[4:].clone(), split / "g1.pt")
+    targets = {}
+    for p in ("NO2", "O3TOT", "HCHO", "CLDO4"):
+        tg = torch.randn((n, H, W), generator=gen)
+        tg[torch.rand((n, H, W), generator=gen) < 0.15] = float("nan")
+        targets[p] = tg
+        (split / f"l2_{p}").mkdir()
+        torch.save(tg[:4].clone(), split / f"l2_{p}" / "g0.pt")
+        torch.save(tg[4:].clone(), split / f"l2_{p}" / "g1.pt")
+    cache = t.DeviceTileCacheWithL2.from_dir(str(tmp_path), "train", torch.device("cuda"))
+    assert len(cache) == n
+    batch = next(cache.batches(4, seed=3, epochs=1))
+    assert batch["spectral"].dtype == torch.bfloat16 and batch["spectral"].shape == (4, C, H, W)
+    # identify which tiles were drawn, rebuild the same batch the reference way
+    flat = tiles.reshape(n, -1)
+    got = batch["spectral"].float().permute(0, 2, 3, 1).reshape(4, -1).cpu()
+    idx = [int(((flat - g[None]).abs().sum(1) == 0).nonzero()[0]) for g in got]
+    ref_batch = {"spectral": tiles[idx].permute(0, 3, 1, 2).contiguous().cuda()}
+    for p, tg in targets.items():
+        ref_batch[p] = tg[idx].cuda()
+        assert torch.equal(torch.nan_to_num(batch[p].cpu(), nan=-7.0), torch.nan_to_num(tg[idx], nan=-7.0))
+    base = build(cfg)
+    model = t.VAEWithL2Supervision(base.vae, latent_channels=cfg["embed_dim"], mlp_hidden=fx["mlp_hidden"]).cuda()
+    model.load_state_dict(fx["state_dict"])
+    eps = torch.randn((4, cfg["embed_dim"], H // 4, W // 4), generator=gen).cuda()
+    eps2 = torch.randn((4, cfg["embed_dim"], H // 4, W // 4), generator=gen).cuda()
+    la, ma = model.compute_loss(batch, l2_weights=fx["weights"], eps=eps, eps2=eps2)
+    lb, mb = model.compute_loss(ref_batch, l2_weights=fx["weights"], eps=eps, eps2=eps2)
+    assert torch.equal(la.detach(), lb.detach()) and ma.keys() == mb.keys()
+    for k in ma:
+        assert ma[k] == mb[k] or (ma[k] != ma[k] and mb[k] != mb[k]), k
+    # the trainer consumes the cached batch without converting it
+    opt = t.FusedAdamW(model.parameters(), lr=1e-4, betas=(0.9, 0.95), weight_decay=0.05)
+    tr = t.L2SupervisedTrainer(model, opt, torch.device("cuda"), str(tmp_path / "out"), kl_weight=cfg["kl_weight"],
+                               l2_weights=fx["weights"])
+    m = tr.train_step(batch)
+    assert all(torch.isfinite(torch.tensor(float(v))) or k.endswith("_loss") for k, v in m.items())
