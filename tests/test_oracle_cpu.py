@@ -140,8 +140,9 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_header_order():
     from tempo_vae_b200._lib import ConvArgs, WgradArgs
+    from tempo_vae_b200.ops import PackDesc
     header = open(os.path.join(ROOT, "include", "tvae.h")).read()
-    for struct, cls in (("tvae_conv_args", ConvArgs), ("tvae_wgrad_args", WgradArgs)):
+    for struct, cls in (("tvae_conv_args", ConvArgs), ("tvae_wgrad_args", WgradArgs), ("tvae_pack_desc", PackDesc)):
         body = header[:header.index("} " + struct)]
         body = body[body.rindex("typedef struct {"):]
         body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
@@ -150,7 +151,7 @@ def test_struct_layouts_match_header_order():
             decl = decl.replace("typedef struct {", "").strip()
             if not decl:
                 continue
-            decl = re.sub(r"^(const\s+)?(void|float|int32_t)\s*\*?", "", decl).strip()
+            decl = re.sub(r"^(const\s+)?(void|float|int32_t|int64_t)\s*\*?", "", decl).strip()
             names += [n.strip().lstrip("*") for n in decl.split(",")]
         assert names == [f[0] for f in cls._fields_], struct
 
@@ -274,3 +275,24 @@ def test_adamw_live_ranges():
     assert opt._live_ranges([]) == [(0, 160)]
     assert opt._live_ranges([P(16, 30)]) == [(0, 16), (32, 160)]
     assert opt._live_ranges([P(0, 16), P(144, 150)]) == [(16, 144)]
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the oracle on the host cores) prints ONE JSON line with the contract's keys; a
+    non-zero rank of a torchrun launch exits 0 without work."""
+    import json
+    import subprocess
+    import sys
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                        "--warmup", "1"], capture_output=True, text=True, env=env, timeout=120)
+    assert r.returncode == 0 and r.stdout.strip() == ""
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "samples/s" and line["higher_is_better"] is True
+    assert line["metric"] == "train samples/sec (fwd+bwd+AdamW)" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
