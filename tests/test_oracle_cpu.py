@@ -296,3 +296,27 @@ def test_bench_reference_arm_contract():
     assert line["metric"] == "train samples/sec (fwd+bwd+AdamW)" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"] == {"value": line["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_header_is_plain_c_and_host_geometry_helpers():
+    """include/tvae.h must be consumable by a C compiler (it is the drop-in boundary: plain pointers and sizes), and
+    the Python mirrors of the kernels' geometry rules agree with what the C side documents."""
+    import shutil
+    import subprocess
+    hdr = os.path.join(ROOT, "include", "tvae.h")
+    if shutil.which("gcc"):
+        r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", hdr],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    code = re.sub(r"/\*.*?\*/", "", open(hdr).read(), flags=re.S)      # comments may mention the reference's PyTorch
+    assert "torch" not in code.lower() and "at::" not in code and "Tensor" not in code   # no framework types
+    from tempo_vae_b200 import ops
+    # vectorised GroupNorm kernels: whole 8-channel octets per group, C/8 dividing 256
+    assert ops.gn_fast_ok(512, 8) and ops.gn_fast_ok(256, 8) and ops.gn_fast_ok(128, 8)
+    assert not ops.gn_fast_ok(32, 8) and not ops.gn_fast_ok(1028, 4) and not ops.gn_fast_ok(128, 0)
+    # fused statistics: group size multiple of 16 dividing the N tile, >= 128 output pixels per image
+    assert ops.fused_stats_ok(2, 64, 64, 512, 8, 0, 64, 64) and ops.fused_stats_ok(2, 16, 16, 128, 8, 0, 16, 16)
+    assert not ops.fused_stats_ok(2, 8, 8, 128, 8, 0, 8, 8)               # 64 pixels per image
+    assert not ops.fused_stats_ok(2, 64, 64, 64, 8, 0, 64, 64)            # groups of 8 channels
+    assert ops.fused_stats_ok(2, 32, 32, 256, 8, 2, 16, 16) is False      # transposed conv: the INPUT grid counts
+    assert ops.round_up(1028, 8) == 1032 and ops.round_up(1028, 64) == 1088
