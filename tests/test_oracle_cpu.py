@@ -318,5 +318,6 @@ def test_header_is_plain_c_and_host_geometry_helpers():
     assert ops.fused_stats_ok(2, 64, 64, 512, 8, 0, 64, 64) and ops.fused_stats_ok(2, 16, 16, 128, 8, 0, 16, 16)
     assert not ops.fused_stats_ok(2, 8, 8, 128, 8, 0, 8, 8)               # 64 pixels per image
     assert not ops.fused_stats_ok(2, 64, 64, 64, 8, 0, 64, 64)            # groups of 8 channels
-    assert ops.fused_stats_ok(2, 32, 32, 256, 8, 2, 16, 16) is False      # transposed conv: the INPUT grid counts
+    assert ops.fused_stats_ok(2, 32, 32, 256, 8, 2, 16, 16)               # transposed conv: the INPUT grid counts ...
+    assert not ops.fused_stats_ok(2, 16, 16, 256, 8, 2, 8, 8)             # ... 64 input pixels per image: no
     assert ops.round_up(1028, 8) == 1032 and ops.round_up(1028, 64) == 1088
