@@ -2,19 +2,28 @@
 """bench.py — headline benchmark of the TEMPO-VAE hot path on B200.
 
   python bench.py --gpus N --steps K --warmup W            our arm (N > 1: launched by torch.distributed.run)
-  python bench.py --impl reference --gpus N --steps K ...  the reference's algorithm on the host CPU cores
+  python bench.py --impl reference --gpus N --steps K ...  the reference itself on the host CPU cores
 
 Metric (BASELINE.json): train samples/sec (fwd + bwd + clip + AdamW) of the default TEMPO-VAE
 (configs/training shape [1028,64,64], chs [512,256,128], z 32) at batch 256 per GPU, bf16 tensor-core operands,
 synthetic radiance-like patches, random-init weights. One "step" = Trainer.train_step on one batch.
 
-  value  : device-resident input (NCHW fp32 already in HBM), CUDA-event timed, max over ranks
-  e2e    : same step through the public API (Trainer.train_step) fed from PINNED HOST memory through the
-           DevicePrefetcher (H2D copy of every batch inside the timed region, overlapped with the previous step)
-           and a device->host read of the metrics every step
-  roofline: the dominant kernel (conv_gemm_kernel on the 512->512 3x3 @64x64 layers, fwd + dgrad launches),
-           bracketed by CUDA events inside the timed region; peak = MEASURED_PEAKS.json bf16_tflops_sustained
-  cpu_baseline: the oracle port of the reference path on the host cores, bounded sample (N = 1 only)
+  value    : device-resident input (NCHW fp32 already in HBM), CUDA-event timed, max over ranks
+  e2e      : the same step through the product's own loader API: `HostTileStore.batches` (the split held in PINNED host
+             memory as channels-last bf16, every batch DMA'd to the device inside the timed region, one step ahead) ->
+             `Trainer.train_step` -> python floats (a device->host read every step)
+  e2e_reference_format : the same, fed the reference loader's fp32 NCHW batches from pinned memory (4.3 GB per step)
+  roofline : the dominant kernel (conv_gemm_kernel on the 512->512 3x3 @64x64 layers, fwd + dgrad launches),
+             bracketed by CUDA events inside the timed region; peak = MEASURED_PEAKS.json bf16_tflops_sustained
+  roofline_hbm : the HBM-bound kernels (GroupNorm fwd / bwd, NLL, AdamW, input layout), timed the same way: achieved
+             GB/s over ALGORITHMIC bytes against MEASURED_PEAKS.json hbm_gbs
+  dp_parity (N > 1) : before anything is timed, two optimiser steps of a small model through DataParallel on N ranks
+             are compared with one process stepping the whole batch; the run FAILS (rc 3) above 2e-3 / 2.5e-4
+  config4  : BASELINE config 4 as written -- global batch 2048 = 2048 / (256 N) accumulated micro-batches per rank,
+             one all-reduce per optimiser step
+  secondary (N = 1): bounded runs of config 3 (L2-supervised step), config 5 (encode sweep) and the same-box
+             PyTorch-eager comparator (bf16 autocast)
+  cpu_baseline (N = 1): the reference's own Trainer.train_step on the host cores, bounded sample
 """
 import argparse
 import json
@@ -38,11 +47,23 @@ DEFAULT_MODEL = dict(
     optimizer_type="AdamW",
     optimizer_params=dict(lr=1e-4, betas=[0.9, 0.95], weight_decay=0.05),
 )
+TINY_MODEL = dict(
+    architecture_type="vae",
+    architecture_params=dict(enc_dec_params=dict(
+        shape=[20, 16, 16], embed_dim=4, chs=[32, 16, 16], attn_sizes=[], mid_attn=True, num_res_blocks=1,
+        z_channels=4, double_z=True, n_attention_heads=4, norm_groups=8, norm_eps=1e-6, act="gelu", kl_weight=1e-6,
+        nll_loss_type="l1")),
+    optimizer_type="AdamW",
+    optimizer_params=dict(lr=1e-4, betas=[0.9, 0.95], weight_decay=0.05),
+)
 FWD_GF, BWD_GF = 165.776, 292.746          # algorithmic conv GFLOP / sample
+REF_BATCH = 8                              # BASELINE config 1: the reference's CPU-runnable case
 # dram bytes of one 512->512 3x3 @64x64 launch at B=256 from the committed ncu capture (profiles/ncu_gemm_r1.md,
 # launch 1: 1.084 GB read + 2.104 GB written; the launch reads a 1.07 GB bf16 activation + 4.7 MB of weights and
 # writes a 2.15 GB fp32 tensor)
 NCU_CONV_TRAFFIC_BYTES = 3.188e9
+WORKLOAD = ("default TEMPO-VAE train step (configs/training/train_vae_default.yaml model), synthetic patches "
+            "[1028,64,64] clamp(N(0,1),-10,10), random-init weights")
 
 
 def peaks():
@@ -103,39 +124,150 @@ def synthetic_batch(torch, B, shape, device, seed):
 
 
 # ================================================================================================= reference arm
-def oracle_step_fn(torch, device="cpu", autocast=False):
+# Nothing below this banner and above "our arm" imports tempo_vae_b200: the reference arm must not depend on the
+# product. It runs the REAL reference (oracle/_ref: byte-compiled from /root/reference by
+# oracle/build_ref.py) when that was built, else the oracle port with weights from oracle.init_state_dict.
+def _oracle():
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import build_ref
     import tempo_vae_oracle as orc
-    import tempo_vae_b200.model as m
-    torch.manual_seed(42)
-    vae = m.AutoencoderKL({k: v for k, v in m.DEFAULT_ENC_DEC.items()}, embed_dim=32, kl_weight=1e-6, nll_loss_type="l1")
-    params = {k: v.detach().clone().to(device) for k, v in m.SpectralVAE(vae).state_dict().items()}
-    state = {}
+    return build_ref, orc
+
+
+class _quiet_stdout:
+    """The reference prints batch statistics at step 0; bench.py's stdout carries exactly one JSON line."""
+
+    def __enter__(self):
+        self._old = sys.stdout
+        sys.stdout = sys.stderr
+
+    def __exit__(self, *a):
+        sys.stdout = self._old
+
+
+def reference_cpu_steps(torch, device="cpu", autocast=False):
+    """Returns (kind, {"train_step": fn(x), "lean_step": fn(x), "encode": fn(x)}) on `device`:
+       kind "reference": src.train_utils.Trainer.train_step as written (src/train_utils.py:149-183: get_loss, the extra
+                         no-grad forward for pixel_mse, backward, clip, AdamW), its lean variant (no extra forward) and
+                         vae.encode, all from the real reference modules;
+       kind "port":      the same three from the oracle's functional restatement."""
+    build_ref, orc = _oracle()
+    ref = build_ref.load()
+    dev = torch.device(device)
+
+    def ctx():
+        if autocast:
+            return torch.autocast(dev.type, dtype=torch.bfloat16)
+        import contextlib
+        return contextlib.nullcontext()
+
+    if ref is not None:
+        import numpy as np
+        import src.model as rm
+        import src.train_utils as rt
+        with _quiet_stdout():
+            rt.seed_all(42)
+            np.random.seed(42)
+            model = rm.get_model(DEFAULT_MODEL, dev)
+            trainer = rt.Trainer(model, model.optimizer, dev, tempfile.mkdtemp(prefix="tvae_ref_"))
+
+        def train_step(x):
+            with _quiet_stdout(), ctx():
+                m = trainer.train_step(x)
+            trainer.step += 1
+            return m["loss"]
+
+        def lean_step(x):
+            with ctx():
+                model.train()
+                loss, _ = model.get_loss(x.to(dev, dtype=torch.float32))
+            model.optimizer.zero_grad()
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=1.0)
+            model.optimizer.step()
+            return float(loss.detach())
+
+        def encode(x):
+            with torch.no_grad(), ctx():
+                return model.vae.encode(x.to(dev, dtype=torch.float32)).mean
+        return "reference", dict(train_step=train_step, lean_step=lean_step, encode=encode)
+
     cfg = orc.DEFAULT_CFG
-    g = torch.Generator(device=device).manual_seed(0)
+    params = {k: v.to(dev) for k, v in orc.init_state_dict(cfg, seed=42).items()}
+    state = {}
+    g = torch.Generator(device=dev).manual_seed(0)
     step_no = [0]
 
-    def step(B, x=None):
-        if x is None:
-            x = torch.randn((B, 1028, 64, 64), generator=g, device=device).clamp_(-10, 10)
-        eps = torch.randn((B, 32, 16, 16), generator=g, device=device)
-
-        def loss_fn(leaves):
-            if autocast:
-                with torch.autocast("cuda", dtype=torch.bfloat16):
-                    return orc.vae_loss(leaves, x, eps, cfg)
-            return orc.vae_loss(leaves, x, eps, cfg)
-        grads, out = orc.grads_of(loss_fn, params)
+    def lean_step(x):
+        eps = torch.randn((x.shape[0], 32, 16, 16), generator=g, device=dev)
+        with ctx():
+            grads, out = orc.grads_of(lambda leaves: orc.vae_loss(leaves, x, eps, cfg), params)
         step_no[0] += 1
         orc.clip_and_adamw(params, grads, state, step=step_no[0])
-        return out["loss"]
-    return step
+        return float(out["loss"])
+
+    def train_step(x):
+        eps = torch.randn((x.shape[0], 32, 16, 16), generator=g, device=dev)
+        with torch.no_grad(), ctx():                      # the reference's extra forward for pixel_mse
+            orc.vae_loss(params, x, eps, cfg)
+        return lean_step(x)
+
+    def encode(x):
+        with torch.no_grad(), ctx():
+            return orc.encode(params, x, cfg)[0]
+    return "port", dict(train_step=train_step, lean_step=lean_step, encode=encode)
+
+
+def time_cpu(fn, x, n, warm=0):
+    for _ in range(warm):
+        fn(x)
+    t0 = time.perf_counter()
+    for _ in range(n):
+        fn(x)
+    return (time.perf_counter() - t0) / n
+
+
+def run_reference(args):
+    """The reference arm of the contract: the reference's own CPU implementation of the path on the host cores, all
+    threads, FIXED batch 8 (BASELINE config 1) every step, Trainer.train_step as written. Rank 0 only."""
+    import torch
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    kind, fns = reference_cpu_steps(torch)
+    B = args.ref_batch
+    xs = [synthetic_batch(torch, B, (1028, 64, 64), "cpu", seed=i) for i in range(2)]
+    for i in range(args.warmup):
+        fns["train_step"](xs[i % 2])
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        fns["train_step"](xs[i % 2])
+    dt = (time.perf_counter() - t0) / args.steps
+    v = B / dt
+    lean = B / time_cpu(fns["lean_step"], xs[0], 2)
+    enc = B / time_cpu(fns["encode"], xs[0], 2)
+    what = ("src.train_utils.Trainer.train_step as written (get_loss + the extra no-grad forward for pixel_mse + "
+            "backward + clip + AdamW), real reference modules from oracle/_ref" if kind == "reference" else
+            "oracle port of Trainer.train_step (incl. the extra forward)")
+    sample = f"{args.steps} timed steps of {what}, fp32, batch {B}, torch CPU threads = {cores}"
+    print(json.dumps({
+        "impl": "reference", "metric": "train samples/sec (fwd+bwd+AdamW)", "value": v, "unit": "samples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "batch_per_step": B, "device": "host CPU"},
+        "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": kind, "sample": sample,
+                         "lean_step_samples_per_s": lean, "encode_samples_per_s": enc},
+        "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }), flush=True)
 
 
 def run_reference_gpu(args):
-    """Same-box comparator: the oracle's restatement of the reference train step executed by
-    stock PyTorch eager kernels (cuDNN/cuBLAS/ATen) on the B200 -- what a user of the reference gets on this GPU.
-    `--ref-device cuda --ref-precision {fp32,tf32,bf16}`; inputs resident in HBM, CUDA events."""
+    """Same-box comparator: the reference's train step executed by stock PyTorch eager kernels
+    (cuDNN/cuBLAS/ATen) on the B200 -- what a user of the reference gets on this GPU. The lean step (no extra pixel_mse
+    forward) is timed, i.e. the same work as our step. `--ref-device cuda --ref-precision {fp32,tf32,bf16}`; inputs
+    resident in HBM, CUDA events."""
     import torch
     if int(os.environ.get("RANK", "0")) != 0:
         return
@@ -144,60 +276,151 @@ def run_reference_gpu(args):
     tf32 = args.ref_precision != "fp32"
     torch.backends.cudnn.allow_tf32 = tf32
     torch.backends.cuda.matmul.allow_tf32 = tf32
-    step = oracle_step_fn(torch, dev, autocast=(args.ref_precision == "bf16"))
+    kind, fns = reference_cpu_steps(torch, dev, autocast=(args.ref_precision == "bf16"))
+    step = fns["lean_step"]
     B = args.batch
     xs = [synthetic_batch(torch, B, (1028, 64, 64), dev, seed=i) for i in range(2)]
     for i in range(max(args.warmup, 1)):
-        step(B, xs[i % 2])
+        step(xs[i % 2])
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
-        loss = step(B, xs[i % 2])
+        loss = step(xs[i % 2])
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.steps
     v = B / (ms / 1e3)
     print(json.dumps({
-        "impl": "reference", "comparator": f"oracle restatement on PyTorch eager CUDA kernels, {args.ref_precision}",
+        "impl": "reference", "comparator": f"{kind}: lean train step on PyTorch eager CUDA kernels, {args.ref_precision}",
         "metric": "train samples/sec (fwd+bwd+AdamW)", "value": v, "unit": "samples/s", "n_gpus": 1,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": args.ref_precision, "data": "synthetic",
-        "config": {"workload": "default TEMPO-VAE train step, synthetic patches [1028,64,64]", "batch_per_gpu": B},
+        "config": {"workload": WORKLOAD, "batch_per_gpu": B},
         "peak_hbm_gb": torch.cuda.max_memory_allocated(dev) / 1e9, "final_loss": float(loss),
     }), flush=True)
 
 
-def run_reference(args):
-    import torch
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    step = oracle_step_fn(torch)
-    t0 = time.perf_counter(); step(1); t1 = time.perf_counter() - t0            # also the first warm-up
-    budget = 150.0
-    B = int(max(1, min(8, budget / max(1e-3, (args.steps + max(args.warmup - 1, 0)) * t1))))
-    for _ in range(max(args.warmup - 1, 0)):
-        step(B)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step(B)
-    dt = time.perf_counter() - t0
-    v = B * args.steps / dt
-    sample = f"{args.steps} timed oracle train steps (fwd+bwd+clip+AdamW, fp32) of the default model at batch {B}"
-    print(json.dumps({
-        "impl": "reference", "metric": "train samples/sec (fwd+bwd+AdamW)", "value": v, "unit": "samples/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "default TEMPO-VAE train step, synthetic patches [1028,64,64]", "batch_per_step": B},
-        "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }), flush=True)
-
-
 # ================================================================================================= our arm
+def dp_parity_check(torch, dist, t, dev, rank, world):
+    """Two optimiser steps of a small TEMPO-VAE through DataParallel (bucketed all-reduce overlapped with backward,
+    1/world folded into AdamW, Philox noise keyed by the global sample index) on `world` ranks, against ONE process
+    stepping the whole batch on rank 0. The logic of tests/test_ddp_gpu.py, placed where a multi-GPU run happens."""
+    from tempo_vae_b200.parallel import DataParallel
+
+    def build():
+        t.seed_all(42)
+        model = t.get_model(TINY_MODEL, dev)
+        g = torch.Generator().manual_seed(1234)
+        with torch.no_grad():                                 # the zero-initialised convs would hide half the network
+            for k, p in model.named_parameters():
+                if k.endswith(("net2.2.weight", "net2.2.bias", "coder.conv_out.weight", "coder.conv_out.bias")):
+                    p.copy_(((torch.rand(p.shape, generator=g) * 2 - 1) * 0.05).to(dev))
+        t.ENGINE.params_changed()
+        return model
+
+    per = 4
+    B = per * world
+    x = torch.randn((B, 20, 16, 16), generator=torch.Generator().manual_seed(77)).clamp_(-10, 10)
+    model = build()
+    dp = DataParallel(model, model.optimizer, bucket_mb=0.05)           # several buckets even for the small model
+    t.seed_all(9)
+    got = []
+    for _ in range(2):
+        xl = x[rank * per:(rank + 1) * per].to(dev)
+        loss, _ = dp.get_loss(xl)
+        model.optimizer.zero_grad()
+        dp.backward(loss)
+        g = model.optimizer.flat_grad.clone() / world
+        dp.step(max_grad_norm=1.0)
+        got.append((g, model.optimizer.flat_param.clone()))
+    out = None
+    if rank == 0:
+        single = build()
+        t.seed_all(9)
+        rel_grad = max_param = rel_param = 0.0
+        for s in range(2):
+            loss, _ = single.get_loss(x.to(dev))
+            single.optimizer.zero_grad()
+            loss.backward()
+            g1 = single.optimizer.flat_grad.clone()
+            single.optimizer.step(max_grad_norm=1.0)
+            p1 = single.optimizer.flat_param
+            rel_grad = max(rel_grad, float((got[s][0] - g1).norm() / g1.norm()))
+            max_param = max(max_param, float((got[s][1] - p1).abs().max()))
+            rel_param = max(rel_param, float((got[s][1] - p1).norm() / p1.norm()))
+        out = {"rel_grad": rel_grad, "max_param": max_param, "rel_param": rel_param, "steps": 2, "ranks": world,
+               "buckets": len(dp.bucketer.buckets), "tol": {"rel_grad": 2e-3, "max_param": 2.5e-4},
+               "ok": bool(rel_grad < 2e-3 and max_param < 2.5e-4)}
+    dist.barrier()
+    torch.cuda.synchronize()
+    return out
+
+
+def hbm_rooflines(prof, pk):
+    out = {}
+    for name, evs in sorted(prof["events"].items()):
+        ms = sum(a.elapsed_time(b) for a, b, _ in evs)
+        nbytes = sum(n for _, _, n in evs)
+        gbs = nbytes / (ms * 1e-3) / 1e9 if ms > 0 else float("nan")
+        out[name] = {"bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"],
+                     "launches_timed": len(evs), "avg_ms": ms / len(evs), "algorithmic_bytes_per_launch": nbytes / len(evs)}
+    return out
+
+
+def measure_train_l2(torch, t, model, dev, B, steps, warmup, rank=0):
+    l2 = t.VAEWithL2Supervision(model.vae, latent_channels=32, mlp_hidden=[512, 512]).to(dev)
+    opt = t.FusedAdamW(l2.parameters(), lr=1e-4, betas=(0.9, 0.95), weight_decay=0.05)
+    trainer = t.L2SupervisedTrainer(l2, opt, dev, tempfile.mkdtemp(prefix="tvae_bench_"), kl_weight=1e-6,
+                                    l2_weights={"NO2": 0.1, "O3TOT": 0.1, "HCHO": 0.1, "CLDO4": 0.1})
+    trainer.step = 1
+    g = torch.Generator(device=dev).manual_seed(rank)
+    batch = {"spectral": synthetic_batch(torch, B, (1028, 64, 64), dev, seed=rank)}
+    for p in ("NO2", "O3TOT", "HCHO", "CLDO4"):
+        tg = torch.randn((B, 64, 64), device=dev, generator=g)
+        blob = torch.nn.functional.interpolate(torch.rand((B, 1, 8, 8), device=dev, generator=g), size=(64, 64))[:, 0]
+        tg[blob < 0.15] = float("nan")            # ~15 % invalid pixels in contiguous blobs (SURVEY.md §8d)
+        batch[p] = tg
+    for _ in range(warmup):
+        trainer.train_step_device(batch)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); e0.record()
+    for _ in range(steps):
+        m = trainer.train_step_device(batch)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"workload": "VAEWithL2Supervision train step (BASELINE config 3), default model + 282,628-parameter L2 head, "
+                        "4 targets with ~15 % NaN blobs", "metric": "train samples/sec (fwd+bwd+AdamW)",
+            "value": B / ms * 1e3, "unit": "samples/s", "ms_per_step": ms, "batch_per_gpu": B, "steps": steps,
+            "final_metrics": {k: float(v.detach()) for k, v in m.items()}}
+
+
+def measure_encode(torch, t, model, dev, B, steps, warmup, rank=0, n_gran=4):
+    # synthetic granules [131, 2048, 1028] -> normalise -> crop [128, 2048] -> 64 patches of [1028, 64, 64] each
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    mean_s = torch.full((1028,), 3.0, device=dev)
+    std_s = torch.full((1028,), 0.5, device=dev)
+    patches = []
+    for _ in range(n_gran):
+        rad = torch.exp(torch.randn((131, 2048, 1028), device=dev, generator=g) * 0.5 + 3.0)
+        patches.append(t.granule_to_patches(t.normalize_radiance(rad, mean_s, std_s)))
+        del rad
+    patches = torch.cat(patches)                    # [64 * n_gran, 1028, 64, 64] per rank
+    for _ in range(warmup):
+        t.encode_patches(model, patches, batch_size=B)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); e0.record()
+    for _ in range(steps):
+        lat = t.encode_patches(model, patches, batch_size=B)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    n = patches.shape[0]
+    return {"workload": "encode-only patch sweep (BASELINE config 5): posterior means of the 64x64 patches of synthetic "
+                        "granules [131,2048,1028]", "metric": "encoded patches/sec", "value": n / ms * 1e3,
+            "unit": "patches/s", "ms_per_sweep": ms, "patches_per_gpu": n, "sweeps": steps,
+            "latent_shape": list(lat.shape[1:]), "encoder_tflops": n / ms * 1e3 * 84.248 / 1e3}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -211,10 +434,12 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    dp_parity = None
     if world > 1:
         from tempo_vae_b200.parallel import bind_to_gpu_numa
         numa_bound = bind_to_gpu_numa(local)          # pinned host batches on the GPU's own NUMA node
         dist.init_process_group("nccl", device_id=dev)
+        dp_parity = dp_parity_check(torch, dist, t, dev, rank, world)
     else:
         numa_bound = None
     B = args.batch
@@ -223,6 +448,7 @@ def run_ours(args):
     t.seed_all(42)
     model = t.get_model(DEFAULT_MODEL, dev)
     trainer = t.Trainer(model, model.optimizer, dev, tempfile.mkdtemp(prefix="tvae_bench_"))
+    trainer.step = 1                  # (the reference prints batch statistics while step == 0)
     dp = DataParallel(model, model.optimizer) if world > 1 else None
 
     def step_device(x):
@@ -244,20 +470,39 @@ def run_ours(args):
         dist.all_reduce(tns, op=dist.ReduceOp.MAX)
         return float(tns.item())
 
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed_loop(step_fn, batches, steps, warmup):
+        """W untimed + K timed calls of step_fn over an iterator, barrier + synchronize on both sides; returns
+        (device ms per step max over ranks incl. host wall clock, last result)."""
+        it = iter(batches)
+        for _ in range(warmup):
+            step_fn(next(it))
+        barrier()
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(steps):
+            out = step_fn(next(it))
+        e1.record()
+        barrier()
+        wall = (time.perf_counter() - t0) / steps * 1e3
+        return max_over_ranks(max(e0.elapsed_time(e1) / steps, wall)), out
+
     # ---------------------------------------------------------------- kernel-only number (inputs resident in HBM)
     xs = [synthetic_batch(torch, B, shape, dev, seed=1000 * rank + i) for i in range(2)]
     for i in range(args.warmup):
         step_device(xs[i % 2])
-        trainer.step = 1                  # (the reference prints batch statistics while step == 0)
     M = B * 64 * 64
     ops.PROFILE["conv"] = {"match": lambda px, co, ci, kind, R: px == M and co == 512 and ci == 512 and kind == 0 and R == 3,
                            "events": []}
     ops.PROFILE["wgrad"] = {"match": lambda px, cm, cn, kind, R: px == M and cm == 512 and cn == 512 and kind == 0 and R == 3,
                             "events": []}
+    # HBM-bound kernels: every call that moves at least 100 MB of algorithmic bytes (the 64x64 and 32x32 levels, the
+    # loss, the input layout pass, AdamW) is timed; the small 16x16-level calls are launch-latency bound and left out
+    ops.PROFILE["hbm"] = {"min_bytes": 100e6, "events": {}}
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     n0 = ops.KERNEL_LAUNCHES[0]
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     th0 = time.perf_counter()
     for i in range(args.steps):
@@ -270,85 +515,102 @@ def run_ours(args):
     ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)
     conv_ms = [a.elapsed_time(b) for a, b in ops.PROFILE["conv"]["events"]]
     wg_ms = [a.elapsed_time(b) for a, b in ops.PROFILE["wgrad"]["events"]]
+    pk = peaks()
+    hbm = hbm_rooflines(ops.PROFILE["hbm"], pk)
     ops.PROFILE.clear()
     final = {k: float(v.detach()) for k, v in last.items()}
     value = world * B / (ms / 1e3)
 
-    # ---------------------------------------------------------------- end to end (host buffers, public API)
     if args.skip_e2e:
         if rank == 0:
             print(json.dumps({"profiling_run": True, "value": value, "ms_per_step": ms, "gpu_launches": launches,
-                              "host_enqueue_ms_per_step": host_enqueue_ms}))
+                              "host_enqueue_ms_per_step": host_enqueue_ms, "roofline_hbm": hbm}))
         if world > 1:
             dist.destroy_process_group()
         return
+
+    # ---------------------------------------------------------------- BASELINE config 4 as written: global batch 2048
+    G = args.global_batch
+    cfg4 = None
+    if G and G % (world * B) == 0:
+        n_micro = G // (world * B)
+        micro = [xs[i % 2] for i in range(n_micro)]
+        acc_step = (lambda _: dp.train_step_device(micro)) if dp is not None else \
+            (lambda _: trainer.train_step_accumulate(micro))
+        c4_steps = max(2, min(args.steps, 3))
+        c4_ms, _ = timed_loop(acc_step, iter(range(1 + c4_steps)), c4_steps, 1)
+        cfg4 = {"global_batch": G, "micro_batches_per_rank": n_micro, "micro_batch": B, "value": G / (c4_ms / 1e3),
+                "unit": "samples/s", "ms_per_optimizer_step": c4_ms, "steps": c4_steps, "scaling": "strong",
+                "note": "gradients of the micro-batches accumulate in the flat buffer (wgrad kernels add in place); one "
+                        "bucketed all-reduce per optimiser step, overlapped with the last micro-batch's backward"}
+
+    # ---------------------------------------------------------------- end to end (host buffers, public loader API)
+    # (a) headline: the product's pinned-host tile store -> per-tile DMA gather -> Trainer.train_step -> floats
+    n_tiles = 2 * B
+    store = t.HostTileStore(shape[1], shape[2], shape[0], n_tiles)
+    for x in xs:
+        store.add(x.permute(0, 2, 3, 1))               # cast once at load time (here: from the synthetic batches)
+    tile_bytes = shape[1] * shape[2] * store.pitch * 2
+    # (b) the reference loader's batch format: fp32 NCHW in pinned memory
     host = [torch.empty((B, *shape), dtype=torch.float32).pin_memory() for _ in range(2)]
     for i, h in enumerate(host):
         h.copy_(xs[i])
-    # the same batches in the engine's own loader format (channels-last bf16 rows, pitch 1032: what DeviceTileCache /
-    # a bf16 tile store holds; cast once at load time, bit-identical results because the engine rounds its input to
-    # bf16 first thing) -- used for the extra e2e_loader_format leg below
-    pitch = (shape[0] + 7) // 8 * 8
-    host_cl = [torch.zeros((B, shape[1], shape[2], pitch), dtype=torch.bfloat16).pin_memory() for _ in range(2)]
-    for i, h in enumerate(host_cl):
-        h[..., :shape[0]].copy_(xs[i].permute(0, 2, 3, 1))
     del xs
     torch.cuda.empty_cache()
-
-    def host_stream(n):
-        for i in range(n):
-            yield host[i % 2]
 
     if dp is None:
         e2e_step = trainer.train_step                       # floats: one device->host read per step
     else:
         def e2e_step(x):
-            m = step_device(x)
-            return t.train_utils._to_floats(m)
-    pf = DevicePrefetcher(host_stream(args.warmup + args.steps), dev)
-    it = iter(pf)
-    for _ in range(args.warmup):
-        e2e_step(next(it))
-    barrier()
-    t0 = time.perf_counter()
-    e0.record()
-    for _ in range(args.steps):
-        m = e2e_step(next(it))
-    e1.record()
-    barrier()
-    wall = (time.perf_counter() - t0) / args.steps * 1e3
-    e2e_ms = max_over_ranks(max(e0.elapsed_time(e1) / args.steps, wall))
+            return t.train_utils._to_floats(step_device(x))
+
+    h2d0 = store.h2d_bytes
+    e2e_ms, m = timed_loop(e2e_step, store.batches(B, dev, seed=rank), args.steps, args.warmup)
+    h2d_per_step = (store.h2d_bytes - h2d0) / (args.steps + args.warmup + 1)      # one batch is in flight at the end
+    assert abs(h2d_per_step - B * tile_bytes) < 1, (h2d_per_step, B * tile_bytes)
     e2e_value = world * B / (e2e_ms / 1e3)
-    h2d = B * shape[0] * shape[1] * shape[2] * 4
     d2h = 4 * len(m)
 
-    # extra leg: host batches in the loader format (half the H2D bytes), same API call, same timing rules
-    def cl_stream(n):
-        for i in range(n):
-            yield host_cl[i % 2]
-    it = iter(DevicePrefetcher(cl_stream(args.warmup + args.steps), dev, dtype=torch.bfloat16))
-
-    def as_nchw_view(d):
-        return d[..., :shape[0]].permute(0, 3, 1, 2)        # [B, C, H, W]-shaped, channels-last strides: used in place
-    for _ in range(args.warmup):
-        e2e_step(as_nchw_view(next(it)))
+    # raw host->device rate of this rank while every rank copies at once (the PCIe number the e2e legs live on)
+    dst = torch.empty((B, shape[1], shape[2], store.pitch), dtype=torch.bfloat16, device=dev)
     barrier()
-    t0 = time.perf_counter()
     e0.record()
-    for _ in range(args.steps):
-        e2e_step(as_nchw_view(next(it)))
+    for _ in range(3):
+        for j in range(B):
+            dst[j].copy_(store.data[j], non_blocking=True)
     e1.record()
     barrier()
-    wall = (time.perf_counter() - t0) / args.steps * 1e3
-    cl_ms = max_over_ranks(max(e0.elapsed_time(e1) / args.steps, wall))
-    cl_h2d = host_cl[0].numel() * 2
+    h2d_gbs = 3 * B * tile_bytes / (max_over_ranks(e0.elapsed_time(e1)) * 1e-3) / 1e9
+    del dst
+
+    def host_stream(n):
+        for i in range(n):
+            yield host[i % 2]
+    ref_ms, _ = timed_loop(e2e_step, DevicePrefetcher(host_stream(args.warmup + args.steps), dev), args.steps, args.warmup)
+    ref_h2d = B * shape[0] * shape[1] * shape[2] * 4
+    del host, store
+    torch.cuda.empty_cache()
+
+    # ---------------------------------------------------------------- secondary workloads (N = 1, bounded)
+    secondary = None
+    if world == 1 and not args.no_secondary:
+        secondary = {}
+        ksteps, kwarm = max(3, min(args.steps, 8)), 3
+        try:
+            secondary["encode"] = measure_encode(torch, t, model, dev, B, ksteps, kwarm)
+        except Exception as e:  # noqa: BLE001
+            secondary["encode"] = {"error": repr(e)[:300]}
+        torch.cuda.empty_cache()
+        try:
+            secondary["train_l2"] = measure_train_l2(torch, t, model, dev, B, ksteps, kwarm)
+        except Exception as e:  # noqa: BLE001
+            secondary["train_l2"] = {"error": repr(e)[:300]}
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    pk = peaks()
     conv_flops = 2.0 * M * 512 * (9 * 512)
     conv_avg = statistics.mean(conv_ms) if conv_ms else float("nan")
     achieved = conv_flops / (conv_avg * 1e-3) / 1e12
@@ -357,9 +619,7 @@ def run_ours(args):
         "metric": "train samples/sec (fwd+bwd+AdamW)", "value": value, "unit": "samples/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "default TEMPO-VAE train step (configs/training/train_vae_default.yaml model), "
-                               "synthetic patches [1028,64,64] clamp(N(0,1),-10,10), random-init weights",
-                   "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
+        "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
                    "l2_flush": "inputs (4.3 GB/step) and activations are far larger than the 126 MB L2",
                    "useful_gflop_per_sample": FWD_GF + BWD_GF},
         "step_tflops": value * (FWD_GF + BWD_GF) / 1e3,
@@ -375,13 +635,16 @@ def run_ours(args):
                      "launches_timed": len(conv_ms), "avg_ms": conv_avg,
                      "wgrad_kernel": {"avg_ms": wg_avg, "achieved": conv_flops / (wg_avg * 1e-3) / 1e12,
                                       "launches_timed": len(wg_ms)}},
-        "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_ms, "api": "Trainer.train_step over DevicePrefetcher (pinned host batches)"},
-        "e2e_loader_format": {"value": world * B / (cl_ms / 1e3), "unit": "samples/s", "ms_per_step": cl_ms,
-                              "h2d_bytes_per_step": cl_h2d, "d2h_bytes_per_step": d2h,
-                              "note": "same call, pinned host batches held as channels-last bf16 (the engine's tile-store "
-                                      "format, results bit-identical); not the headline e2e, which copies the "
-                                      "reference loader's fp32 NCHW batches"},
+        "roofline_hbm": hbm,
+        "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(h2d_per_step),
+                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
+                "api": "HostTileStore.batches (pinned host tile store, channels-last bf16, one async DMA per tile into "
+                       "rotating device buffers, one batch ahead) -> Trainer.train_step (python floats)",
+                "h2d_gb_per_s_per_gpu_all_ranks_copying": h2d_gbs},
+        "e2e_reference_format": {"value": world * B / (ref_ms / 1e3), "unit": "samples/s", "ms_per_step": ref_ms,
+                                 "h2d_bytes_per_step": ref_h2d, "d2h_bytes_per_step": d2h,
+                                 "api": "DevicePrefetcher over pinned fp32 NCHW batches (what the reference's DataLoader "
+                                        "yields) -> Trainer.train_step"},
         "gpu_launches": launches,
         "host_enqueue_ms_per_step": host_enqueue_ms,
         "numa_bound": numa_bound, "host_cpus": len(os.sched_getaffinity(0)),
@@ -389,23 +652,49 @@ def run_ours(args):
         "clocks": clocks,
         "final_metrics": final,
     }
+    if cfg4 is not None:
+        out["config4_global_batch"] = cfg4
+    if dp_parity is not None:
+        out["dp_parity"] = dp_parity
+    if world > 1:
+        dist.destroy_process_group()
+    if secondary is not None:
+        # same-box comparator: the reference's lean train step on stock PyTorch CUDA kernels under bf16 autocast, in a
+        # subprocess (its 78 GB of activations need the memory this process is still holding)
+        del model, trainer
+        torch.cuda.empty_cache()
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--ref-device", "cuda",
+                                "--ref-precision", "bf16", "--batch", str(B), "--steps", "5", "--warmup", "3"],
+                               capture_output=True, text=True, timeout=420)
+            line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+            eg = json.loads(line[-1]) if line else {"error": (r.stderr or "no output")[-300:]}
+            secondary["eager_bf16"] = {k: eg.get(k) for k in ("comparator", "value", "unit", "ms_per_step", "peak_hbm_gb",
+                                                              "error") if k in eg}
+            if "value" in eg:
+                secondary["eager_bf16"]["engine_over_eager"] = value / eg["value"]
+        except Exception as e:  # noqa: BLE001
+            secondary["eager_bf16"] = {"error": repr(e)[:300]}
+        out["secondary"] = secondary
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
-        step = oracle_step_fn(torch)
-        step(1)
-        cb = 4
-        t0 = time.perf_counter(); step(cb); dt = time.perf_counter() - t0
-        out["cpu_baseline"] = {"value": cb / dt, "unit": "samples/s", "cores": cores, "kind": "port",
-                               "sample": f"1 oracle train step (fp32 fwd+bwd+clip+AdamW) of the default model at "
-                                         f"batch {cb} after a batch-1 warm-up, torch CPU threads = {cores}"}
+        kind, fns = reference_cpu_steps(torch)
+        x8 = synthetic_batch(torch, REF_BATCH, shape, "cpu", seed=0)
+        dt = time_cpu(fns["train_step"], x8, 3, warm=1)
+        out["cpu_baseline"] = {"value": REF_BATCH / dt, "unit": "samples/s", "cores": cores, "kind": kind,
+                               "sample": f"3 timed steps (after 1 warm-up) of the reference's Trainer.train_step as "
+                                         f"written (incl. its extra pixel_mse forward), fp32, batch {REF_BATCH}, torch "
+                                         f"CPU threads = {cores}",
+                               "lean_step_samples_per_s": REF_BATCH / time_cpu(fns["lean_step"], x8, 2),
+                               "encode_samples_per_s": REF_BATCH / time_cpu(fns["encode"], x8, 2)}
     print(json.dumps(out), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    if dp_parity is not None and not dp_parity["ok"]:
+        sys.exit(3)
 
 
 def run_extra(args):
-    """Secondary workloads (parity-test configs of BASELINE.json measured for reference, not the headline)."""
+    """Secondary workloads on their own (parity-test configs of BASELINE.json, not the headline); any N."""
     import torch
     import torch.distributed as dist
     import tempo_vae_b200 as t
@@ -420,37 +709,10 @@ def run_extra(args):
     B = args.batch
     t.seed_all(42)
     model = t.get_model(DEFAULT_MODEL, dev)
-
-    def sync():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        dist.barrier()
     if args.workload == "train_l2":
-        l2 = t.VAEWithL2Supervision(model.vae, latent_channels=32, mlp_hidden=[512, 512]).to(dev)
-        opt = t.FusedAdamW(l2.parameters(), lr=1e-4, betas=(0.9, 0.95), weight_decay=0.05)
-        trainer = t.L2SupervisedTrainer(l2, opt, dev, tempfile.mkdtemp(prefix="tvae_bench_"), kl_weight=1e-6,
-                                        l2_weights={"NO2": 0.1, "O3TOT": 0.1, "HCHO": 0.1, "CLDO4": 0.1})
-        trainer.step = 1
-        g = torch.Generator(device=dev).manual_seed(rank)
-        batch = {"spectral": synthetic_batch(torch, B, (1028, 64, 64), dev, seed=rank)}
-        for p in ("NO2", "O3TOT", "HCHO", "CLDO4"):
-            tg = torch.randn((B, 64, 64), device=dev, generator=g)
-            blob = torch.nn.functional.interpolate(torch.rand((B, 1, 8, 8), device=dev, generator=g), size=(64, 64))[:, 0]
-            tg[blob < 0.15] = float("nan")            # ~15 % invalid pixels in contiguous blobs
-            batch[p] = tg
-        for _ in range(args.warmup):
-            trainer.train_step_device(batch)
-        sync(); e0.record()
-        for _ in range(args.steps):
-            m = trainer.train_step_device(batch)
-        e1.record(); sync()
-        ms = e0.elapsed_time(e1) / args.steps
-        out = {"workload": "VAEWithL2Supervision train step (config 3), default model + 282,628-parameter L2 head",
-               "metric": "train samples/sec (fwd+bwd+AdamW)", "value": world * B / ms * 1e3, "unit": "samples/s",
-               "ms_per_step": ms, "n_gpus": world, "batch_per_gpu": B,
-               "final_metrics": {k: float(v.detach()) for k, v in m.items()}}
+        out = measure_train_l2(torch, t, model, dev, B, args.steps, args.warmup, rank)
     elif args.workload == "train_cached":
         # the train step fed from a device-resident channels-last bf16 tile cache
         trainer = t.Trainer(model, model.optimizer, dev, tempfile.mkdtemp(prefix="tvae_bench_"))
@@ -463,44 +725,24 @@ def run_extra(args):
         it = cache.batches(B, seed=rank)
         for _ in range(args.warmup):
             trainer.train_step_device(next(it))
-        sync(); e0.record()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); e0.record()
         for _ in range(args.steps):
             m = trainer.train_step_device(next(it))
-        e1.record(); sync()
+        e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / args.steps
         out = {"workload": "train step fed from DeviceTileCache (tiles resident in HBM as channels-last bf16, batches "
-                           "gathered on the device and consumed without a layout pass)",
-               "metric": "train samples/sec (fwd+bwd+AdamW)", "value": world * B / ms * 1e3, "unit": "samples/s",
-               "ms_per_step": ms, "n_gpus": world, "batch_per_gpu": B, "cached_tiles_per_gpu": n_tiles,
+                           "gathered on the device by tvae_gather_rows and consumed without a layout pass)",
+               "metric": "train samples/sec (fwd+bwd+AdamW)", "value": B / ms * 1e3, "unit": "samples/s",
+               "ms_per_step": ms, "batch_per_gpu": B, "cached_tiles_per_gpu": n_tiles,
                "final_metrics": {k: float(v.detach()) for k, v in m.items()}}
     else:
-        # synthetic granules [131, 2048, 1028] -> normalise -> crop [128, 2048] -> 64 patches of [1028, 64, 64] each
-        n_gran = 4
-        g = torch.Generator(device=dev).manual_seed(100 + rank)
-        mean_s = torch.full((1028,), 3.0, device=dev)
-        std_s = torch.full((1028,), 0.5, device=dev)
-        patches = []
-        for _ in range(n_gran):
-            rad = torch.exp(torch.randn((131, 2048, 1028), device=dev, generator=g) * 0.5 + 3.0)
-            patches.append(t.granule_to_patches(t.normalize_radiance(rad, mean_s, std_s)))
-            del rad
-        patches = torch.cat(patches)                    # [256, 1028, 64, 64] per rank
-        for _ in range(args.warmup):
-            t.encode_patches(model, patches, batch_size=B)
-        sync(); e0.record()
-        for _ in range(args.steps):
-            lat = t.encode_patches(model, patches, batch_size=B)
-        e1.record(); sync()
-        ms = e0.elapsed_time(e1) / args.steps
-        n = patches.shape[0]
-        out = {"workload": "encode-only patch sweep (config 5): posterior means of 64x64 patches of synthetic granules",
-               "metric": "encoded patches/sec", "value": world * n / ms * 1e3, "unit": "patches/s", "ms_per_sweep": ms,
-               "patches_per_gpu": n, "n_gpus": world, "latent_shape": list(lat.shape[1:]),
-               "encoder_tflops": world * n / ms * 1e3 * 84.248 / 1e3}
+        out = measure_encode(torch, t, model, dev, B, args.steps, args.warmup, rank)
+    out["n_gpus"] = world
     if world > 1:
         tns = torch.tensor([out["value"]], device=dev, dtype=torch.float64)
         dist.all_reduce(tns, op=dist.ReduceOp.MIN)
-        out["value"] = float(tns.item())
+        out["value"] = world * float(tns.item())
         dist.destroy_process_group()
     if rank == 0:
         print(json.dumps(out), flush=True)
@@ -512,17 +754,23 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=256, help="samples per GPU per step")
+    ap.add_argument("--batch", type=int, default=256, help="samples per GPU per (micro-)step")
+    ap.add_argument("--global-batch", type=int, default=2048,
+                    help="BASELINE config 4: the extra 'config4_global_batch' leg accumulates global_batch / (gpus * batch) "
+                         "micro-batches per optimiser step (0 = skip the leg)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the config 3 / config 5 / eager comparator legs")
     ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
                     help="--impl reference only: cpu = the contract's reference arm; cuda = same-box PyTorch-eager comparator")
     ap.add_argument("--ref-precision", default="tf32", choices=["fp32", "tf32", "bf16"])
-    ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: skip the host-fed leg")
+    ap.add_argument("--ref-batch", type=int, default=REF_BATCH,
+                    help="--impl reference on the CPU: samples per step; FIXED at 8 (BASELINE config 1) unless a test "
+                         "overrides it")
+    ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: stop after the device-resident leg")
     ap.add_argument("--workload", default="train", choices=["train", "train_l2", "train_cached", "encode"],
-                    help="train = headline (BASELINE config 2/4); train_l2 = L2-supervised variant (config 3); "
-                         "encode = inference-only patch sweep of synthetic granules (config 5); train_cached = train step "
-                         "fed from the device-resident tile cache (SURVEY 8f). The extra workloads "
-                         "print their own JSON line and are not the headline metric.")
+                    help="train = headline (BASELINE config 2/4); the others print their own JSON line: train_l2 = "
+                         "L2-supervised variant (config 3), encode = patch sweep of synthetic granules (config 5), "
+                         "train_cached = train step fed from the device-resident tile cache (SURVEY 8f)")
     args = ap.parse_args()
     if args.impl == "reference" and args.ref_device == "cuda":
         run_reference_gpu(args)

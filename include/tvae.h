@@ -279,6 +279,46 @@ int32_t tvae_adamw(float* param, const float* grad, float* exp_avg, float* exp_a
                    float beta1, float beta2, float eps, float weight_decay, int64_t step, const double* sumsq,
                    float max_norm, float grad_scale, tvae_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Data side: what feeds the path above.
+ *
+ * tvae_gather_rows: dst[j] = src[idx[j]] for n rows of row_bytes (multiple of 16) bytes; idx is an int64 DEVICE array
+ *  with values in [0, n_src). The device-resident tile cache builds its batches with it (replaces the reference
+ *  loader's shuffle-buffer draw + default_collate copy, src/tempo_data.py:34-110).
+ *
+ * tvae_extract_tiles: n_tiles square TxT tiles cut out of a raw radiance granule rad[M][NT][C] (fp32), each with the
+ *  reference's random augmentation chain -- crop at (row0, col0), torch.flip(dims=[0]) if flags & 1,
+ *  torch.flip(dims=[1]) if flags & 2, torch.rot90(k, dims=[0,1]) -- and, when mean/std are given, its normalisation
+ *  z = clamp((log(max(rad, min_radiance)) - mean[c]) / (std[c] + 1e-8), clip_min, clip_max) applied on the fly
+ *  (src/scripts/prepare_tempo_tiles.py:21-58 and :61-83 in ONE pass: the normalised granule is never materialised).
+ *  spec: int32 DEVICE array [n_tiles][4] = {row0, col0, flags, k}. Outputs (either may be NULL): out_f32
+ *  [n_tiles][T][T][C] (the on-disk tile format) and out_bf16 [n_tiles][T][T][out_pitch] (the conv operand rows, pad
+ *  lanes zeroed). mean == std == NULL copies raw values (augmentation only).
+ *
+ * tvae_spectrum_stats_*: per-channel mean and population standard deviation of log(max(rad, min_radiance)) over all
+ *  pixels of any number of granules (src/scripts/compute_tempo_stats.py:58-86: np.log(np.clip) -> mean / std over the
+ *  stacked pixels). acc is a caller-zeroed fp64 DEVICE array [2][C] (running sum, sum of squares) that _accum adds
+ *  `rows` pixels to (fixed-order reduction through the workspace); _finalize writes mean[C], std[C] (fp32).
+ *  take_log = 0 accumulates the values as they are.
+ *
+ * tvae_batch_stats: out[4] = {min, max, mean, unbiased std} over the C valid channels of `rows` rows with row pitch
+ *  `pitch` elements (fp32, or bf16 when is_bf16) -- the batch statistics Trainer.train_step prints at step 0
+ *  (src/train_utils.py:156-159). workspace: tvae_batch_stats_workspace_bytes().
+ */
+int32_t tvae_gather_rows(const void* src, int64_t n_src, int64_t row_bytes, const int64_t* idx, int32_t n, void* dst,
+                         tvae_stream_t stream);
+int32_t tvae_extract_tiles(const float* rad, int32_t M, int32_t NT, int32_t C, const int32_t* spec, int32_t n_tiles,
+                           int32_t T, const float* mean, const float* std, float min_radiance, float clip_min,
+                           float clip_max, float* out_f32, void* out_bf16, int32_t out_pitch, tvae_stream_t stream);
+int64_t tvae_spectrum_stats_workspace_bytes(int64_t rows, int32_t C);
+int32_t tvae_spectrum_stats_accum(const float* rad, int64_t rows, int32_t C, float min_radiance, int32_t take_log,
+                                  double* acc, double* workspace, tvae_stream_t stream);
+int32_t tvae_spectrum_stats_finalize(const double* acc, int64_t total_rows, int32_t C, float* mean, float* std,
+                                     tvae_stream_t stream);
+int64_t tvae_batch_stats_workspace_bytes(void);
+int32_t tvae_batch_stats(const void* x, int32_t is_bf16, int64_t rows, int64_t C, int64_t pitch, float* out,
+                         double* workspace, tvae_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -255,3 +255,155 @@ def structured_batch(B, cfg, seed=0, device="cpu"):
     f = f / f.std()
     x = torch.einsum("cr,brhw->bchw", basis, f) + 0.05 * torch.randn((B, C, H, W), generator=g)
     return torch.clamp(x, -10, 10).to(device)
+
+
+# ------------------------------------------------------------------------------------------------ oracle utilities
+class bf16_operands:
+    """Context manager: every convolution of this oracle rounds its input AND weight to bf16 (fp32 accumulation);
+    GroupNorm, activations, the residual stream, attention and the loss stay fp32. That is the BEST any bf16-operand
+    engine can do, so the forward error it shows against plain fp32 is the floor the GPU parity tests measure the
+    engine against (tools/bf16_floor.py, profiles/bf16_floor_r2.json)."""
+
+    def __enter__(self):
+        self._conv, self._convT = F.conv2d, F.conv_transpose2d
+        c, ct = self._conv, self._convT
+
+        def r(t):
+            return t.to(torch.bfloat16).to(t.dtype)
+        F.conv2d = lambda inp, w, b=None, **kw: c(r(inp), r(w), b, **kw)
+        F.conv_transpose2d = lambda inp, w, b=None, **kw: ct(r(inp), r(w), b, **kw)
+        return self
+
+    def __exit__(self, *a):
+        F.conv2d, F.conv_transpose2d = self._conv, self._convT
+
+
+def init_state_dict(cfg=None, seed=42, l2_hidden=None):
+    """Seed-`seed` initial weights of the reference WITHOUT importing it (or the product): plain torch.nn modules
+    created in the reference's construction order (src/model.py:358-408 encoder, :502-550 decoder, :609-632
+    AutoencoderKL; src/model_with_l2.py:19-40 head), so the global RNG is consumed exactly as `seed_all(seed);
+    get_model(...)` consumes it. Checked bit for bit against the real reference in tests/test_oracle_cpu.py."""
+    import torch.nn as nn
+    cfg = cfg or DEFAULT_CFG
+    torch.manual_seed(seed)
+    sd = {}
+
+    def conv(name, cin, cout, k=3, zero=False, transposed=False, bias=True):
+        m = (nn.ConvTranspose2d if transposed else nn.Conv2d)(cin, cout, kernel_size=k, stride=(2 if k == 2 else 1),
+                                                              padding=(1 if k == 3 else 0), bias=bias)
+        sd[name + ".weight"] = torch.zeros_like(m.weight) if zero else m.weight.detach().clone()
+        if bias:
+            sd[name + ".bias"] = torch.zeros_like(m.bias) if zero else m.bias.detach().clone()
+
+    def norm(name, c):
+        sd[name + ".weight"], sd[name + ".bias"] = torch.ones(c), torch.zeros(c)
+
+    def res(pre, cin, cout):
+        norm(pre + ".net1.0", cin); conv(pre + ".net1.2", cin, cout)
+        norm(pre + ".net2.0", cout); conv(pre + ".net2.2", cout, cout, zero=True)
+        if cin != cout:
+            conv(pre + ".skip_conv", cin, cout, k=1)
+
+    def attn(pre, c):
+        norm(pre + ".norm", c)
+        for n in ("q", "k", "v", "proj_out"):
+            conv(f"{pre}.{n}", c, c, k=1)
+
+    C, size = cfg["shape"][0], cfg["shape"][1]
+    chs, nres = cfg["chs"], cfg["num_res_blocks"]
+    zc = cfg["z_channels"]
+    sd["vae.logvar"] = None                                       # placeholder: keeps the reference's key order
+    e = "vae.encoder"
+    conv(e + ".conv_in", C, chs[0])
+    cur, cin = size, chs[0]
+    for i, cout in enumerate(chs):
+        cin = chs[0] if i == 0 else chs[i - 1]
+        for j in range(nres):
+            res(f"{e}.downs.{i}.resnet_blocks.{j}", cin, cout)
+            if cur in cfg["attn_sizes"]:
+                attn(f"{e}.downs.{i}.attention_blocks.{j}", cout)
+            cin = cout
+        conv(f"{e}.downs.{i}.down", cout, cout, k=2)
+        cur //= 2
+    res(e + ".mid1", cin, cin)
+    if cfg["mid_attn"]:
+        attn(e + ".mid_attn1", cin)
+    res(e + ".mid2", cin, cin)
+    norm(e + ".norm_out", cin)
+    conv(e + ".conv_out", cin, 2 * zc if cfg["double_z"] else zc, zero=True)
+    d = "vae.decoder"
+    cin = chs[-1]
+    conv(d + ".conv_in", zc, cin)
+    res(d + ".mid1", cin, cin)
+    if cfg["mid_attn"]:
+        attn(d + ".mid_attn1", cin)
+    res(d + ".mid2", cin, cin)
+    cur = size // 2 ** (len(chs) - 1)
+    for n, i in enumerate(reversed(range(len(chs)))):
+        cin = chs[i]
+        for j in range(nres):
+            res(f"{d}.ups.{n}.resnet_blocks.{j}", cin, cin)
+            if cur in cfg["attn_sizes"]:
+                attn(f"{d}.ups.{n}.attention_blocks.{j}", cin)
+        cout = chs[0] if i == 0 else chs[i - 1]
+        conv(f"{d}.ups.{n}.up", cin, cout, k=2, transposed=True)
+        cur //= 2
+    norm(d + ".norm_out", cout)
+    conv(d + ".conv_out", cout, C, zero=True)
+    conv("vae.quant_conv", 2 * zc, 2 * cfg["embed_dim"], k=1)
+    conv("vae.post_quant_conv", cfg["embed_dim"], zc, k=1)
+    sd["vae.logvar"] = torch.tensor(6.0)
+    if l2_hidden is not None:
+        cin = cfg["embed_dim"]
+        idx = 0
+        for h in l2_hidden:
+            conv(f"l2_head.mlp.{idx}", cin, h, k=1, bias=False)
+            norm(f"l2_head.mlp.{idx + 1}", h)
+            idx += 3
+            cin = h
+        conv(f"l2_head.mlp.{idx}", cin, 4, k=1)
+    return sd
+
+
+# ------------------------------------------------------------------------------------------------ data preparation
+def normalize_radiance(rad, mean_spectrum, std_spectrum, min_radiance=1.0, clip_min=-10.0, clip_max=10.0):
+    """log -> z-score -> clip (src/scripts/prepare_tempo_tiles.py:69-83)."""
+    log_rad = torch.log(torch.clamp(rad, min_radiance, float("inf")))
+    return torch.clamp((log_rad - mean_spectrum) / (std_spectrum + 1e-8), clip_min, clip_max)
+
+
+def extract_tiles(z_rad, tile_size, n_tiles, seed=None):
+    """Random crop + flip(dims=[0]) + flip(dims=[1]) + rot90(k, dims=[0,1]), numpy draws in the reference's order
+    (src/scripts/prepare_tempo_tiles.py:21-58). Returns (tiles [n, T, T, C], specs [n, 4])."""
+    import numpy as np
+    if seed is not None:
+        np.random.seed(seed)
+    n_mirror, n_track, _ = z_rad.shape
+    tm, tt = tile_size
+    if n_mirror < tm or n_track < tt:
+        return None, None
+    tiles, specs = [], []
+    for _ in range(n_tiles):
+        i = np.random.randint(0, n_mirror - tm + 1)
+        j = np.random.randint(0, n_track - tt + 1)
+        tile = z_rad[i:i + tm, j:j + tt].clone()
+        f0 = np.random.rand() > 0.5
+        if f0:
+            tile = torch.flip(tile, dims=[0])
+        f1 = np.random.rand() > 0.5
+        if f1:
+            tile = torch.flip(tile, dims=[1])
+        k = np.random.randint(0, 4)
+        if k > 0:
+            tile = torch.rot90(tile, k, dims=[0, 1])
+        tiles.append(tile)
+        specs.append((i, j, int(f0) | (int(f1) << 1), k))
+    return torch.stack(tiles), specs
+
+
+def spectrum_statistics(rads, min_radiance=1.0):
+    """Per-channel mean / population std of log(clip(rad, min_radiance)) over the stacked pixels of all granules, in
+    numpy like src/scripts/compute_tempo_stats.py:58-86. Returns (mean, std) as float32 torch tensors."""
+    import numpy as np
+    allp = np.vstack([np.log(np.clip(r.numpy(), min_radiance, None)).reshape(-1, r.shape[-1]) for r in rads])
+    return (torch.from_numpy(allp.mean(axis=0).astype(np.float32)), torch.from_numpy(allp.std(axis=0).astype(np.float32)))

@@ -103,6 +103,13 @@ def _load():
         "tvae_sumsq_workspace_bytes": (i64, [i64]),
         "tvae_sumsq": (i32, [vp, i64, vp, vp, vp]),
         "tvae_adamw": (i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i64, vp, f32, f32, vp]),
+        "tvae_gather_rows": (i32, [vp, i64, i64, vp, i32, vp, vp]),
+        "tvae_extract_tiles": (i32, [vp, i32, i32, i32, vp, i32, i32, vp, vp, f32, f32, f32, vp, vp, i32, vp]),
+        "tvae_spectrum_stats_workspace_bytes": (i64, [i64, i32]),
+        "tvae_spectrum_stats_accum": (i32, [vp, i64, i32, f32, i32, vp, vp, vp]),
+        "tvae_spectrum_stats_finalize": (i32, [vp, i64, i32, vp, vp, vp]),
+        "tvae_batch_stats_workspace_bytes": (i64, []),
+        "tvae_batch_stats": (i32, [vp, i32, i64, i64, i64, vp, vp, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol

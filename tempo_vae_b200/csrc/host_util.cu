@@ -32,7 +32,8 @@ int num_sms() {
 // Thread/context binding. PyTorch's autograd worker threads set their CUDA device lazily, so an entry point can be
 // called on a thread that has NO current context yet; this library's (statically linked) runtime would then bind
 // device 0. Every entry point therefore calls enter(ptr): if the thread has no current context it binds the primary
-// context of the device that owns `ptr` (a device pointer argument). It never switches an already-bound thread.
+// context of the device that owns `ptr` (a device pointer argument). It never switches an already-bound thread; if that
+// thread's current device is not the one that owns `ptr`, the call is refused with an error.
 typedef CUresult (*ctx_get_current_fn)(CUcontext*);
 typedef CUresult (*ptr_get_attr_fn)(void*, CUpointer_attribute, CUdeviceptr);
 
@@ -54,7 +55,20 @@ int enter(const void* device_ptr) {
   });
   if (!get_cur || !get_attr) return 0;  // cannot check: rely on the caller's thread state
   CUcontext cur = nullptr;
-  if (get_cur(&cur) == CUDA_SUCCESS && cur != nullptr) return 0;
+  if (get_cur(&cur) == CUDA_SUCCESS && cur != nullptr) {
+    // Bound thread: the launch goes to the thread's current device. A pointer that lives on ANOTHER device would
+    // fault inside the kernel (sticky error, dead process); refuse the call instead. The library still never
+    // switches the device -- the caller does (tempo_vae_b200/ops.py: _on_device).
+    int ord = -1, dev = -1;
+    if (device_ptr != nullptr &&
+        get_attr(&ord, CU_POINTER_ATTRIBUTE_DEVICE_ORDINAL, reinterpret_cast<CUdeviceptr>(device_ptr)) == CUDA_SUCCESS &&
+        ord >= 0 && cudaGetDevice(&dev) == cudaSuccess && dev != ord) {
+      set_error("operand %p lives on CUDA device %d but the calling thread's current device is %d: make the "
+                "operand's device current before calling (cudaSetDevice / torch.cuda.device)", device_ptr, ord, dev);
+      return -1;
+    }
+    return 0;
+  }
   int ordinal = -1;
   if (device_ptr == nullptr ||
       get_attr(&ordinal, CU_POINTER_ATTRIBUTE_DEVICE_ORDINAL, reinterpret_cast<CUdeviceptr>(device_ptr)) != CUDA_SUCCESS ||

@@ -52,11 +52,17 @@ def encode_patches(model, patches: torch.Tensor, batch_size: int = 256, rank: in
     host (each chunk is copied over) or on the device."""
     vae = model.vae if hasattr(model, "vae") else model
     dev = device or next(vae.parameters()).device
+    from .model import ENGINE
     mine = patches[rank::world]
     outs = []
-    for i in range(0, mine.shape[0], batch_size):
-        chunk = mine[i:i + batch_size].to(dev, dtype=torch.float32, non_blocking=True)
-        outs.append(vae.encode(chunk).mean)
+    with ENGINE.frozen_weights():          # weights do not change inside the sweep: pack them once, not per batch
+        for i in range(0, mine.shape[0], batch_size):
+            chunk = mine[i:i + batch_size]
+            if chunk.dtype != torch.bfloat16:          # bf16 channels-last views (tile stores) are consumed in place
+                chunk = chunk.to(dev, dtype=torch.float32, non_blocking=True)
+            elif chunk.device != dev:
+                chunk = chunk.to(dev, non_blocking=True)
+            outs.append(vae.encode(chunk).mean)
     if not outs:
         Z = vae.embed_dim
         return torch.empty((0, Z, 0, 0), device=dev)
@@ -88,6 +94,7 @@ def evaluate_reconstruction(model, x: torch.Tensor, eps: Optional[torch.Tensor] 
     C, Z = vae.encoder.in_channels, vae.embed_dim
     _check_input(x, C)
     B = x.shape[0]
+    ENGINE.begin_forward()
     xb = ops.input_nhwc_bf16(x)
     mom, _ = _EncodeProgram(vae).program_fwd(xb, False)
     if not sample_posterior:

@@ -53,9 +53,34 @@ class _Engine:
         # launch per pack, on first use)
         self.batched_packing = os.environ.get("TVAE_BATCHED_PACKING", "1") != "0"
         self._packs = []
+        # Weight packs are refreshed at the start of EVERY top-level forward (one batched launch, 0.34 ms): writes that
+        # autograd cannot see (`p.data.copy_(ema)`, `nn.init.*_(p.data)`, weight surgery) are honoured like the
+        # reference's modules, which read the live parameter on every call. `frozen_weights()` opts a sweep out.
+        self.forward_serial = 0
+        self._frozen = 0
 
     def params_changed(self):
+        """Public: marks every bf16 weight pack stale (called by FusedAdamW.step, load_state_dict paths, set_precision).
+        Not needed after ordinary `.data` writes between forwards -- see forward_serial."""
         self.param_epoch += 1
+
+    def begin_forward(self):
+        if not self._frozen:
+            self.forward_serial += 1
+
+    def frozen_weights(self):
+        """Context manager for inference sweeps: packs are refreshed once on entry, then assumed unchanged."""
+        import contextlib
+
+        @contextlib.contextmanager
+        def cm():
+            self.forward_serial += 1
+            self._frozen += 1
+            try:
+                yield
+            finally:
+                self._frozen -= 1
+        return cm()
 
     def register_pack(self, module, mode, ent):
         import weakref
@@ -74,7 +99,7 @@ class _Engine:
             w = mod.weight
             if w.device != device or ent.data.device != device or not w.is_contiguous():
                 continue
-            key = (w.data_ptr(), w._version, self.param_epoch, False)
+            key = (w.data_ptr(), w._version, self.param_epoch, self.forward_serial, False)
             if ent.version != key:
                 items.append((w.detach(), mode, ent))
                 keys.append((ent, key))
@@ -146,12 +171,15 @@ def _grad_done(p):
         hook(p)
 
 
-def _write_grad(p, fn):
-    """fn(dst) overwrites dst with the gradient of p; handles autograd's accumulate-into-.grad semantics."""
+def _write_grad(p, fn, native_accumulate=False):
+    """fn(dst) overwrites dst with the gradient of p; handles autograd's accumulate-into-.grad semantics (micro-batch
+    accumulation: bench.py --global-batch). native_accumulate: fn(dst, accumulate) can add in place itself."""
     if not p.requires_grad:
         return
     g, acc = _grad_begin(p)
-    if acc:
+    if native_accumulate:
+        fn(g, acc)
+    elif acc:
         tmp = torch.empty_like(g)
         fn(tmp)
         g.add_(tmp)
@@ -175,7 +203,7 @@ class _PackedMixin:
     def packed(self, mode):
         packs = self.__dict__.setdefault("_packs", {})
         w = self.weight
-        key = (w.data_ptr(), w._version, ENGINE.param_epoch, ops.SPLIT_BF16[0])
+        key = (w.data_ptr(), w._version, ENGINE.param_epoch, ENGINE.forward_serial, ops.SPLIT_BF16[0])
         ent = packs.get(mode)
         if ent is None or ent.data.device != w.device:
             ent = ops.pack_weight(w, mode)
@@ -328,24 +356,24 @@ def conv_bwd(mod, dy_bf16, x_bf16, Cin, *, dgrad=None, dgrad_residual=None, bias
     if dgrad is not None:       # data gradient first: it is on the critical path, the weight gradient is not
         dx = _conv_dgrad(mod, kind, R, Cin, Cout, dy_bf16, dgrad, dgrad_residual)
     if w.requires_grad:
-        def wg(dst):
+        def wg(dst, acc):
             if kind == 2:   # ConvTranspose2d [Cin][Cout][2][2]: P = x (coarse), Q = dy (fine)
-                ops.wgrad_gemm(x_bf16, Cin, dy_bf16, Cout, kind=1, R=2, grad=dst)
+                ops.wgrad_gemm(x_bf16, Cin, dy_bf16, Cout, kind=1, R=2, grad=dst, accumulate=acc)
             elif kind == 0 and Cin > 256 and Cin % 256 and Cout % 128 == 0:
                 # a wide, awkward channel count (1028) goes on the GEMM's M side: operand roles exchanged. (Measured:
                 # the opposite choice, N = 1028 as 5 tiles of 208, pads less (1.2 % vs 12 %) but is 3 ms per launch
                 # SLOWER: a 208-wide tile still stages 256 channels per K block, and the kernel is operand-bound.)
-                ops.wgrad_gemm(x_bf16, Cin, dy_bf16, Cout, kind=0, R=R, grad=dst, flip=True)
+                ops.wgrad_gemm(x_bf16, Cin, dy_bf16, Cout, kind=0, R=R, grad=dst, flip=True, accumulate=acc)
             else:
-                ops.wgrad_gemm(dy_bf16, Cout, x_bf16, Cin, kind=kind, R=R, grad=dst)
+                ops.wgrad_gemm(dy_bf16, Cout, x_bf16, Cin, kind=kind, R=R, grad=dst, accumulate=acc)
         if ENGINE.wgrad_overlap:
             side = ENGINE.side_stream(dy_bf16.device)
             with torch.cuda.stream(side):
-                _write_grad(w, wg)
+                _write_grad(w, wg, native_accumulate=True)
             dy_bf16.record_stream(side)       # the caching allocator must not recycle the operands early
             x_bf16.record_stream(side)
         else:
-            _write_grad(w, wg)
+            _write_grad(w, wg, native_accumulate=True)
     if mod.bias is not None and mod.bias.requires_grad:
         if bias_grad_from is None:
             bias_grad_from = getattr(dy_bf16, "tvae_colsum", None)     # produced together with dy (norm_act_bwd)
@@ -884,6 +912,7 @@ class _ModuleFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, mod, *params):
         _check_input(x, mod.in_channels_api())
+        ENGINE.begin_forward()
         save = any(ctx.needs_input_grad)
         xb = ops.input_nhwc_bf16(x)
         out, saved = mod.program_fwd(xb, save)
@@ -975,6 +1004,7 @@ class _VAELossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, eps, vae, extra, *params):
         _check_input(x, vae.encoder.in_channels)
+        ENGINE.begin_forward()
         B = x.shape[0]
         train = any(ctx.needs_input_grad)
         C = vae.encoder.in_channels

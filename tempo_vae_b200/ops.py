@@ -5,6 +5,7 @@ libtvae_b200.so on torch's current CUDA stream. Activations are NHWC tensors `[N
 fp32 residual stream); `C` (the number of valid channels, <= pitch) travels next to them.
 """
 import ctypes as C
+import functools
 import os
 
 import torch
@@ -15,7 +16,35 @@ from ._lib import check as _check
 
 
 def _stream():
+    """Current stream of the CURRENT device; every tensor-taking wrapper below runs under `_on_device`, which makes the
+    device that owns its operands current for the duration of the call (the C ABI launches on the calling thread's
+    current device and never switches it)."""
     return torch.cuda.current_stream().cuda_stream
+
+
+def _device_of(args):
+    for a in args:
+        if torch.is_tensor(a):
+            if a.is_cuda:
+                return a.device
+        elif isinstance(a, Pair):
+            return a.hi.device
+        elif isinstance(a, (list, tuple)) and a and isinstance(a[0], tuple) and torch.is_tensor(a[0][0]):
+            return a[0][0].device                    # pack_weights_batched(items)
+    return None
+
+
+def _on_device(fn):
+    """Run `fn` with the device of its first CUDA tensor argument current (no-op when it already is). The reference's
+    torch ops work from any current device (`model.to('cuda:3')` while the current device is 0); so must these."""
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        dev = _device_of(args)
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return wrapper
 
 
 def check(rc, what):
@@ -29,6 +58,21 @@ PROFILE = {}
 
 KERNEL_LAUNCHES = [0]   # kernels of libtvae_b200.so enqueued through this module (bench.py reports the delta)
 
+
+def _timed(name, nbytes, call):
+    """bench.py hook for the HBM-bound kernels: PROFILE["hbm"] = {"min_bytes": n, "events": {}} brackets every call
+    whose ALGORITHMIC byte count (operands read once + results written once) is at least min_bytes with CUDA events
+    on the launching stream and records (start, stop, bytes) under `name`."""
+    prof = PROFILE.get("hbm")
+    if prof is None or nbytes < prof.get("min_bytes", 0):
+        return call()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    r = call()
+    e1.record()
+    prof["events"].setdefault(name, []).append((e0, e1, nbytes))
+    return r
+
 # kernels launched by one call of each C-ABI entry point
 _KERNELS_PER_CALL = {
     "tvae_pack_weight": 1, "tvae_pack_weights_batched": 1, "tvae_conv_gemm": 1, "tvae_wgrad_gemm": 2, "tvae_nchw_f32_to_nhwc_bf16": 1,
@@ -36,6 +80,8 @@ _KERNELS_PER_CALL = {
     "tvae_gn_act_fwd": 1, "tvae_gn_stats_finalize": 1, "tvae_gn_act_bwd": 4, "tvae_colsum_bf16": 2, "tvae_attn_fwd": 1, "tvae_attn_bwd": 2, "tvae_attn_fwd_tc": 1, "tvae_attn_bwd_tc": 2,
     "tvae_reparam_fwd": 1, "tvae_reparam_bwd": 1, "tvae_nll_fwd": 2, "tvae_vae_loss_finalize": 1,
     "tvae_l2head_loss_fwd": 1, "tvae_l2head_loss_bwd": 1, "tvae_l2head_finalize": 1, "tvae_sumsq": 2, "tvae_adamw": 1,
+    "tvae_gather_rows": 1, "tvae_extract_tiles": 1, "tvae_spectrum_stats_accum": 2, "tvae_spectrum_stats_finalize": 1,
+    "tvae_batch_stats": 2,
 }
 
 
@@ -138,6 +184,7 @@ def pack_geometry(shape, mode):
     raise ValueError(mode)
 
 
+@_on_device
 def pack_weight(w, mode, out=None):
     require_cuda(w, "weight")
     g = pack_geometry(tuple(w.shape), mode)
@@ -165,6 +212,7 @@ class PackDesc(C.Structure):      # tvae_pack_desc
 _pack_tables = {}      # signature of (weight ptr, pack ptr, mode) triples -> (descs tensor, block_start tensor, n, total)
 
 
+@_on_device
 def pack_weights_batched(items):
     """items: list of (weight parameter, mode, PackedWeight). Rebuilds every pack with ONE kernel launch
     (tvae_pack_weights_batched). The descriptor table lives on the device and is reused while the pointers stay the
@@ -205,6 +253,7 @@ def fused_stats_ok(N, oH, oW, Cout, G, kind, H, W):
         and bn // gs <= 16 and grid % 128 == 0
 
 
+@_on_device
 def conv_gemm(x, C_in, wp, *, kind, R, Cout, flip=False, bias=None, residual=None, want_f32=True, want_bf16=False,
               bf16_pitch=None, bn=0, out_f32=None, out_bf16=None, stats=None, split_out=True):
     """x: bf16 [N,H,W,pitch]. Returns (out_f32 or None, out_bf16 or None) as NHWC tensors; with stats=(G, eps) the
@@ -284,6 +333,7 @@ def _workspace(nbytes, device, key="ws"):
     return buf
 
 
+@_on_device
 def wgrad_gemm(p, Cm, q, Cn, *, kind, R, grad, accumulate=False, splits=0, flip=False):
     """grad[m][n][tap] (+)= sum_pixels p[pixel][m] * q[pixel (+) tap][n]; p: bf16 [N,H,W,pitch] (the dense grid).
     flip=True (stride-1 only): p = x, q = dY read at pixel (-) tap, grad written as [n][m][tap] (see include/tvae.h)."""
@@ -317,6 +367,7 @@ def wgrad_gemm(p, Cm, q, Cn, *, kind, R, grad, accumulate=False, splits=0, flip=
 
 
 # ----------------------------------------------------------------------------------------------- layout
+@_on_device
 def nchw_to_nhwc_bf16(x, pitch=None):
     require_cuda(x, "input")
     N, Cc, H, W = x.shape
@@ -326,11 +377,13 @@ def nchw_to_nhwc_bf16(x, pitch=None):
         x = x.float()
     out = torch.empty((N, H, W, pitch), dtype=torch.bfloat16, device=x.device)
     lo = _lo_like(out)
-    check(lib.tvae_nchw_f32_to_nhwc_bf16(x.data_ptr(), out.data_ptr(), N, Cc, H * W, pitch, _ptr(lo), _stream()),
-          "tvae_nchw_f32_to_nhwc_bf16")
+    _timed("nchw_to_nhwc_bf16", N * Cc * H * W * 6,
+           lambda: check(lib.tvae_nchw_f32_to_nhwc_bf16(x.data_ptr(), out.data_ptr(), N, Cc, H * W, pitch, _ptr(lo),
+                                                        _stream()), "tvae_nchw_f32_to_nhwc_bf16"))
     return _pair(out, lo)
 
 
+@_on_device
 def input_nhwc_bf16(x):
     """The engine's bf16 channels-last operand for an NCHW-SHAPED input tensor [N, C, H, W], whatever its memory
     layout: (a) bf16 with channels-last strides and a row pitch that is a multiple of 8 (what DeviceTileCache
@@ -354,6 +407,7 @@ def input_nhwc_bf16(x):
     return nchw_to_nhwc_bf16(x)
 
 
+@_on_device
 def normalize_radiance(rad, mean, std, min_radiance, clip_min, clip_max, want_f32=True, want_bf16=False):
     """rad [..., C] fp32 on the device -> (z fp32 [..., C] or None, z bf16 [..., pitch] operand rows or None)."""
     require_cuda(rad, "radiance")
@@ -373,6 +427,7 @@ def normalize_radiance(rad, mean, std, min_radiance, clip_min, clip_max, want_f3
     return zf, zb
 
 
+@_on_device
 def nhwc_to_nchw_f32(x, Cc):
     x = hi_of(x)
     N, H, W, pitch = x.shape
@@ -386,6 +441,7 @@ def nhwc_to_nchw_f32(x, Cc):
     return out
 
 
+@_on_device
 def f32_to_bf16(x):
     out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
     lo = _lo_like(out)
@@ -394,6 +450,7 @@ def f32_to_bf16(x):
 
 
 # ----------------------------------------------------------------------------------------------- GroupNorm
+@_on_device
 def gn_stats(x, Cc, G, eps):
     N, H, W, pitch = x.shape
     assert pitch == Cc and x.dtype == torch.float32
@@ -410,18 +467,21 @@ def gn_fast_ok(Cc, G):
     return 1 <= U <= 256 and 256 % U == 0 and 256 % (Cc // G // 8) == 0
 
 
+@_on_device
 def gn_act_fwd(x, stats, gamma, beta, G, act):
     """x: the GroupNorm input, dense NHWC, fp32 or bf16 (see tvae_gn_act_fwd)."""
     N, H, W, Cc = x.shape
     assert x.is_contiguous() and x.dtype in (torch.float32, torch.bfloat16)
     out = torch.empty((N, H, W, Cc), dtype=torch.bfloat16, device=x.device)
     lo = _lo_like(out)
-    check(lib.tvae_gn_act_fwd(x.data_ptr(), int(x.dtype == torch.bfloat16), stats.data_ptr(), gamma.data_ptr(),
-                              beta.data_ptr(), N, H * W, Cc, G, int(act), out.data_ptr(), _ptr(lo), _stream()),
-          "tvae_gn_act_fwd")
+    _timed("gn_act_fwd", x.numel() * (x.element_size() + 2),
+           lambda: check(lib.tvae_gn_act_fwd(x.data_ptr(), int(x.dtype == torch.bfloat16), stats.data_ptr(),
+                                             gamma.data_ptr(), beta.data_ptr(), N, H * W, Cc, G, int(act),
+                                             out.data_ptr(), _ptr(lo), _stream()), "tvae_gn_act_fwd"))
     return _pair(out, lo)
 
 
+@_on_device
 def gn_act_bwd(x, stats, gamma, beta, da, gres, G, act, dgamma, dbeta, dx_colsum=None):
     """dx_colsum (optional fp32 [C]): receives the column sums of dx (= bias gradient of the conv that produced x)."""
     N, H, W, Cc = x.shape
@@ -430,14 +490,18 @@ def gn_act_bwd(x, stats, gamma, beta, da, gres, G, act, dgamma, dbeta, dx_colsum
     dx = torch.empty((N, H, W, Cc), dtype=torch.bfloat16, device=x.device)
     ws = _workspace(lib.tvae_gn_bwd_workspace_bytes(N, H * W, Cc, G), x.device, "gn")
     assert x.is_contiguous() and x.dtype in (torch.float32, torch.bfloat16)
-    check(lib.tvae_gn_act_bwd(x.data_ptr(), int(x.dtype == torch.bfloat16), stats.data_ptr(), gamma.data_ptr(),
-                              beta.data_ptr(), da.data_ptr(), _ptr(gres), N, H * W, Cc, G, int(act), dx.data_ptr(), dgamma.data_ptr(),
-                              dbeta.data_ptr(), _ptr(dx_colsum), ws.data_ptr(), _stream()), "tvae_gn_act_bwd")
+    # algorithmic bytes of ONE pass: x + da (+ the residual-branch gradient) read, dx written
+    _timed("gn_act_bwd", x.numel() * (x.element_size() + 2 + (2 if gres is not None else 0) + 2),
+           lambda: check(lib.tvae_gn_act_bwd(x.data_ptr(), int(x.dtype == torch.bfloat16), stats.data_ptr(),
+                                             gamma.data_ptr(), beta.data_ptr(), da.data_ptr(), _ptr(gres), N, H * W, Cc,
+                                             G, int(act), dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(),
+                                             _ptr(dx_colsum), ws.data_ptr(), _stream()), "tvae_gn_act_bwd"))
     if dx_colsum is not None:
         KERNEL_LAUNCHES[0] += 2
     return dx
 
 
+@_on_device
 def colsum_bf16(x, Cc, out):
     x = hi_of(x)
     rows = x.numel() // x.shape[-1]
@@ -454,6 +518,7 @@ def attn_uses_tensor_cores(Cc, heads):
     return ATTN_TENSOR_CORES[0] and not SPLIT_BF16[0] and Cc == 32 * heads
 
 
+@_on_device
 def attn_fwd(qkv, Cc, heads, B, T):
     """qkv: fp32 [B*T (any leading shape), 3C]. Returns (o_bf16, o_f32, lse)."""
     pitch = qkv.shape[-1]
@@ -473,6 +538,7 @@ def attn_fwd(qkv, Cc, heads, B, T):
     return o_bf16, o_f32, lse
 
 
+@_on_device
 def attn_bwd(qkv, o_f32, d_out, lse, Cc, heads, B, T):
     pitch = qkv.shape[-1]
     dev = qkv.device
@@ -487,6 +553,7 @@ def attn_bwd(qkv, o_f32, d_out, lse, Cc, heads, B, T):
 
 
 # ----------------------------------------------------------------------------------------------- latent / losses
+@_on_device
 def reparam_fwd(moments, Z, *, eps=None, seed=0, sample_offset=0, want_z_nchw=False, z_pitch=None):
     """moments: fp32 [B,h,w,2Z]. Returns (z_bf16 [B,h,w,z_pitch], z_nchw or None, eps_nchw, kl[B])."""
     B, h, w, _ = moments.shape
@@ -508,6 +575,7 @@ def reparam_fwd(moments, Z, *, eps=None, seed=0, sample_offset=0, want_z_nchw=Fa
     return _pair(z_bf16, z_lo), z_nchw, (eps if eps is not None else eps_out), kl
 
 
+@_on_device
 def reparam_bwd(moments, Z, dz1, eps1, dz2, eps2, kl_scale):
     B, h, w, _ = moments.shape
     dm = torch.empty((B, h, w, 2 * Z), dtype=torch.bfloat16, device=moments.device)
@@ -516,6 +584,7 @@ def reparam_bwd(moments, Z, dz1, eps1, dz2, eps2, kl_scale):
     return dm
 
 
+@_on_device
 def nll_fwd(x_bf16, xhat, Cc, loss_type, logvar, batch, want_grad):
     """x_bf16 [N,H,W,xp] bf16; xhat [N,H,W,hp] fp32. Returns (sums fp64[3], dxhat bf16 or None); dxhat carries its
     column sums (the bias gradient of the conv that produced xhat) as `dxhat.tvae_colsum`."""
@@ -528,15 +597,17 @@ def nll_fwd(x_bf16, xhat, Cc, loss_type, logvar, batch, want_grad):
     if want_grad:
         dx = torch.empty(x_bf16.shape[:-1] + (round_up(Cc, 8),), dtype=torch.bfloat16, device=dev)
         cs = torch.empty((Cc,), dtype=torch.float32, device=dev)
-    check(lib.tvae_nll_fwd(x_bf16.data_ptr(), pitch_of(x_bf16), xhat.data_ptr(), pitch_of(xhat), P, Cc, loss_type,
-                           _ptr(logvar), batch, _ptr(dx), dx.shape[-1] if dx is not None else 0, _ptr(cs),
-                           sums.data_ptr(), ws.data_ptr(), _stream()), "tvae_nll_fwd")
+    _timed("nll_fwd", P * Cc * (2 + 4 + (2 if dx is not None else 0)),
+           lambda: check(lib.tvae_nll_fwd(x_bf16.data_ptr(), pitch_of(x_bf16), xhat.data_ptr(), pitch_of(xhat), P, Cc,
+                                          loss_type, _ptr(logvar), batch, _ptr(dx), dx.shape[-1] if dx is not None else 0,
+                                          _ptr(cs), sums.data_ptr(), ws.data_ptr(), _stream()), "tvae_nll_fwd"))
     if dx is not None:
         dx.tvae_colsum = cs
         KERNEL_LAUNCHES[0] += 1
     return sums, dx
 
 
+@_on_device
 def recon_metrics(x_bf16, xhat, Cc):
     """x_bf16 [N,H,W,xp] bf16, xhat [N,H,W,hp] fp32 -> fp32 [N, 2] = per-sample (MAE, MSE)."""
     x_bf16 = hi_of(x_bf16)
@@ -548,6 +619,7 @@ def recon_metrics(x_bf16, xhat, Cc):
     return out
 
 
+@_on_device
 def vae_loss_finalize(sums, kl, logvar, n_elem, kl_weight):
     """Returns fp32[5] = (loss, nll_loss, kl_loss, pixel_mse, dloss/dlogvar) on the device."""
     out = torch.empty((5,), dtype=torch.float32, device=kl.device)
@@ -563,6 +635,7 @@ def _target_array(targets):
     return arr
 
 
+@_on_device
 def l2head_loss_fwd(pred, targets, B, h, w):
     sums = torch.empty((len(targets), 2), dtype=torch.float64, device=pred.device)
     check(lib.tvae_l2head_loss_fwd(pred.data_ptr(), pred.shape[-1], _target_array(targets), len(targets), B, h, w,
@@ -570,6 +643,7 @@ def l2head_loss_fwd(pred, targets, B, h, w):
     return sums
 
 
+@_on_device
 def l2head_loss_bwd(pred, targets, B, h, w, sums, weights, grad_scale, dp_pitch=8):
     dpred = torch.empty((B, h, w, dp_pitch), dtype=torch.bfloat16, device=pred.device)
     check(lib.tvae_l2head_loss_bwd(pred.data_ptr(), pred.shape[-1], _target_array(targets), len(targets), B, h, w,
@@ -578,6 +652,7 @@ def l2head_loss_bwd(pred, targets, B, h, w, sums, weights, grad_scale, dp_pitch=
     return dpred
 
 
+@_on_device
 def l2head_finalize(sums, weights, vae_scal):
     out = torch.empty((1 + sums.shape[0],), dtype=torch.float32, device=sums.device)
     check(lib.tvae_l2head_finalize(sums.data_ptr(), weights.data_ptr(), sums.shape[0], vae_scal.data_ptr(),
@@ -586,11 +661,106 @@ def l2head_finalize(sums, weights, vae_scal):
 
 
 # ----------------------------------------------------------------------------------------------- optimiser
+@_on_device
 def sumsq(g, out):
     ws = _workspace(lib.tvae_sumsq_workspace_bytes(g.numel()), g.device, "sumsq")
     check(lib.tvae_sumsq(g.data_ptr(), g.numel(), out.data_ptr(), ws.data_ptr(), _stream()), "tvae_sumsq")
 
 
+@_on_device
 def adamw(p, g, m, v, *, lr, beta1, beta2, eps, weight_decay, step, sumsq_buf=None, max_norm=0.0, grad_scale=1.0):
-    check(lib.tvae_adamw(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, beta1, beta2, eps,
-                         weight_decay, step, _ptr(sumsq_buf), max_norm, grad_scale, _stream()), "tvae_adamw")
+    _timed("adamw", p.numel() * 28,
+           lambda: check(lib.tvae_adamw(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, beta1,
+                                        beta2, eps, weight_decay, step, _ptr(sumsq_buf), max_norm, grad_scale,
+                                        _stream()), "tvae_adamw"))
+
+
+# ----------------------------------------------------------------------------------------------- data side
+@_on_device
+def gather_rows(src, idx, out):
+    """out[j] = src[idx[j]] along dim 0 (contiguous rows, row bytes a multiple of 16); idx int64 on the device."""
+    assert src.is_contiguous() and out.is_contiguous() and idx.dtype == torch.int64 and idx.is_cuda
+    row_bytes = src[0].numel() * src.element_size() if src.dim() > 1 else src.element_size()
+    if row_bytes % 16:
+        raise _lib.TvaeError(f"gather_rows: rows of {row_bytes} bytes are not a multiple of 16")
+    n = idx.numel()
+    for i in range(0, n, 65535):
+        k = min(65535, n - i)
+        check(lib.tvae_gather_rows(src.data_ptr(), src.shape[0], row_bytes, idx.data_ptr() + 8 * i, k,
+                                   out.data_ptr() + i * row_bytes, _stream()), "tvae_gather_rows")
+    return out
+
+
+@_on_device
+def extract_tiles(rad, spec, T, mean=None, std=None, min_radiance=1.0, clip_min=-10.0, clip_max=10.0, want_f32=True,
+                  want_bf16=False, out_bf16=None):
+    """rad fp32 [M, NT, C] on the device; spec int32 [n, 4] = (row0, col0, flags, k) on the device. Returns
+    (tiles fp32 [n, T, T, C] or None, tiles bf16 [n, T, T, pitch] or None) -- see tvae_extract_tiles."""
+    require_cuda(rad, "radiance")
+    assert rad.is_contiguous() and rad.dtype == torch.float32 and rad.dim() == 3
+    assert spec.is_contiguous() and spec.dtype == torch.int32 and spec.dim() == 2 and spec.shape[1] == 4
+    M, NT, Cc = rad.shape
+    n = spec.shape[0]
+    if mean is not None:
+        mean = mean.to(rad.device, torch.float32).contiguous()
+        std = std.to(rad.device, torch.float32).contiguous()
+        if mean.numel() != Cc or std.numel() != Cc:
+            raise _lib.TvaeError(f"mean/std spectra must have {Cc} channels")
+    pitch = round_up(Cc, 8)
+    of = torch.empty((n, T, T, Cc), dtype=torch.float32, device=rad.device) if want_f32 else None
+    ob = out_bf16
+    if ob is not None:          # e.g. a slice of DeviceTileCache.data: tiles land in the cache without a staging copy
+        assert ob.is_contiguous() and ob.dtype == torch.bfloat16 and tuple(ob.shape[:3]) == (n, T, T)
+        pitch = ob.shape[3]
+    elif want_bf16:
+        ob = torch.empty((n, T, T, pitch), dtype=torch.bfloat16, device=rad.device)
+    check(lib.tvae_extract_tiles(rad.data_ptr(), M, NT, Cc, spec.data_ptr(), n, T, _ptr(mean), _ptr(std),
+                                 float(min_radiance), float(clip_min), float(clip_max), _ptr(of), _ptr(ob), pitch,
+                                 _stream()), "tvae_extract_tiles")
+    return of, ob
+
+
+@_on_device
+def spectrum_stats_accum(rad, acc, min_radiance=1.0, take_log=True):
+    """Adds the pixels of rad [..., C] (fp32, device) to the running fp64 sums acc [2, C]."""
+    require_cuda(rad, "radiance")
+    rad = rad.contiguous()
+    Cc = rad.shape[-1]
+    rows = rad.numel() // Cc
+    assert acc.dtype == torch.float64 and tuple(acc.shape) == (2, Cc) and acc.is_contiguous()
+    ws = _workspace(lib.tvae_spectrum_stats_workspace_bytes(rows, Cc), rad.device, "spectrum")
+    check(lib.tvae_spectrum_stats_accum(rad.data_ptr(), rows, Cc, float(min_radiance), int(take_log), acc.data_ptr(),
+                                        ws.data_ptr(), _stream()), "tvae_spectrum_stats_accum")
+    return rows
+
+
+@_on_device
+def spectrum_stats_finalize(acc, total_rows):
+    Cc = acc.shape[1]
+    mean = torch.empty((Cc,), dtype=torch.float32, device=acc.device)
+    std = torch.empty((Cc,), dtype=torch.float32, device=acc.device)
+    check(lib.tvae_spectrum_stats_finalize(acc.data_ptr(), int(total_rows), Cc, mean.data_ptr(), std.data_ptr(),
+                                           _stream()), "tvae_spectrum_stats_finalize")
+    return mean, std
+
+
+@_on_device
+def batch_stats(x):
+    """fp32[4] = (min, max, mean, unbiased std) of a device tensor: any contiguous fp32/bf16 tensor, or an NCHW-shaped
+    channels-last view (the bf16 batches of the tile stores; pad lanes are skipped)."""
+    require_cuda(x, "batch")
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        x = x.float()
+    if x.is_contiguous():
+        rows, Cc, pitch = 1, x.numel(), x.numel()
+    elif x.dim() == 4 and x.stride(1) == 1 and x.stride(2) == x.shape[3] * x.stride(3) \
+            and x.stride(0) == x.shape[2] * x.stride(2):
+        rows, Cc, pitch = x.shape[0] * x.shape[2] * x.shape[3], x.shape[1], x.stride(3)
+    else:
+        x = x.contiguous()
+        rows, Cc, pitch = 1, x.numel(), x.numel()
+    out = torch.empty((4,), dtype=torch.float32, device=x.device)
+    ws = _workspace(lib.tvae_batch_stats_workspace_bytes(), x.device, "batch_stats")
+    check(lib.tvae_batch_stats(x.data_ptr(), int(x.dtype == torch.bfloat16), rows, Cc, pitch, out.data_ptr(),
+                               ws.data_ptr(), _stream()), "tvae_batch_stats")
+    return out

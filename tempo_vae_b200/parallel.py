@@ -144,26 +144,39 @@ class DataParallel:
         B = x.shape[0]
         return self.model.get_loss(x, sample_offset=self.rank * B, global_batch=self.world * B, **kw)
 
-    def backward(self, loss):
+    def backward(self, loss, sync: bool = True):
+        """sync=False: a micro-batch that is not the last of its optimiser step -- gradients are only accumulated
+        into the flat buffer (no hooks, no collective); the all-reduce of the step runs, overlapped as usual, with the
+        backward of the LAST micro-batch, whose kernels add to the buffer that already holds the earlier ones."""
         eng = self.engine
         prev_hook, prev_unit = eng.grad_ready_hook, eng.unit_loss_grad
-        eng.grad_ready_hook, eng.unit_loss_grad = self.bucketer.ready, True
+        eng.grad_ready_hook, eng.unit_loss_grad = (self.bucketer.ready if sync else None), True
         try:
             loss.backward()
         finally:
             eng.grad_ready_hook, eng.unit_loss_grad = prev_hook, prev_unit
-        self.bucketer.finish()
+        if sync:
+            self.bucketer.finish()
 
-    def step(self, max_grad_norm: Optional[float] = 1.0):
-        self.optimizer.step(max_grad_norm=max_grad_norm, grad_scale=1.0 / self.world)
+    def step(self, max_grad_norm: Optional[float] = 1.0, micro_batches: int = 1):
+        self.optimizer.step(max_grad_norm=max_grad_norm, grad_scale=1.0 / (self.world * micro_batches))
 
     def train_step_device(self, x, max_grad_norm: Optional[float] = 1.0):
-        """zero_grad -> get_loss -> backward (+ overlapped all-reduce) -> fused clip + AdamW. Device metrics."""
+        """zero_grad -> get_loss -> backward (+ overlapped all-reduce) -> fused clip + AdamW. Device metrics.
+        x: this rank's batch, or a list of micro-batches (gradient accumulation: BASELINE config 4's global batch of
+        2048 at 2 / 4 GPUs is 4 / 2 micro-batches of 256 per rank; one all-reduce per optimiser step)."""
         self.model.train()
-        loss, metrics = self.get_loss(x)
+        xs = list(x) if isinstance(x, (list, tuple)) else [x]
         self.optimizer.zero_grad()
-        self.backward(loss)
-        self.step(max_grad_norm)
+        metrics = None
+        for i, xm in enumerate(xs):
+            loss, m = self.get_loss(xm)
+            self.backward(loss, sync=(i == len(xs) - 1))
+            m = {k: v.detach() for k, v in m.items()}
+            metrics = m if metrics is None else {k: metrics[k] + m[k] for k in m}
+        if len(xs) > 1:
+            metrics = {k: v / len(xs) for k, v in metrics.items()}
+        self.step(max_grad_norm, micro_batches=len(xs))
         return metrics
 
     def reduce_metrics(self, scalars: torch.Tensor) -> torch.Tensor:

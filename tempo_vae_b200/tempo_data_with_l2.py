@@ -13,7 +13,8 @@ import torch
 from torch.utils.data import DataLoader, IterableDataset
 from tqdm import tqdm
 
-from .tempo_data import RandomBuffer
+from . import ops
+from .tempo_data import RandomBuffer, epoch_shard
 
 L2_PRODUCTS = ('NO2', 'O3TOT', 'HCHO', 'CLDO4')
 
@@ -141,11 +142,13 @@ class DeviceTileCacheWithL2:
         g = torch.Generator().manual_seed(seed)
         epoch = 0
         while epochs is None or epoch < epochs:
-            perm = torch.randperm(sp.n, generator=g)[rank::world].to(sp.device)
-            for i in range(0, perm.numel() - batch_size + 1, batch_size):
+            perm = epoch_shard(torch.randperm(sp.n, generator=g), batch_size, rank, world).to(sp.device)
+            for i in range(0, perm.numel(), batch_size):
                 idx = perm[i:i + batch_size]
-                batch = {'spectral': torch.index_select(sp.data, 0, idx)[..., :sp.C].permute(0, 3, 1, 2)}
+                batch = {'spectral': sp.gather(idx)[..., :sp.C].permute(0, 3, 1, 2)}
                 for product, tg in self.targets.items():
-                    batch[product] = torch.index_select(tg, 0, idx)
+                    out = torch.empty((idx.numel(),) + tuple(tg.shape[1:]), dtype=tg.dtype, device=tg.device)
+                    ops.gather_rows(tg, idx, out)
+                    batch[product] = out
                 yield batch
             epoch += 1

@@ -46,9 +46,10 @@ def get_device() -> torch.device:
         raise RuntimeError("tempo_vae_b200 needs a CUDA device (B200, sm_100a); no CPU fallback exists")
     free = []
     for i in range(torch.cuda.device_count()):
-        with torch.cuda.device(i):
-            free.append((torch.cuda.mem_get_info()[0], i))
-    return torch.device(f"cuda:{max(free)[1]}")
+        free.append((torch.cuda.mem_get_info(i)[0], -i))       # ties go to the LOWEST index
+    best = -max(free)[1]
+    torch.cuda.set_device(best)       # the chosen GPU becomes the current device (kernels launch where the tensors live
+    return torch.device(f"cuda:{best}")   # either way -- ops._on_device -- but allocations default to it from here on)
 
 
 def get_sqrt_schedule(n_steps: int, n_saves: int = 100) -> List[int]:
@@ -60,6 +61,13 @@ def get_sqrt_schedule(n_steps: int, n_saves: int = 100) -> List[int]:
     return steps
 
 
+def _is_skipped_product(key: str, value: float) -> bool:
+    """A `<PRODUCT>_loss` that came back NaN marks an L2 product without a single valid pixel in the batch: the
+    reference emits NO key for it (src/model_with_l2.py:155-166), so neither do we -- a NaN would poison the running
+    means of Trainer.train and the sums of validate(), and put non-standard tokens into metrics.json."""
+    return key.endswith('_loss') and key not in ('loss', 'nll_loss', 'kl_loss') and value != value
+
+
 def _to_floats(metrics: Dict[str, object]) -> Dict[str, float]:
     """Device scalars -> python floats with a single synchronising copy."""
     keys = [k for k, v in metrics.items() if torch.is_tensor(v)]
@@ -67,7 +75,7 @@ def _to_floats(metrics: Dict[str, object]) -> Dict[str, float]:
     if keys:
         vals = torch.stack([metrics[k].detach().reshape(()).float() for k in keys]).tolist()
         out.update(dict(zip(keys, vals)))
-    return {k: out[k] for k in metrics}
+    return {k: out[k] for k in metrics if not _is_skipped_product(k, out[k])}
 
 
 class Trainer:
@@ -136,8 +144,9 @@ class Trainer:
         elif batch.device != self.device:
             batch = batch.to(self.device, non_blocking=True)
         if self.step == 0 and torch.is_grad_enabled():
-            print(f"Batch stats - min: {batch.min():.3f}, max: {batch.max():.3f}, "
-                  f"mean: {batch.mean():.3f}, std: {batch.std():.3f}")
+            from . import ops
+            mn, mx, mean, std = ops.batch_stats(batch).tolist()          # one fused reduction (tvae_batch_stats)
+            print(f"Batch stats - min: {mn:.3f}, max: {mx:.3f}, mean: {mean:.3f}, std: {std:.3f}")
         loss, metrics = self.model.get_loss(batch)
         return batch, loss, dict(metrics)
 
@@ -178,24 +187,56 @@ class Trainer:
         """Single training step (src/train_utils.py:149-183): returns python floats."""
         return _to_floats(self.train_step_device(batch))
 
+    def train_step_accumulate(self, batches) -> Dict[str, torch.Tensor]:
+        """One optimiser step over several micro-batches (gradient accumulation; the mean of the micro-batch losses is
+        what gets differentiated, so equal-sized micro-batches reproduce the step on their concatenation). Extension of
+        the reference API for global batches that do not fit one forward. Device metrics (means over micro-batches)."""
+        self.model.train()
+        if not isinstance(self.optimizer, FusedAdamW):
+            raise TypeError("train_step_accumulate needs the flat-buffer FusedAdamW optimiser")
+        batches = list(batches)
+        self.optimizer.zero_grad()
+        total = None
+        prev = ENGINE.unit_loss_grad
+        ENGINE.unit_loss_grad = True
+        try:
+            for b in batches:
+                _, loss, metrics = self._loss_and_metrics(b)
+                metrics['pixel_mse'] = self._vae().last_pixel_mse()
+                loss.backward()                       # adds into the flat gradient buffer (wgrad accumulates in place)
+                metrics = {k: (v.detach() if torch.is_tensor(v) else v) for k, v in metrics.items()}
+                total = metrics if total is None else {k: total[k] + v for k, v in metrics.items()}
+        finally:
+            ENGINE.unit_loss_grad = prev
+        self.optimizer.step(max_grad_norm=self.max_grad_norm, grad_scale=1.0 / len(batches))
+        return {k: v / len(batches) for k, v in total.items()}
+
     def validate(self, val_loader, n_batches: int = 10) -> Dict[str, float]:
         """Sample-weighted mean of get_loss metrics over n_batches, `val_` prefixed (src/train_utils.py:185-212)."""
         self.model.eval()
-        acc = {}
-        n_samples = 0
+        rows = []
         with torch.no_grad():
             for i, batch in enumerate(val_loader):
                 if i >= n_batches:
                     break
                 b, _, metrics = self._loss_and_metrics(batch)
                 bs = (b if torch.is_tensor(b) else b['spectral']).shape[0]
-                for k, v in metrics.items():
-                    v = v.detach().double() if torch.is_tensor(v) else torch.tensor(float(v), dtype=torch.float64)
-                    acc[k] = acc.get(k, 0) + v.to(self.device) * bs
-                n_samples += bs
-        if n_samples == 0:
+                rows.append((bs, metrics))
+        if not rows:
             return {}
-        return {f'val_{k}': v for k, v in _to_floats({k: v / n_samples for k, v in acc.items()}).items()}
+        # one device->host copy for all batches; a product that had no valid pixel in a batch (NaN) is left out of
+        # that batch's contribution, exactly like the reference, whose metrics dict simply lacks the key there
+        keys = list(rows[0][1])
+        flat = torch.stack([torch.stack([(m[k].detach().reshape(()).double() if torch.is_tensor(m[k])
+                                          else torch.tensor(float(m[k]), dtype=torch.float64, device=self.device))
+                                         for k in keys]) for _, m in rows]).tolist()
+        n_samples = sum(bs for bs, _ in rows)
+        out = {}
+        for j, k in enumerate(keys):
+            vals = [(bs, r[j]) for (bs, _), r in zip(rows, flat) if not _is_skipped_product(k, r[j])]
+            if vals:
+                out[f'val_{k}'] = sum(bs * v for bs, v in vals) / n_samples
+        return out
 
     # ------------------------------------------------------------------------------------------------ loop
     def train(self, train_loader, val_loader=None, n_steps: int = 10000):

@@ -92,3 +92,35 @@ def test_two_rank_step_equals_single_process_step(tmp_path):
         assert rel < 2e-3, (step, rel)                      # same math, different bf16 summation order in wgrad
         assert (p_dp - p).abs().max().item() < 2.5e-4       # AdamW normalises: sign flips of ~0 gradients move <= 2 lr
         assert ((p_dp - p).norm() / p.norm()).item() < 1e-4
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_model_on_cuda1_while_current_device_is_0():
+    """launches must follow the device the tensors live on (the reference's torch ops work from any current
+    device): build, step and encode a model on cuda:1 while the current device stays 0, same numbers as on cuda:0."""
+    import tempo_vae_b200 as t
+    torch.cuda.set_device(0)
+    out = []
+    for idx in (0, 1):
+        dev = torch.device("cuda", idx)
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        model, orc = _build(dev)
+        x = orc.structured_batch(4, orc.TINY_CFG, seed=5).to(dev)
+        t.seed_all(3)
+        loss, _ = model.get_loss(x)
+        model.optimizer.zero_grad()
+        loss.backward()
+        model.optimizer.step(max_grad_norm=1.0)
+        with torch.no_grad():
+            mean = model.get_latent(x).mean
+        assert torch.cuda.current_device() == 0
+        assert mean.device == dev and model.optimizer.flat_param.device == dev
+        out.append((float(loss), model.optimizer.flat_param.cpu().clone(), mean.cpu().clone()))
+    assert out[0][0] == out[1][0] and torch.equal(out[0][1], out[1][1]) and torch.equal(out[0][2], out[1][2])
+    # the C ABI refuses a pointer that lives on another device instead of faulting inside the kernel
+    from tempo_vae_b200 import _lib
+    a = torch.zeros(64, device="cuda:1")
+    b = torch.zeros(64, dtype=torch.bfloat16, device="cuda:1")
+    rc = _lib.lib.tvae_f32_to_bf16(a.data_ptr(), b.data_ptr(), 64, None, torch.cuda.current_stream(0).cuda_stream)
+    assert rc != 0 and "device" in _lib.last_error()
+    assert t.get_device().type == "cuda"

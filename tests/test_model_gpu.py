@@ -4,16 +4,25 @@
 
 Stated tolerances (bf16 tensor-core operands, fp32 accumulation / statistics / residual stream):
   forward mean, logvar, reconstruction ... relative L2 error <= 1e-2 on the default model (north star: "rel 1e-2 in
-                                           bf16"); <= 1.5e-2 on the tiny fixture model, whose 2-4-channel GroupNorm
-                                           groups and fully re-randomised residual branches amplify operand rounding
-                                           (PyTorch's own autocast-bf16 path measures 1.2e-2 .. 2.1e-2)
+                                           bf16"). On the tiny fixture model the bound is max(1e-2, 1.1 x FLOOR), where
+                                           FLOOR is the error of an IDEAL bf16-operand engine on the same fixture,
+                                           computed live by the oracle under `orc.bf16_operands()` (every conv input and
+                                           weight rounded to bf16, everything else fp32): 1.32e-2 / 9.7e-3 / 1.04e-2 for
+                                           mean / logvar / recon -- no bf16-operand engine can meet 1e-2 there (2-4-channel
+                                           GroupNorm groups, fully re-randomised residual branches), and the reference's
+                                           own autocast-bf16 path measures 1.44e-2 / 1.18e-2 / 1.48e-2 on it and
+                                           1.14e-2 / 1.26e-2 / 1.37e-2 on the default-model fixture
+                                           (tools/bf16_floor.py -> profiles/bf16_floor_r2.json)
   loss, nll_loss ......................... relative error   <= 1e-4   (dominated by N * logvar)
   kl_loss, pixel_mse ..................... relative error   <= 2e-2
-  parameter gradients .................... default model: gradient norms <= 5e-2, per-tensor median rel-L2 <= 5e-2, every
-                                           tensor <= 3e-1; tiny fixture (see check_grads): whole gradient vector <= 8e-2,
-                                           per-tensor median <= 1e-1, every tensor <= 3e-1; tensors whose true gradient is
-                                           numerically zero are compared at an absolute floor (1e-5 x largest grad norm)
-  500-step criterion (loss within 1 %) ... checked on a shortened run here, full curve by bench/parity script
+  parameter gradients .................... see check_grads: every tensor is held to max(0.15, 3 x its own FLOOR error)
+                                           and to a cosine >= 0.8 with the reference gradient; the whole vector and the
+                                           median to 1.5 x FLOOR (FLOOR = the same ideal bf16-operand oracle, whose
+                                           autograd also rounds the gradient stream to bf16 at every conv); tensors whose
+                                           true gradient is numerically zero are compared at an absolute floor (1e-5 x
+                                           largest grad norm). Default model (no live floor: too slow on the host): gradient
+                                           norms <= 5e-2, per-tensor median rel-L2 <= 5e-2, every tensor <= 3e-1
+  500-step criterion (loss within 1 %) ... tests/test_parity_500_gpu.py (default model), shortened run here
 """
 import math
 import os
@@ -61,48 +70,95 @@ def build(cfg, state_dict=None, seed=42):
     return model
 
 
-def check_grads(model, ref, tol, report, global_tol=8e-2, median_tol=1e-1):
-    """Gradient parity of a bf16 gradient stream against fp32 autograd, three criteria:
-      * the whole gradient vector (logvar aside: its 4e6-scale entry would hide everything else): rel-L2 <= global_tol
-      * the median per-tensor rel-L2 error <= median_tol
-      * every tensor <= tol (a layout / tap-order / missing-term bug gives ~1.0; small bias and norm-scale gradients
-        are cancellation-dominated sums of few bf16-rounded terms and legitimately reach 1e-1 on the tiny fixture)
-    Tensors whose true gradient is numerically zero (e.g. attention k-bias) are compared at an absolute floor.
-    The defaults are for the TINY fixture model: ~80 bf16 roundings of the gradient stream between the loss and
-    encoder.conv_in, each ~0.3 %, on top of a 1 % forward difference, with 16-32-channel reductions that average
-    nothing out: measured 5e-2 (vector) / 7e-2 (median). The default-size model is held to 3e-2 / 5e-2 in
-    test_default_config_b2_vs_reference_golden."""
-    norms = [float(g.norm()) for k, g in ref.items() if g is not None and not k.endswith("logvar")]
-    floor = 1e-5 * max(norms)
-    errs = {}
+def rel_errors(got, ref):
+    """(whole-vector rel-L2 without logvar, {tensor: rel-L2}) of a gradient dict against the reference's."""
     num = den = 0.0
-    for k, p in model.named_parameters():
+    errs = {}
+    for k, g in ref.items():
+        if g is None or got.get(k) is None:
+            continue
+        a = got[k].detach().float().cpu()
+        if not k.endswith("logvar"):
+            num += float((a - g).double().pow(2).sum())
+            den += float(g.double().pow(2).sum())
+        errs[k] = rel(a, g)
+    return (num / max(den, 1e-300)) ** 0.5, errs
+
+
+def bf16_floor_grads(loss_fn, sd):
+    """Gradients of the IDEAL bf16-operand engine (oracle under orc.bf16_operands(): conv inputs / weights and, through
+    autograd, the gradient stream rounded to bf16; everything else fp32) -- the floor check_grads measures against."""
+    with orc.bf16_operands():
+        grads, _ = orc.grads_of(loss_fn, sd)
+    return grads
+
+
+def check_grads(model, ref, tol, report, global_tol=8e-2, median_tol=1e-1, floor=None):
+    """Gradient parity of a bf16 gradient stream against fp32 autograd.
+      * the whole gradient vector (logvar aside: its 4e6-scale entry would hide everything else) and the median
+        per-tensor rel-L2: <= 1.5 x the ideal-bf16 floor when `floor` (bf16_floor_grads) is given, else the fixed
+        global_tol / median_tol;
+      * every tensor: rel-L2 <= max(0.15, 3 x its own floor error) (with a floor) or <= tol (without), AND cosine with
+        the reference >= 0.8 -- a sign, layout, tap-order or missing-term bug fails both;
+      * a tensor that misses its relative bound passes only if its ABSOLUTE error is below 0.1 % of the norm of the
+        whole gradient vector (cancellation-dominated sums such as a 4-element bias gradient over 32 pixels); every
+        tensor that needed this is named in the report;
+      * tensors whose true gradient is numerically zero (e.g. attention k-bias) are compared at an absolute floor."""
+    norms = [float(g.norm()) for k, g in ref.items() if g is not None and not k.endswith("logvar")]
+    zero_floor = 1e-5 * max(norms)
+    named = dict(model.named_parameters())
+    got = {}
+    for k, p in named.items():
         g = ref[k]
         if g is None:
             assert p.grad is None, f"{k}: reference has no gradient here"
             continue
         assert p.grad is not None, k
-        got = p.grad.detach().float().cpu()
-        if not k.endswith("logvar"):
-            num += float((got - g).double().pow(2).sum())
-            den += float(g.double().pow(2).sum())
-        if float(g.norm()) < floor:
-            assert float((got - g).norm()) < floor, k
-            continue
-        errs[k] = rel(got, g)
-    glob = (num / den) ** 0.5
-    vals = sorted(errs.values())
+        got[k] = p.grad
+    glob, errs = rel_errors(got, ref)
+    gnorm = sum(float(g.double().pow(2).sum()) for k, g in ref.items() if g is not None and not k.endswith("logvar")) ** 0.5
+    live = {}
+    for k, e in errs.items():
+        if float(ref[k].norm()) < zero_floor:
+            assert float((got[k].detach().float().cpu() - ref[k]).norm()) < zero_floor, k
+        else:
+            live[k] = e
+    vals = sorted(live.values())
     med = vals[len(vals) // 2]
-    worst = max(errs.items(), key=lambda kv: kv[1])
-    report.append(f"gradient vector rel-L2 {glob:.3e}; per-tensor median {med:.3e}, worst {worst[1]:.3e} at {worst[0]}")
-    # a tensor passes if its relative error is below tol OR its absolute error is negligible on the scale of the whole
-    # gradient vector (cancellation-dominated sums such as a 4-element bias gradient over 32 pixels)
-    named = dict(model.named_parameters())
-    gnorm = den ** 0.5
-    bad = {k: round(v, 4) for k, v in errs.items()
-           if v >= tol and float((named[k].grad.detach().float().cpu() - ref[k]).norm()) > 1e-2 * gnorm}
+    worst = max(live.items(), key=lambda kv: kv[1])
+    line = f"gradient vector rel-L2 {glob:.3e}; per-tensor median {med:.3e}, worst {worst[1]:.3e} at {worst[0]}"
+    fl_err = {}
+    if floor is not None:
+        fglob, fl_err = rel_errors(floor, ref)
+        fvals = sorted(v for k, v in fl_err.items() if k in live)
+        fmed = fvals[len(fvals) // 2]
+        line += f" [ideal-bf16 floor: vector {fglob:.3e}, median {fmed:.3e}]"
+        global_tol, median_tol = 1.5 * fglob, 1.5 * fmed
+    bad, escaped = {}, []
+    for k, e in live.items():
+        a, g = got[k].detach().float().cpu(), ref[k]
+        bound = max(0.15, 3.0 * fl_err[k]) if floor is not None else tol
+        cos = float((a * g).sum() / (a.norm() * g.norm()).clamp_min(1e-30))
+        if e < bound and cos >= 0.8:
+            continue
+        if float((a - g).norm()) <= 1e-3 * gnorm:
+            escaped.append(f"{k} (rel {e:.2f}, cos {cos:.2f})")
+            continue
+        bad[k] = (round(e, 4), round(cos, 3), round(bound, 3))
+    if escaped:
+        line += "; passed on absolute error < 1e-3 |g|: " + ", ".join(escaped)
+    report.append(line)
     assert not bad, bad
-    assert glob < global_tol and med < median_tol, (glob, med)
+    assert glob < global_tol and med < median_tol, (glob, med, global_tol, median_tol)
+
+
+def bf16_floor_forward(sd, x, eps, cfg):
+    """(mean, logvar, recon) rel-L2 errors of the ideal bf16-operand oracle against the fp32 oracle on this fixture."""
+    with torch.no_grad():
+        ref = orc.vae_loss(sd, x, eps, cfg)
+        with orc.bf16_operands():
+            idl = orc.vae_loss(sd, x, eps, cfg)
+    return tuple(rel(idl[k], ref[k]) for k in ("mean", "logvar", "recon"))
 
 
 def test_tiny_forward_loss_grads_and_three_steps_vs_reference_golden(capsys):
@@ -118,9 +174,12 @@ def test_tiny_forward_loss_grads_and_three_steps_vs_reference_golden(capsys):
             with torch.no_grad():
                 recon, post = model.vae(x, eps=eps)
             e = (rel(post.mean, s["mean"]), rel(post.logvar, s["logvar"]), rel(recon, s["recon"]))
-            report.append(f"forward rel-L2 mean {e[0]:.3e} logvar {e[1]:.3e} recon {e[2]:.3e}; "
+            fl = bf16_floor_forward(fx["state_dict"], fx["x"][0], fx["eps"][0], cfg)
+            report.append(f"forward rel-L2 mean {e[0]:.3e} logvar {e[1]:.3e} recon {e[2]:.3e} "
+                          f"[ideal-bf16 floor {fl[0]:.3e} {fl[1]:.3e} {fl[2]:.3e}]; "
                           f"rel-Linf recon {relinf(recon, s['recon']):.3e}")
-            assert max(e) < 1.5e-2, e
+            for got_e, floor_e in zip(e, fl):
+                assert got_e < max(1e-2, 1.1 * floor_e), (e, fl)
             z = post.mode()
             assert z.shape == post.mean.shape and recon.shape == x.shape
         loss, metrics = model.get_loss(x, eps=eps)
@@ -130,7 +189,10 @@ def test_tiny_forward_loss_grads_and_three_steps_vs_reference_golden(capsys):
         assert abs(metrics["nll_loss"].item() - s["nll_loss"]) / s["nll_loss"] < 1e-4
         assert abs(metrics["kl_loss"].item() - s["kl_loss"]) / s["kl_loss"] < 2e-2
         assert abs(model.vae.last_pixel_mse().item() - s["pixel_mse"]) / s["pixel_mse"] < 2e-2
-        check_grads(model, s["grads"], 3e-1, report)
+        floor = None
+        if i == 0:       # the golden parameters of later steps are the reference's own trajectory; the floor is per state
+            floor = bf16_floor_grads(lambda leaves: orc.vae_loss(leaves, fx["x"][0], fx["eps"][0], cfg), fx["state_dict"])
+        check_grads(model, s["grads"], 3e-1, report, floor=floor)
         gn = model.optimizer.grad_norm().item()
         assert abs(gn - s["grad_norm"]) / s["grad_norm"] < 1e-3
         model.optimizer.step(max_grad_norm=1.0)
@@ -219,7 +281,9 @@ def test_l2_variant_vs_reference_golden(capsys):
         tol = 1e-4 if k in ("loss", "nll_loss") else 3e-2
         assert abs(metrics[k] - v) / abs(v) < tol, (k, metrics[k], v)
     report = []
-    check_grads(model, fx["grads"], 3e-1, report)
+    floor = bf16_floor_grads(lambda leaves: orc.l2_supervised_loss(leaves, fx["batch"], fx["eps"], fx["eps2"], cfg,
+                                                                   fx["weights"]), fx["state_dict"])
+    check_grads(model, fx["grads"], 3e-1, report, floor=floor)
     out = model(batch["spectral"])
     assert out["reconstruction"].shape == batch["spectral"].shape
     assert set(out["l2_predictions"]) == {"NO2", "O3TOT", "HCHO", "CLDO4"}
@@ -247,10 +311,14 @@ def test_modular_api_is_differentiable_and_matches_oracle():
         r = orc.decode(leaves, zz, cfg)
         return dict(loss=((r - fx["x"][1]) ** 2).mean() + 1e-3 * orc.kl_per_sample(mean, logvar).mean(), recon=r)
     grads, out = orc.grads_of(ref_loss, fx["state_dict"])
-    assert rel(recon, out["recon"]) < 1.5e-2
+    with torch.no_grad(), orc.bf16_operands():
+        ideal = ref_loss(fx["state_dict"])["recon"]
+    assert rel(recon, out["recon"]) < max(1e-2, 1.1 * rel(ideal, out["recon"]))
     assert abs(loss.item() - out["loss"].item()) / out["loss"].item() < 2e-2
     grads["vae.logvar"] = None
-    check_grads(model, grads, 3e-1, [])
+    floor = bf16_floor_grads(ref_loss, fx["state_dict"])
+    floor["vae.logvar"] = None
+    check_grads(model, grads, 3e-1, [], floor=floor)
     # deterministic path + latent helper
     with torch.no_grad():
         r2, p2 = model.vae(x, sample_posterior=False)
@@ -367,9 +435,13 @@ def test_inference_patch_sweep_and_whole_granule_vs_oracle(capsys):
         ref_whole, _, _ = orc.encode(fx["state_dict"], z[:128, :256].permute(2, 0, 1).unsqueeze(0), cfg)
     assert whole.shape == ref_whole.shape == (1, cfg["embed_dim"], 32, 64)
     e_whole = rel(whole, ref_whole)
+    with torch.no_grad(), orc.bf16_operands():            # the ideal bf16-operand engine on the same two inputs
+        f_patch = rel(orc.encode(fx["state_dict"], patches[order], cfg)[0], ref_mean)
+        f_whole = rel(orc.encode(fx["state_dict"], z[:128, :256].permute(2, 0, 1).unsqueeze(0), cfg)[0], ref_whole)
     with capsys.disabled():
-        print(f"\n[inference] patch-sweep latent rel-L2 {e_patch:.3e}; whole-granule (2048-token attention) {e_whole:.3e}")
-    assert e_patch < 1.5e-2 and e_whole < 1.5e-2
+        print(f"\n[inference] patch-sweep latent rel-L2 {e_patch:.3e} (ideal-bf16 floor {f_patch:.3e}); whole-granule "
+              f"(2048-token attention) {e_whole:.3e} (floor {f_whole:.3e})")
+    assert e_patch < max(1e-2, 1.1 * f_patch) and e_whole < max(1e-2, 1.1 * f_whole)
 
 
 def test_fp32_mode_forward_parity_1e4(capsys):
@@ -441,9 +513,10 @@ def test_config_variants_loss_and_grads_vs_oracle(name, capsys):
     assert abs(metrics["kl_loss"].item() - out["kl_loss"].item()) / out["kl_loss"].item() < 3e-2
     assert abs(model.vae.last_pixel_mse().item() - out["pixel_mse"].item()) / out["pixel_mse"].item() < 2e-2
     report = []
-    # ReLU's derivative is discontinuous: activations that straddle 0 between the bf16 and fp32 forwards flip whole
-    # gradient terms, so that variant gets a wider (still sub-20 %) median band
-    check_grads(model, grads, 4e-1, report, global_tol=1e-1, median_tol=(2e-1 if cfg["act"] == "relu" else 1.2e-1))
+    # the floor is computed per variant: e.g. ReLU's discontinuous derivative flips whole gradient terms wherever an
+    # activation straddles 0 between a bf16 and an fp32 forward, in the ideal bf16-operand oracle exactly as in the engine
+    floor = bf16_floor_grads(lambda leaves: orc.vae_loss(leaves, x, eps, cfg), sd)
+    check_grads(model, grads, 4e-1, report, floor=floor)
     with capsys.disabled():
         print(f"\n[variant {name}] " + report[0])
 
@@ -653,3 +726,57 @@ def test_l2_device_tile_cache_batches_match_host_batches(tmp_path):
                                l2_weights=fx["weights"])
     m = tr.train_step(batch)
     assert all(torch.isfinite(torch.tensor(float(v))) or k.endswith("_loss") for k, v in m.items())
+
+
+def test_data_writes_to_weights_are_seen_by_the_next_forward():
+    """`p.data.copy_(...)` / `nn.init.*_(p.data)` do not bump the autograd version counter; the bf16 weight packs
+    must still follow (they are refreshed at the start of every top-level forward), like the reference's modules, which
+    read the live parameter on every call. `ENGINE.frozen_weights()` is the documented opt-out for inference sweeps."""
+    import tempo_vae_b200 as t
+    cfg = orc.TINY_CFG
+    fx = gold("tiny_train.pt")
+    model = build(cfg, fx["state_dict"])
+    x = fx["x"][0].cuda()
+    with torch.no_grad():
+        m0 = model.vae.encode(x).mean.clone()
+        w = model.vae.encoder.conv_in.weight
+        ver = w._version
+        w.data.mul_(1.5)                                        # invisible to autograd's version counter
+        assert w._version == ver
+        m1 = model.vae.encode(x).mean.clone()
+        assert not torch.equal(m0, m1)
+        sd = {k: v.clone() for k, v in fx["state_dict"].items()}
+        sd["vae.encoder.conv_in.weight"] = sd["vae.encoder.conv_in.weight"] * 1.5
+        ref_mean, _, _ = orc.encode(sd, fx["x"][0], cfg)
+        assert rel(m1, ref_mean) < 2e-2
+        with t.ENGINE.frozen_weights():                         # packs refreshed on entry, then assumed unchanged
+            m2 = model.vae.encode(x).mean.clone()
+            w.data.mul_(2.0)
+            m3 = model.vae.encode(x).mean.clone()
+        assert torch.equal(m1, m2) and torch.equal(m2, m3)
+        m4 = model.vae.encode(x).mean
+        assert not torch.equal(m3, m4)
+
+
+def test_accumulated_micro_batches_equal_one_step_on_their_concatenation(tmp_path):
+    """bench.py's config-4 leg (global batch 2048 as accumulated micro-batches of 256): Trainer.train_step_accumulate over
+    two halves gives the gradient / parameters of one train_step on the whole batch (same noise: keyed by sample index)."""
+    import tempo_vae_b200 as t
+    cfg = orc.TINY_CFG
+    fx = gold("tiny_train.pt")
+    x = orc.structured_batch(8, cfg, seed=21).cuda()
+    res = []
+    for halves in (False, True):
+        model = build(cfg, fx["state_dict"])
+        tr = t.Trainer(model, model.optimizer, torch.device("cuda"), tmp_path / str(halves))
+        tr.step = 1
+        t.seed_all(3)
+        if halves:
+            m = tr.train_step_accumulate([x[:4], x[4:]])
+        else:
+            m = tr.train_step_device(x)
+        res.append((model.optimizer.flat_grad.clone(), model.optimizer.flat_param.clone(), float(m["loss"])))
+    (g1, p1, l1), (g2, p2, l2) = res
+    assert abs(l1 - l2) / abs(l1) < 1e-6
+    assert float((g2 / 2 - g1).norm() / g1.norm()) < 2e-3           # accumulated sum = 2 x the mean gradient
+    assert float((p2 - p1).abs().max()) < 2.5e-4
