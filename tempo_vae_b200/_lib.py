@@ -84,6 +84,7 @@ def _load():
         "tvae_gn_act_fwd": (i32, [vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp]),
         "tvae_gn_bwd_workspace_bytes": (i64, [i32, i32, i32, i32]),
         "tvae_gn_act_bwd": (i32, [vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]),
+        "tvae_gn_set_bwd_fused": (i32, [i32, i32]),
         "tvae_colsum_workspace_bytes": (i64, [i64, i32]),
         "tvae_colsum_bf16": (i32, [vp, i64, i32, i32, vp, vp, vp]),
         "tvae_attn_fwd": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp]),

@@ -816,6 +816,11 @@ extern "C" int32_t tvae_gn_act_bwd(const void* xv, int32_t x_is_bf16, const floa
   return 0;
 }
 
+extern "C" int32_t tvae_gn_set_bwd_fused(int32_t on, int32_t group_mb) {
+  gn_set_bwd_fused(on, group_mb);
+  return 0;
+}
+
 extern "C" int64_t tvae_colsum_workspace_bytes(int64_t rows, int32_t C) {
   return (int64_t)colsum_blocks(rows) * C * 4;
 }

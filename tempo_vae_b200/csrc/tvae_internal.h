@@ -35,4 +35,7 @@ int gn_act_bwd_fast(const void* x, bool x_bf16, const float* stats, const float*
                     const __nv_bfloat16* gres, int N, int HW, int C, int G, int act, __nv_bfloat16* dx, float* dgamma,
                     float* dbeta, float* dx_colsum, float* ws, cudaStream_t stream);
 
+// A/B switch of the single-pass GroupNorm backward (gn_fast.cu); group_mb <= 0 keeps the current group size
+void gn_set_bwd_fused(int on, int group_mb);
+
 }  // namespace tvae

@@ -88,7 +88,12 @@ def test_spectrum_statistics_vs_numpy_oracle():
     mean, std = st.finalize()
     ref_mean, ref_std = orc.spectrum_statistics(rads)
     assert st.rows == 13 * 300 + 7 * 129
-    assert float((mean.cpu() - ref_mean).abs().max()) < 2e-6 and float((std.cpu() - ref_std).abs().max()) < 2e-6
+    # the reference sums ~5,000 float32 rows in float32 (numpy): ITS result is ~1e-5 off the exact mean; the kernel
+    # accumulates in fp64, so it is held to 1e-6 of the exact statistics and to the reference's own error of the reference
+    allp = torch.cat([torch.log(torch.clamp(r, min=1.0)).reshape(-1, C) for r in rads]).double()
+    assert float((mean.cpu().double() - allp.mean(0)).abs().max()) < 1e-6
+    assert float((std.cpu().double() - allp.std(0, unbiased=False)).abs().max()) < 1e-6
+    assert float((mean.cpu() - ref_mean).abs().max()) < 5e-5 and float((std.cpu() - ref_std).abs().max()) < 5e-5
     st2 = t.SpectrumStats(C)
     for r in rads:
         st2.update(r.to(DEV))
@@ -125,7 +130,7 @@ def test_host_tile_store_batches_feed_the_engine_bit_identically(tmp_path):
     torch.save(tiles[6:].clone(), tmp_path / "b.pt")
     store = t.TEMPODataLoader.get_host_store(str(tmp_path), verbose=False)
     assert len(store) == 10 and store.data.is_pinned() and store.pitch % 8 == 0
-    assert torch.equal(store.data[:, :, :, :C].float(), tiles)
+    assert torch.equal(store.data[:10, :, :, :C].float(), tiles)
     key = lambda z: sorted(round(float(v), 3) for v in z.reshape(z.shape[0], -1).sum(1))      # noqa: E731
     seen = [x.float().permute(0, 2, 3, 1).cpu() for x in store.batches(2, DEV, seed=1, epochs=1)]
     assert len(seen) == 5 and key(torch.cat(seen)) == key(tiles)

@@ -302,7 +302,7 @@ def test_bench_reference_arm_contract():
     line = json.loads(lines[0])
     assert line["impl"] == "reference" and line["unit"] == "samples/s" and line["higher_is_better"] is True
     assert line["metric"] == "train samples/sec (fwd+bwd+AdamW)" and line["value"] > 0
-    built = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "src", "model.pyc"))
+    built = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "src", "model.bytecode"))
     assert line["cpu_baseline"]["kind"] == ("reference" if built else "port") and line["cpu_baseline"]["cores"] >= 1
     assert line["cpu_baseline"]["lean_step_samples_per_s"] > 0 and line["cpu_baseline"]["encode_samples_per_s"] > 0
     assert line["config"]["batch_per_step"] == 1            # (the driver's run uses the fixed default: 8)
