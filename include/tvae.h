@@ -326,6 +326,28 @@ int64_t tvae_batch_stats_workspace_bytes(void);
 int32_t tvae_batch_stats(const void* x, int32_t is_bf16, int64_t rows, int64_t C, int64_t pitch, float* out,
                          double* workspace, tvae_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Probe training on latents (src/scripts/linear_probe_analysis.py:212-353): nn.Linear layers run as
+ * 1x1 convolutions through tvae_conv_gemm / tvae_wgrad_gemm and AdamW through tvae_adamw; these are the rest.
+ *
+ * tvae_act_dropout_fwd: out = dropout_p(act(x)) as bf16 operand rows. x fp32 [rows][x_pitch] (the Linear output, bias
+ *  included); act: 0 identity, 1 GELU, 2 ReLU, 3 SiLU, 4 tanh (nn.ReLU / nn.GELU / nn.Tanh of MLPProbe); the keep mask
+ *  of element (row, c) is Philox4x32-10 keyed by (seed, offset + row, c / 4): an element is zeroed with probability
+ *  p_drop, kept ones are scaled by 1 / (1 - p_drop) (nn.Dropout). p_drop = 0 is plain activation (eval mode).
+ *  Pad lanes [C, out_pitch) are zeroed.
+ * tvae_act_dropout_bwd: dx = da * mask * act'(x) with the SAME (seed, offset): the mask is regenerated, not stored.
+ * tvae_probe_mse: nn.MSELoss() on a [n, 1] prediction (target element r at target[r * target_pitch]): sums[0] = sum (pred - y)^2, sums[1] = sum y, sums[2] = sum y^2
+ *  over the first n_valid rows (fp64, fixed order) -- loss = sums[0] / n_valid, R^2 = 1 - sums[0] / (sums[2] -
+ *  sums[1]^2 / n); dpred (optional, bf16 [rows_padded][dp_pitch], column 0) = 2 (pred - y) / n_valid, 0 on pad rows.
+ */
+int32_t tvae_act_dropout_fwd(const float* x, int32_t x_pitch, int64_t rows, int32_t C, int32_t act, float p_drop,
+                             uint64_t seed, uint64_t offset, void* out_bf16, int32_t out_pitch, tvae_stream_t stream);
+int32_t tvae_act_dropout_bwd(const float* x, int32_t x_pitch, const void* da_bf16, int32_t da_pitch, int64_t rows,
+                             int32_t C, int32_t act, float p_drop, uint64_t seed, uint64_t offset, void* dx_bf16,
+                             int32_t dx_pitch, tvae_stream_t stream);
+int32_t tvae_probe_mse(const float* pred, int32_t pred_pitch, const float* target, int64_t target_pitch, int64_t n_valid,
+                       int64_t rows_padded, double* sums, void* dpred_bf16, int32_t dp_pitch, tvae_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

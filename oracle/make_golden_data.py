@@ -47,3 +47,48 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def probe_fixture():
+    """tests/golden/probes.pt: the reference's own LinearProbe / MLPProbe / train_probe (compiled on their own from
+    src/scripts/linear_probe_analysis.py:212-353, which imports netCDF4 at module level) trained on a small synthetic
+    latent -> component regression, CPU, fixed seeds."""
+    import ast as _ast
+    import torch.nn as nn
+    path = os.path.join(REF, "src/scripts/linear_probe_analysis.py")
+    tree = _ast.parse(open(path).read())
+    want = {"LinearProbe", "MLPProbe", "train_probe"}
+    body = [n for n in tree.body if isinstance(n, (_ast.ClassDef, _ast.FunctionDef)) and n.name in want]
+    ns = {"np": np, "torch": torch, "nn": nn}
+    exec(compile(_ast.Module(body=body, type_ignores=[]), "<reference>/src/scripts/linear_probe_analysis.py", "exec"), ns)
+    g = torch.Generator().manual_seed(5)
+    n_tr, n_va = 1600, 400
+    X = torch.randn((n_tr + n_va, 32), generator=g)
+    w = torch.randn((32,), generator=g) / 32 ** 0.5
+    y = X @ w + 0.5 * torch.tanh(X[:, 0] * X[:, 1]) + 0.1 * torch.randn((n_tr + n_va,), generator=g)
+    Xtr, ytr, Xva, yva = X[:n_tr].numpy(), y[:n_tr].numpy(), X[n_tr:].numpy(), y[n_tr:].numpy()
+    cases = {}
+    for name, cfg in {
+        "linear": dict(architecture="linear", learning_rate=0.01, weight_decay=0.01, batch_size=512, max_epochs=30),
+        "mlp_relu_nodrop": dict(architecture="mlp", hidden_dims=[64, 64], dropout=0.0, activation="relu", learning_rate=0.001,
+                                weight_decay=0.01, batch_size=512, max_epochs=15),
+        "mlp_gelu_drop": dict(architecture="mlp", hidden_dims=[64, 64], dropout=0.1, activation="gelu", learning_rate=0.001,
+                              weight_decay=0.01, batch_size=512, max_epochs=15),
+    }.items():
+        torch.manual_seed(31)
+        probe, tl, vl = ns["train_probe"](Xtr, ytr, Xva, yva, cfg)
+        probe.eval()
+        with torch.no_grad():
+            pred = probe(torch.from_numpy(Xva)).squeeze(1)
+        cases[name] = dict(config=cfg, train_losses=tl, val_losses=vl, pred_val=pred.clone(),
+                           state_dict={k: v.clone() for k, v in probe.state_dict().items()})
+        print(name, "final train/val loss", tl[-1], vl[-1])
+    out = os.path.join(ROOT, "tests", "golden", "probes.pt")
+    torch.save(dict(X_train=torch.from_numpy(Xtr), y_train=torch.from_numpy(ytr), X_val=torch.from_numpy(Xva),
+                    y_val=torch.from_numpy(yva), seed=31, cases=cases,
+                    source="src/scripts/linear_probe_analysis.py:212-353 executed from /root/reference"), out)
+    print("wrote", out, os.path.getsize(out), "bytes")
+
+
+if __name__ == "__main__":
+    probe_fixture()

@@ -407,3 +407,67 @@ def spectrum_statistics(rads, min_radiance=1.0):
     import numpy as np
     allp = np.vstack([np.log(np.clip(r.numpy(), min_radiance, None)).reshape(-1, r.shape[-1]) for r in rads])
     return (torch.from_numpy(allp.mean(axis=0).astype(np.float32)), torch.from_numpy(allp.std(axis=0).astype(np.float32)))
+
+
+# ------------------------------------------------------------------------------------------------ probes
+def probe_init(input_dim=32, hidden_dims=None, seed=None):
+    """nn.Linear-initialised weights of LinearProbe (hidden_dims None) / MLPProbe in the reference's construction order
+    (src/scripts/linear_probe_analysis.py:212-252): [(W [out, in], b [out]), ...]."""
+    import torch.nn as nn
+    if seed is not None:
+        torch.manual_seed(seed)
+    dims = [input_dim] + list(hidden_dims or []) + [1]
+    out = []
+    for a, b in zip(dims[:-1], dims[1:]):
+        m = nn.Linear(a, b)
+        out.append((m.weight.detach().clone(), m.bias.detach().clone()))
+    return out
+
+
+def probe_forward(params, x, activation="relu", dropout=0.0, train=False):
+    acts = {"relu": F.relu, "gelu": F.gelu, "tanh": torch.tanh}
+    h = x
+    for i, (w, b) in enumerate(params):
+        h = F.linear(h, w, b)
+        if i < len(params) - 1:
+            h = acts[activation](h)
+            if dropout > 0:
+                h = F.dropout(h, dropout, training=train)
+    return h
+
+
+def train_probe(X_train, y_train, X_val, y_val, config, params):
+    """The reference's probe training loop (src/scripts/linear_probe_analysis.py:255-353) on explicit weight tensors:
+    torch.optim.AdamW(lr, weight_decay), nn.MSELoss, one torch.randperm per epoch, mini-batches with a partial last
+    one, full-batch validation per epoch. Returns (params, train_losses, val_losses); like the reference (whose
+    `best_state` is a shallow copy) the returned weights are the last epoch's."""
+    leaves = [t.clone().requires_grad_(True) for wb in params for t in wb]
+    pairs = [(leaves[2 * i], leaves[2 * i + 1]) for i in range(len(params))]
+    opt = torch.optim.AdamW(leaves, lr=config["learning_rate"], weight_decay=config.get("weight_decay", 0.01))
+    X_train, X_val = torch.as_tensor(X_train).float(), torch.as_tensor(X_val).float()
+    y_train, y_val = torch.as_tensor(y_train).float().unsqueeze(1), torch.as_tensor(y_val).float().unsqueeze(1)
+    bs = config.get("batch_size", 512)
+    nb = (len(X_train) + bs - 1) // bs
+    act, p = config.get("activation", "relu"), (config.get("dropout", 0.1) if len(params) > 1 else 0.0)
+    tl, vl = [], []
+    for _ in range(config["max_epochs"]):
+        perm = torch.randperm(len(X_train))
+        Xs, ys = X_train[perm], y_train[perm]
+        tot = 0.0
+        for b in range(nb):
+            s, e = b * bs, min((b + 1) * bs, len(X_train))
+            opt.zero_grad()
+            loss = F.mse_loss(probe_forward(pairs, Xs[s:e], act, p, True), ys[s:e])
+            loss.backward()
+            opt.step()
+            tot += loss.item() * (e - s)
+        tl.append(tot / len(X_train))
+        with torch.no_grad():
+            vl.append(F.mse_loss(probe_forward(pairs, X_val, act, p, False), y_val).item())
+    return [(w.detach(), b.detach()) for w, b in pairs], tl, vl
+
+
+def r2_score(y, pred):
+    """sklearn.metrics.r2_score for 1-D arrays (src/scripts/linear_probe_analysis.py:680)."""
+    y, pred = torch.as_tensor(y).double().reshape(-1), torch.as_tensor(pred).double().reshape(-1)
+    return float(1.0 - ((y - pred) ** 2).sum() / ((y - y.mean()) ** 2).sum())

@@ -111,6 +111,9 @@ def _load():
         "tvae_spectrum_stats_finalize": (i32, [vp, i64, i32, vp, vp, vp]),
         "tvae_batch_stats_workspace_bytes": (i64, []),
         "tvae_batch_stats": (i32, [vp, i32, i64, i64, i64, vp, vp, vp]),
+        "tvae_act_dropout_fwd": (i32, [vp, i32, i64, i32, i32, f32, u64, u64, vp, i32, vp]),
+        "tvae_act_dropout_bwd": (i32, [vp, i32, vp, i32, i64, i32, i32, f32, u64, u64, vp, i32, vp]),
+        "tvae_probe_mse": (i32, [vp, i32, vp, i64, i64, i64, vp, vp, i32, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol

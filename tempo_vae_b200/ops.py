@@ -81,7 +81,7 @@ _KERNELS_PER_CALL = {
     "tvae_reparam_fwd": 1, "tvae_reparam_bwd": 1, "tvae_nll_fwd": 2, "tvae_vae_loss_finalize": 1,
     "tvae_l2head_loss_fwd": 1, "tvae_l2head_loss_bwd": 1, "tvae_l2head_finalize": 1, "tvae_sumsq": 2, "tvae_adamw": 1,
     "tvae_gather_rows": 1, "tvae_extract_tiles": 1, "tvae_spectrum_stats_accum": 2, "tvae_spectrum_stats_finalize": 1,
-    "tvae_batch_stats": 2,
+    "tvae_batch_stats": 2, "tvae_act_dropout_fwd": 1, "tvae_act_dropout_bwd": 1, "tvae_probe_mse": 1,
 }
 
 
@@ -169,6 +169,8 @@ class PackedWeight:
 #  "up_fwd"     ConvT  [Ci][Co][2][2]     -> [(tap, Co)][Ci_pad]          (forward)
 #  "up_dgrad"   ConvT                     -> [Ci][tap][Co_pad]            (dgrad as 2x2 s2 conv)
 def pack_geometry(shape, mode):
+    if len(shape) == 2:                # nn.Linear [out, in] = a 1x1 convolution (probes)
+        shape = tuple(shape) + (1, 1)
     a, b, r, s = shape
     taps = r * s
     if mode == "fwd":
@@ -764,3 +766,46 @@ def batch_stats(x):
     check(lib.tvae_batch_stats(x.data_ptr(), int(x.dtype == torch.bfloat16), rows, Cc, pitch, out.data_ptr(),
                                ws.data_ptr(), _stream()), "tvae_batch_stats")
     return out
+
+
+# ----------------------------------------------------------------------------------------------- probes
+@_on_device
+def rows_f32_to_bf16(x, out):
+    """x fp32 [rows, C] (row pitch = x.stride(0)) -> out bf16 [rows, pitch] (pad lanes zeroed)."""
+    require_cuda(x, "rows")
+    assert x.dtype == torch.float32 and x.stride(1) == 1 and out.dtype == torch.bfloat16 and out.stride(1) == 1
+    if x.shape[0] == 0:
+        return out
+    check(lib.tvae_nhwc_f32_to_nhwc_bf16(x.data_ptr(), x.stride(0), x.shape[0], x.shape[1], out.data_ptr(),
+                                         out.stride(0), None, _stream()), "tvae_nhwc_f32_to_nhwc_bf16")
+    return out
+
+
+@_on_device
+def act_dropout_fwd(x, Cc, act, p, seed, offset):
+    """x fp32 [rows, pitch] -> bf16 [rows, round_up(C, 8)] = dropout_p(act(x)) (tvae_act_dropout_fwd)."""
+    rows = x.shape[0]
+    out = torch.empty((rows, round_up(Cc, 8)), dtype=torch.bfloat16, device=x.device)
+    check(lib.tvae_act_dropout_fwd(x.data_ptr(), x.stride(0), rows, Cc, int(act), float(p), int(seed) & (2 ** 64 - 1),
+                                   int(offset), out.data_ptr(), out.stride(0), _stream()), "tvae_act_dropout_fwd")
+    return out
+
+
+@_on_device
+def act_dropout_bwd(x, da, Cc, act, p, seed, offset):
+    rows = x.shape[0]
+    dx = torch.empty((rows, round_up(Cc, 8)), dtype=torch.bfloat16, device=x.device)
+    check(lib.tvae_act_dropout_bwd(x.data_ptr(), x.stride(0), da.data_ptr(), da.stride(0), rows, Cc, int(act), float(p),
+                                   int(seed) & (2 ** 64 - 1), int(offset), dx.data_ptr(), dx.stride(0), _stream()),
+          "tvae_act_dropout_bwd")
+    return dx
+
+
+@_on_device
+def probe_mse(pred, y, n_valid, rows_padded, sums, dpred=None):
+    """y: fp32 vector (any element stride: a column of the shuffled [X | y] matrix is read in place)."""
+    assert pred.dtype == torch.float32 and y.dtype == torch.float32 and y.dim() == 1
+    check(lib.tvae_probe_mse(pred.data_ptr(), pred.stride(0), y.data_ptr(), y.stride(0) if y.numel() > 1 else 1,
+                             int(n_valid), int(rows_padded), sums.data_ptr(), _ptr(dpred),
+                             dpred.stride(0) if dpred is not None else 0, _stream()), "tvae_probe_mse")
+    return sums

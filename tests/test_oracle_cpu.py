@@ -361,6 +361,22 @@ def test_oracle_tile_extraction_matches_the_reference_function():
     assert float(z.abs().max()) <= 10.0 and z.shape == rads[0].shape
 
 
+def test_oracle_probe_training_matches_the_reference_run():
+    """oracle.train_probe against tests/golden/probes.pt (the reference's own train_probe, oracle/make_golden_data.py): same
+    seed => the same loss curves to the last bit, dropout included (identical RNG consumption)."""
+    fx = gold("probes.pt")
+    for name, c in fx["cases"].items():
+        cfg = c["config"]
+        torch.manual_seed(fx["seed"])
+        params = orc.probe_init(32, cfg.get("hidden_dims"))
+        trained, tl, vl = orc.train_probe(fx["X_train"], fx["y_train"], fx["X_val"], fx["y_val"], cfg, params)
+        assert tl == c["train_losses"] and vl == c["val_losses"], name
+        with torch.no_grad():
+            pred = orc.probe_forward(trained, fx["X_val"], cfg.get("activation", "relu"), cfg.get("dropout", 0.0)).squeeze(1)
+        assert torch.allclose(pred, c["pred_val"], atol=1e-6)
+        assert 0.0 < orc.r2_score(fx["y_val"], pred) < 1.0
+
+
 def test_epoch_shard_gives_every_rank_the_same_number_of_batches():
     """ADVICE r1: with n % world != 0, perm[rank::world] alone can hand rank 0 one batch more than the others (n=4089,
     world=8, B=256: 2 vs 1) and the ranks would issue different numbers of all-reduces."""
