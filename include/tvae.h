@@ -176,9 +176,9 @@ int32_t tvae_gn_act_bwd(const void* x, int32_t x_is_bf16, const float* stats, co
 
 /* Scheduling switch of tvae_gn_act_bwd (results agree up to the summation order of the row sums): on = 0 (default) runs
  * the two-pass kernels (row sums, then apply: x and da are read from DRAM twice); on = 1 uses ONE persistent pass for
- * tensors that do not fit the L2 (x and da are read from DRAM once; the second read is served by the L2, group by group
- * of `group_mb` megabytes); on = 2 forces the single pass whatever the size (tests). group_mb <= 0 keeps the current
- * group size (default 24). */
+ * tensors that do not fit the L2 (cp.async.bulk ring; x and da are read from DRAM once, the second read is served by the
+ * L2 group by group of `group_mb` megabytes: 38 % less DRAM traffic, but slower on B200 because it is issue-bound, see
+ * DESIGN.md); on = 2 forces the single pass whatever the size (tests). group_mb <= 0 keeps the current group size (24). */
 int32_t tvae_gn_set_bwd_fused(int32_t on, int32_t group_mb);
 
 /* Column sums: out[c] = sum_rows x[row][c] (bias gradients). x bf16 [rows][pitch]; workspace rows_blocks*C floats:

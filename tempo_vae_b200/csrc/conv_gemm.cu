@@ -584,11 +584,11 @@ extern "C" int32_t tvae_conv_gemm(const tvae_conv_args* a, cudaStream_t stream) 
   const bool lean = g_conv_lean_epilogue && p.out_bf16 && !p.out_f32 && !p.res && !p.stats_part && !p.out_bf16_lo &&
                     !p.up_mode;
   if (pair) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_set;
+    if (attr_set.pending()) {
       TVAE_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
       TVAE_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-      attr_set = true;
+      attr_set.mark();
     }
     const int total = (p.m_tiles + 1) / 2 * p.n_tiles;
     int grid = num_sms() / 2;
@@ -605,11 +605,11 @@ extern "C" int32_t tvae_conv_gemm(const tvae_conv_args* a, cudaStream_t stream) 
     if (lean) TVAE_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<true, true>, maps, p));
     else TVAE_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<true, false>, maps, p));
   } else {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_set;
+    if (attr_set.pending()) {
       TVAE_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
       TVAE_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-      attr_set = true;
+      attr_set.mark();
     }
     const int total = p.m_tiles * p.n_tiles;
     int grid = num_sms();

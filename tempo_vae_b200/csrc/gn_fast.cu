@@ -299,31 +299,40 @@ gn_bwd_param_fast_kernel(const float* __restrict__ ws, int N, int C, float* __re
 // ---------------------------------------------------------------------------------------------------------------
 // GroupNorm backward in ONE pass over HBM (round 2). The two-kernel version above reads x and da twice (row sums, then
 // apply): 16 B/element for an fp32 x with a residual-branch gradient against 10 B for a single pass. Here one
-// persistent cooperative kernel (one 512-thread CTA per SM, all co-resident) walks the batch in groups of a few samples
-// that fit the 126 MB L2: phase A units (64 rows of one sample) produce the per-channel partial sums exactly like
-// gn_bwd_rowsum_fast_kernel; the LAST unit of a sample to finish (atomic ticket) reduces that sample's partials in fixed
-// order (bit-reproducible whoever does it), publishes S1/S2 and the group means and raises the sample's flag; phase B
-// units of the same group then re-read x and da -- served by L2, they were loaded microseconds ago -- and write dx.
-// Every CTA walks the same static unit list (A(g0), A(g1), B(g0), A(g2), B(g1), ...) strided by the grid size, so a B unit
-// only ever waits for A units that sit EARLIER in every CTA's list: no deadlock with co-resident CTAs, no grid-wide barrier. Streaming operands (gres, dx, and x/da on their second
-// read) use evict-first cache hints so they do not push the group out of L2.
-constexpr int GNF_THREADS = 256;
-constexpr int GNF_MIN_ROWS = 32;    // smallest rows-per-unit setting (sizes the partial-sum workspace)
+// persistent kernel (one CTA per SM, all co-resident: cooperative launch) walks the batch in groups of a few samples
+// that fit the 126 MB L2:
+//   phase A units (128 rows of one sample) produce the per-channel partial sums exactly like gn_bwd_rowsum_fast_kernel;
+//   the LAST unit of a sample to finish (atomic ticket) reduces that sample's partials in fixed order (bit-reproducible
+//   whoever does it), publishes S1/S2 and the group means and raises the sample's flag;
+//   phase B units of the same group then re-read x and da -- served by the L2, they were loaded microseconds ago -- and
+//   write dx.
+// Every CTA walks the same static unit list A(0), [A(1), B(0)], [A(2), B(1)], ..., B(last) strided by the grid size: a B
+// unit only ever waits for A units that sit EARLIER in every CTA's list (no deadlock with co-resident CTAs, no grid-wide
+// barrier), and by the time a CTA reaches B(g) that group's A units were handed out a whole group earlier.
+// Data path: a producer warp streams 32 KB stages (8-32 rows of x, da and, in phase B, gres) into a 6-deep shared-memory
+// ring with cp.async.bulk + mbarrier transaction counts; eight consumer warps compute from shared memory. A first
+// version with register-staged global loads moved the right number of bytes (ncu: 5.39 GB instead of 8.67 GB per
+// [256,64,64,512] call) but was latency-bound at one or two CTAs per SM (2.1 ms against 1.58 ms for the two kernels):
+// only ~100 KB in flight per SM and a chain of dependent round trips (partials, fence, ticket, flag) per unit. The ring
+// keeps ~190 KB in flight per SM whatever the consumers are doing. Second-read operands and the streams (gres, dx) carry
+// evict-first hints so they do not push the group out of L2.
+constexpr int GNR_CONSUMERS = 512;
+constexpr int GNR_THREADS = GNR_CONSUMERS + 32;
+constexpr int GNR_UNIT_ROWS = 128;
+constexpr int GNR_STAGE_BYTES = 32 * 1024;
+constexpr int GNR_STAGES = 6;
+constexpr size_t GNR_SMEM = (size_t)GNR_STAGES * GNR_STAGE_BYTES + GNR_CONSUMERS * 16 * sizeof(float) + 256 + 128 /*align*/;
+constexpr unsigned long long L2_EVICT_FIRST = 0x12F0000000000000ull;   // createpolicy.fractional.L2::evict_first, 1.0
+constexpr unsigned long long L2_EVICT_NORMAL = 0x1000000000000000ull;
 
-__device__ __forceinline__ void load8_stream(const float* p, float (&v)[8]) {
-  const float4 a = __ldcs(reinterpret_cast<const float4*>(p));
-  const float4 b = __ldcs(reinterpret_cast<const float4*>(p + 4));
-  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar,
+                                          unsigned long long policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+      ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
 }
-__device__ __forceinline__ void load8_stream(const __nv_bfloat16* p, float (&v)[8]) {
-  const uint4 d = __ldcs(reinterpret_cast<const uint4*>(p));
-  const uint32_t w[4] = {d.x, d.y, d.z, d.w};
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    v[2 * j] = bf16_bits_to_f(w[j] & 0xffffu);
-    v[2 * j + 1] = bf16_bits_to_f(w[j] >> 16);
-  }
-}
+__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(GNR_CONSUMERS) : "memory"); }
 __device__ __forceinline__ void store8_bf16_stream(__nv_bfloat16* p, const float (&v)[8]) {
   uint4 o;
   o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]);
@@ -339,108 +348,126 @@ __device__ __forceinline__ void st_release_gpu(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// raw (still packed) 8-channel row pieces: keeping them packed until use lets four rows be in flight per thread
-struct Raw8F { float4 a, b; };
-struct Raw8H { uint4 d; };
-template <bool STREAM> __device__ __forceinline__ Raw8F ldraw(const float* p) {
-  Raw8F r;
-  if (STREAM) { r.a = __ldcs(reinterpret_cast<const float4*>(p)); r.b = __ldcs(reinterpret_cast<const float4*>(p + 4)); }
-  else { r.a = *reinterpret_cast<const float4*>(p); r.b = *reinterpret_cast<const float4*>(p + 4); }
-  return r;
-}
-template <bool STREAM> __device__ __forceinline__ Raw8H ldraw(const __nv_bfloat16* p) {
-  Raw8H r;
-  if (STREAM) r.d = __ldcs(reinterpret_cast<const uint4*>(p));
-  else r.d = *reinterpret_cast<const uint4*>(p);
-  return r;
-}
-__device__ __forceinline__ void unpack(const Raw8F& r, float (&v)[8]) {
-  v[0] = r.a.x; v[1] = r.a.y; v[2] = r.a.z; v[3] = r.a.w; v[4] = r.b.x; v[5] = r.b.y; v[6] = r.b.z; v[7] = r.b.w;
-}
-__device__ __forceinline__ void unpack(const Raw8H& r, float (&v)[8]) {
-  const uint32_t w[4] = {r.d.x, r.d.y, r.d.z, r.d.w};
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    v[2 * j] = bf16_bits_to_f(w[j] & 0xffffu);
-    v[2 * j + 1] = bf16_bits_to_f(w[j] >> 16);
+struct GnUnit { int n, k, phase; };
+// unit t of the software-pipelined static list (groups padded to S samples; n >= N means "skip")
+__device__ __forceinline__ GnUnit gn_unit(long long t, int S, int Kc, int groups) {
+  const long long UG = (long long)S * Kc;
+  int g, phase;
+  long long local;
+  if (t < UG) { g = 0; phase = 0; local = t; }
+  else {
+    const long long tt = t - UG;
+    const int slot = (int)(tt / (2 * UG)) + 1;
+    const long long r = tt - (long long)(slot - 1) * 2 * UG;
+    if (slot == groups) { g = groups - 1; phase = 1; local = r; }
+    else if (r < UG) { g = slot; phase = 0; local = r; }
+    else { g = slot - 1; phase = 1; local = r - UG; }
   }
+  GnUnit u;
+  u.n = g * S + (int)(local / Kc);
+  u.k = (int)(local % Kc);
+  u.phase = phase;
+  return u;
 }
-template <typename TX> struct RawOf;
-template <> struct RawOf<float> { typedef Raw8F type; };
-template <> struct RawOf<__nv_bfloat16> { typedef Raw8H type; };
 
 template <typename TX>
-__global__ void __launch_bounds__(GNF_THREADS, 2)
-gn_bwd_fused_kernel(const TX* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gamma,
-                    const float* __restrict__ beta, const __nv_bfloat16* __restrict__ da,
-                    const __nv_bfloat16* __restrict__ gres, int N, int HW, int C, int G, int act, int S, int GNF_ROWS,
-                    float* __restrict__ part, float* __restrict__ ws, int* __restrict__ tickets, int* __restrict__ flags,
-                    __nv_bfloat16* __restrict__ dx, float* __restrict__ cs_part) {
-  typedef typename RawOf<TX>::type RawX;
-  extern __shared__ float sm[];     // [GNF_THREADS][16]
+__global__ void __launch_bounds__(GNR_THREADS, 1)
+gn_bwd_ring_kernel(const TX* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, const __nv_bfloat16* __restrict__ da,
+                   const __nv_bfloat16* __restrict__ gres, int N, int HW, int C, int G, int act, int S, int rs,
+                   float* __restrict__ part, float* __restrict__ ws, int* __restrict__ tickets, int* __restrict__ flags,
+                   __nv_bfloat16* __restrict__ dx, float* __restrict__ cs_part) {
+  extern __shared__ uint8_t gnr_raw[];
+  const uint32_t raw_addr = smem_u32(gnr_raw);
+  uint8_t* smem = gnr_raw + ((128u - (raw_addr & 127u)) & 127u);
+  float* red = reinterpret_cast<float*>(smem + GNR_STAGES * GNR_STAGE_BYTES);            // [GNR_CONSUMERS][16]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + GNR_STAGES * GNR_STAGE_BYTES + GNR_CONSUMERS * 16 * sizeof(float));
+  uint64_t* empty_bar = full_bar + GNR_STAGES;
   __shared__ int s_last;
-  const int U = C >> 3, lanes = GNF_THREADS / U;
-  const int u = threadIdx.x % U, lane = threadIdx.x / U;
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < GNR_STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], GNR_CONSUMERS / 32);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const int Kc = HW / GNR_UNIT_ROWS;
+  const int groups = (N + S - 1) / S;
+  const long long total = 2ll * groups * S * Kc;
+  const int nsub = GNR_UNIT_ROWS / rs;
+  const uint32_t x_bytes = (uint32_t)rs * C * sizeof(TX), h_bytes = (uint32_t)rs * C * 2;
+
+  if (warp == GNR_CONSUMERS / 32) {
+    // ------------------------------------------------------------------ producer: one lane streams the ring
+    if ((threadIdx.x & 31) == 0) {
+      int stage = 0;
+      uint32_t ph = 0;
+      for (long long t = blockIdx.x; t < total; t += gridDim.x) {
+        const GnUnit un = gn_unit(t, S, Kc, groups);
+        if (un.n >= N) continue;
+        const long long row0 = (long long)un.n * HW + (long long)un.k * GNR_UNIT_ROWS;
+        const bool with_res = un.phase && gres != nullptr;
+        const unsigned long long pol = un.phase ? L2_EVICT_FIRST : L2_EVICT_NORMAL;
+        for (int sub = 0; sub < nsub; ++sub) {
+          mbar_wait(&empty_bar[stage], ph ^ 1, 11);
+          uint8_t* st = smem + stage * GNR_STAGE_BYTES;
+          const long long e0 = (row0 + (long long)sub * rs) * C;
+          mbar_arrive_expect_tx(&full_bar[stage], x_bytes + h_bytes + (with_res ? h_bytes : 0u));
+          bulk_load(st, x + e0, x_bytes, &full_bar[stage], pol);
+          bulk_load(st + x_bytes, da + e0, h_bytes, &full_bar[stage], pol);
+          if (with_res) bulk_load(st + x_bytes + h_bytes, gres + e0, h_bytes, &full_bar[stage], L2_EVICT_FIRST);
+          if (++stage == GNR_STAGES) { stage = 0; ph ^= 1; }
+        }
+      }
+    }
+    return;
+  }
+
+  // -------------------------------------------------------------------- consumers (8 warps)
+  const int tid = threadIdx.x;
+  const int U = C >> 3, lanes = GNR_CONSUMERS / U;
+  const int u = tid % U, lane = tid / U;
   const int c = u << 3;
-  const int Kc = (HW + GNF_ROWS - 1) / GNF_ROWS;
   const int gs = C / G;
   const int gidx = c / gs;
+  const int rpt = rs / lanes;                 // rows per thread per stage
   float cs[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) cs[j] = 0.f;
-  // Static unit list, software-pipelined by one group: A(0), [A(1), B(0)], [A(2), B(1)], ..., B(last). When a CTA
-  // reaches the B units of group g, that group's A units were handed out a whole group earlier, so its flags are
-  // (almost always) already up and nobody idles; the L2 holds two groups. Groups are padded to S samples
-  // (units of samples >= N are skipped), which keeps the index arithmetic closed-form.
-  const int groups = (N + S - 1) / S;
-  const long long UG = (long long)S * Kc;                 // units of one group in one phase
-  const long long total = 2ll * groups * UG;
+  int stage = 0;
+  uint32_t ph = 0;
   for (long long t = blockIdx.x; t < total; t += gridDim.x) {
-    int g, phase;
-    long long local;
-    if (t < UG) { g = 0; phase = 0; local = t; }
-    else {
-      const long long tt = t - UG;
-      const int slot = (int)(tt / (2 * UG)) + 1;
-      const long long r = tt - (long long)(slot - 1) * 2 * UG;
-      if (slot == groups) { g = groups - 1; phase = 1; local = r; }
-      else if (r < UG) { g = slot; phase = 0; local = r; }
-      else { g = slot - 1; phase = 1; local = r - UG; }
-    }
-    const int n = g * S + (int)(local / Kc), k = (int)(local % Kc);
-    if (n >= N) continue;
+    const GnUnit un = gn_unit(t, S, Kc, groups);
+    if (un.n >= N) continue;
+    const int n = un.n, k = un.k;
     const int sg = n * G + gidx;
     const float mean = stats[2 * sg], rstd = stats[2 * sg + 1];
     float sc[8], sh[8];
-    load8(gamma + c, sc);            // (L1-resident after the first unit; not worth 16 registers across units)
+    load8(gamma + c, sc);
     load8(beta + c, sh);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       sc[j] *= rstd;
       sh[j] = fmaf(-mean, sc[j], sh[j]);
     }
-    const int r0 = k * GNF_ROWS;
-    const int r1 = min(r0 + GNF_ROWS, HW);
-    const long long base = (long long)n * HW * C + c;
-    if (!phase) {
+    const long long row0 = (long long)n * HW + (long long)k * GNR_UNIT_ROWS;
+    if (!un.phase) {
       // ---------------------------------------------------------------- phase A: per-channel sums of dy and dy*x
       float s1[8], s2[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
-      int rr = r0 + lane;
-      for (; rr + 3 * lanes < r1; rr += 4 * lanes) {           // four rows in flight per thread
-        RawX xr[4];
-        Raw8H dr[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          xr[q] = ldraw<false>(x + base + (long long)(rr + q * lanes) * C);
-          dr[q] = ldraw<false>(da + base + (long long)(rr + q * lanes) * C);
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
+      for (int sub = 0; sub < nsub; ++sub) {
+        mbar_wait(&full_bar[stage], ph, 12);
+        const uint8_t* st = smem + stage * GNR_STAGE_BYTES;
+        const TX* xs = reinterpret_cast<const TX*>(st);
+        const __nv_bfloat16* ds = reinterpret_cast<const __nv_bfloat16*>(st + x_bytes);
+        for (int q = 0; q < rpt; ++q) {
+          const int r = lane + q * lanes;
           float xv[8], dv[8];
-          unpack(xr[q], xv);
-          unpack(dr[q], dv);
+          load8x(xs + (size_t)r * C + c, xv);
+          load8_bf16(ds + (size_t)r * C + c, dv);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float dy = dv[j];
@@ -449,54 +476,44 @@ gn_bwd_fused_kernel(const TX* __restrict__ x, const float* __restrict__ stats, c
             s2[j] = fmaf(dy, xv[j], s2[j]);
           }
         }
-      }
-      for (; rr < r1; rr += lanes) {
-        float xv[8], dv[8];
-        load8x(x + base + (long long)rr * C, xv);
-        load8_bf16(da + base + (long long)rr * C, dv);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float dy = dv[j];
-          if (act) dy *= act_grad_fast(fmaf(xv[j], sc[j], sh[j]), act);
-          s1[j] += dy;
-          s2[j] = fmaf(dy, xv[j], s2[j]);
-        }
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(&empty_bar[stage]);
+        if (++stage == GNR_STAGES) { stage = 0; ph ^= 1; }
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) s2[j] = (s2[j] - mean * s1[j]) * rstd;     // sum dy*x  ->  sum dy*xhat
-      float* mine = sm + (size_t)threadIdx.x * 16;
+      float* mine = red + (size_t)tid * 16;
 #pragma unroll
       for (int j = 0; j < 8; ++j) { mine[j] = s1[j]; mine[8 + j] = s2[j]; }
-      __syncthreads();
+      consumer_bar();
       float* out = part + ((long long)n * Kc + k) * 2 * C;
-      for (int q = threadIdx.x; q < U * 16; q += GNF_THREADS) {
+      for (int q = tid; q < U * 16; q += GNR_CONSUMERS) {
         const int uu = q >> 4, kk = q & 15;
         float acc = 0.f;
-        for (int l = 0; l < lanes; ++l) acc += sm[(size_t)(l * U + uu) * 16 + kk];   // fixed order
+        for (int l = 0; l < lanes; ++l) acc += red[(size_t)(l * U + uu) * 16 + kk];   // fixed order
         __stcg(out + (kk >> 3) * C + (uu << 3) + (kk & 7), acc);
       }
-      __syncthreads();
-      if (threadIdx.x == 0) {
+      consumer_bar();
+      if (tid == 0) {
         __threadfence();                                     // release the CTA's partials (cumulative over the barrier)
         s_last = (atomicAdd(tickets + n, 1) == Kc - 1);
       }
-      __syncthreads();
+      consumer_bar();
       if (s_last) {
         // -------------------------------------------------------------- the sample's last unit: finalize (fixed order)
         __threadfence();
         const float* pn = part + (long long)n * Kc * 2 * C;
-        float* smf = sm;             // [2][C]
-        for (int cc = threadIdx.x; cc < 2 * C; cc += GNF_THREADS) {
+        float* smf = red;             // [2][C]
+        for (int cc = tid; cc < 2 * C; cc += GNR_CONSUMERS) {
           float a = 0.f;
 #pragma unroll 8
           for (int q = 0; q < Kc; ++q) a += __ldcg(pn + (long long)q * 2 * C + cc);
-          // cc < C: S1 (sum dy) -> ws[n][c]; else S2 (sum dy*xhat) -> ws[N + n][c]
           const int ch = cc < C ? cc : cc - C;
-          ws[((long long)(cc < C ? 0 : N) + n) * C + ch] = a;
+          ws[((long long)(cc < C ? 0 : N) + n) * C + ch] = a;               // S1 (sum dy) | S2 (sum dy*xhat)
           smf[cc] = a * gamma[ch];
         }
-        __syncthreads();
-        for (int gg = threadIdx.x; gg < G; gg += GNF_THREADS) {
+        consumer_bar();
+        for (int gg = tid; gg < G; gg += GNR_CONSUMERS) {
           float t1 = 0.f, t2 = 0.f;
           for (int j = 0; j < gs; ++j) { t1 += smf[gg * gs + j]; t2 += smf[C + gg * gs + j]; }
           const float inv = 1.0f / ((float)HW * (float)gs);
@@ -504,48 +521,43 @@ gn_bwd_fused_kernel(const TX* __restrict__ x, const float* __restrict__ stats, c
           __stcg(gm_out, t1 * inv);
           __stcg(gm_out + 1, t2 * inv);
         }
-        __syncthreads();
-        if (threadIdx.x == 0) {
+        consumer_bar();
+        if (tid == 0) {
           __threadfence();
           st_release_gpu(flags + n, 1);
         }
       }
-      __syncthreads();           // sm is reused by the next unit
+      consumer_bar();            // `red` is reused by the next unit
     } else {
       // ---------------------------------------------------------------- phase B: dx (x and da come from L2)
-      if (threadIdx.x == 0) {
+      if (tid == 0) {
         long long t0 = clock64();
         while (ld_acquire_gpu(flags + n) == 0) {
           __nanosleep(64);
           if (clock64() - t0 > TVAE_WAIT_TIMEOUT_CYCLES) {
-            printf("tvae: gn_bwd_fused flag wait timeout sample=%d block=%d\n", n, (int)blockIdx.x);
+            printf("tvae: gn_bwd_ring flag wait timeout sample=%d block=%d\n", n, (int)blockIdx.x);
             __trap();
           }
         }
       }
-      __syncthreads();
+      consumer_bar();
       const float* gmeans = ws + 2ll * N * C;
       const float m1 = __ldcg(gmeans + 2 * sg), m2 = __ldcg(gmeans + 2 * sg + 1);
       const float ta = m2 * rstd * rstd;
       const float tb = m1 * rstd - mean * ta;
-      int rr = r0 + lane;
-      for (; rr + 3 * lanes < r1; rr += 4 * lanes) {           // four rows in flight per thread
-        RawX xr[4];
-        Raw8H dr[4], gr4[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const long long off = base + (long long)(rr + q * lanes) * C;
-          xr[q] = ldraw<true>(x + off);
-          dr[q] = ldraw<true>(da + off);
-          if (gres) gr4[q] = ldraw<true>(gres + off);
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
+      for (int sub = 0; sub < nsub; ++sub) {
+        mbar_wait(&full_bar[stage], ph, 13);
+        const uint8_t* st = smem + stage * GNR_STAGE_BYTES;
+        const TX* xs = reinterpret_cast<const TX*>(st);
+        const __nv_bfloat16* ds = reinterpret_cast<const __nv_bfloat16*>(st + x_bytes);
+        const __nv_bfloat16* gsm = reinterpret_cast<const __nv_bfloat16*>(st + x_bytes + h_bytes);
+        for (int q = 0; q < rpt; ++q) {
+          const int r = lane + q * lanes;
           float xv[8], dv[8], rv[8], o[8];
-          unpack(xr[q], xv);
-          unpack(dr[q], dv);
+          load8x(xs + (size_t)r * C + c, xv);
+          load8_bf16(ds + (size_t)r * C + c, dv);
           if (gres) {
-            unpack(gr4[q], rv);
+            load8_bf16(gsm + (size_t)r * C + c, rv);
           } else {
 #pragma unroll
             for (int j = 0; j < 8; ++j) rv[j] = 0.f;
@@ -557,41 +569,24 @@ gn_bwd_fused_kernel(const TX* __restrict__ x, const float* __restrict__ stats, c
             o[j] = fmaf(dy, sc[j], rv[j]) - fmaf(xv[j], ta, tb);
             cs[j] += o[j];
           }
-          store8_bf16_stream(dx + base + (long long)(rr + q * lanes) * C, o);
+          store8_bf16_stream(dx + (row0 + (long long)sub * rs + r) * C + c, o);
         }
-      }
-      for (; rr < r1; rr += lanes) {
-        const long long o0 = base + (long long)rr * C;
-        float xa[8], d0[8], ra[8], oa[8];
-        load8_stream(x + o0, xa);
-        load8_stream(da + o0, d0);
-        if (gres) {
-          load8_stream(gres + o0, ra);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) ra[j] = 0.f;
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float dy0 = d0[j];
-          if (act) dy0 *= act_grad_fast(fmaf(xa[j], sc[j], sh[j]), act);
-          oa[j] = fmaf(dy0, sc[j], ra[j]) - fmaf(xa[j], ta, tb);
-          cs[j] += oa[j];
-        }
-        store8_bf16_stream(dx + o0, oa);
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(&empty_bar[stage]);
+        if (++stage == GNR_STAGES) { stage = 0; ph ^= 1; }
       }
     }
   }
   if (cs_part) {       // column sums of dx over every unit this CTA applied (static schedule => reproducible)
-    __syncthreads();
+    consumer_bar();
 #pragma unroll
-    for (int j = 0; j < 8; ++j) sm[threadIdx.x * 8 + j] = cs[j];
-    __syncthreads();
+    for (int j = 0; j < 8; ++j) red[tid * 8 + j] = cs[j];
+    consumer_bar();
     float* out = cs_part + (long long)blockIdx.x * C;
-    for (int q = threadIdx.x; q < U * 8; q += GNF_THREADS) {
+    for (int q = tid; q < U * 8; q += GNR_CONSUMERS) {
       const int uu = q >> 3, kk = q & 7;
       float acc = 0.f;
-      for (int l = 0; l < lanes; ++l) acc += sm[(l * U + uu) * 8 + kk];   // fixed order
+      for (int l = 0; l < lanes; ++l) acc += red[(l * U + uu) * 8 + kk];   // fixed order
       out[(uu << 3) + kk] = acc;
     }
   }
@@ -628,62 +623,64 @@ long long gn_bwd_fast_ws_floats(int N, int HW, int C, int G) {
   const int rpb = rows_per_block(HW);
   const long long chunks = (HW + rpb - 1) / rpb;
   const long long two_pass = 2ll * N * C + 2ll * N * G + (long long)N * chunks * 2 * C + (long long)CS_SLICES * C;
-  const long long kc = (HW + GNF_MIN_ROWS - 1) / GNF_MIN_ROWS;
+  const long long kc = (HW + GNR_UNIT_ROWS - 1) / GNR_UNIT_ROWS;
   const long long fused = 2ll * N * C + 2ll * N * G + (long long)N * kc * 2 * C + (long long)(GNF_MAX_GRID + CS_SLICES) * C +
                           2ll * N + 64;
   return two_pass > fused ? two_pass : fused;
 }
 
-// 1: the single-pass persistent kernel for tensors that do not fit L2; 0: always the two-pass kernels (A/B switch,
-// TVAE_GN_BWD_FUSED / tvae_gn_set_bwd_fused). group_mb: megabytes of (x + da) per L2-resident group.
+// 0: always the two-pass kernels; 1: the single-pass persistent kernel for tensors that do not fit the L2; 2: the single
+// pass whatever the size (tests). TVAE_GN_BWD_FUSED / tvae_gn_set_bwd_fused. group_mb: megabytes of (x + da) per
+// L2-resident group.
 static int g_gn_fused = -1;
 static int g_gn_group_mb = 24;
-static int g_gn_rows = 128;         // rows per unit (TVAE_GN_ROWS: 32, 64 or 128)
-static int g_gn_ctas = 2;           // CTAs per SM (TVAE_GN_CTAS: 1 or 2)
 static void gn_read_env() {
   if (g_gn_fused >= 0) return;
-  // Default OFF (measured, B200, [256,64,64,512] fp32 x + gres): the single pass moves 5.39 GB instead of 8.67 GB
-  // (ncu dram bytes: the L2 hand-over works) but takes 2.1 ms against 1.58 ms for the two kernels -- with one or two
-  // CTAs per SM and register-staged loads it is latency-bound (~100 KB in flight per SM, synchronous per iteration).
-  // TVAE_GN_BWD_FUSED=1 / tvae_gn_set_bwd_fused(1, mb) turns it on; see DESIGN.md section 8.
+  // Default OFF. Measured on B200, [256,64,64,512] (profiles/gn_bwd_single_pass_r2.md): the single pass moves 5.39 GB
+  // instead of 8.67 GB (ncu dram bytes -- the L2 hand-over works) but takes 2.05 ms against 1.59 ms for the two kernels:
+  // it is bound by instruction issue, not by bytes (same time for 5.4 GB fp32+gres and 3.2 GB bf16 inputs; 2.73 ms with
+  // 8 consumer warps, 2.05 ms with 16), because GELU' is evaluated in both phases (~50 instructions per element) and one
+  // CTA per SM leaves 16 warps to hide the MUFU / shared-memory latencies where the two-pass kernels have 64.
   const char* e = getenv("TVAE_GN_BWD_FUSED");
   g_gn_fused = (e && e[0] == '1') ? 1 : 0;
   const char* m = getenv("TVAE_GN_GROUP_MB");
   if (m && atoi(m) > 0) g_gn_group_mb = atoi(m);
-  const char* r = getenv("TVAE_GN_ROWS");
-  if (r && (atoi(r) == 32 || atoi(r) == 64 || atoi(r) == 128)) g_gn_rows = atoi(r);
-  const char* c = getenv("TVAE_GN_CTAS");
-  if (c && (atoi(c) == 1 || atoi(c) == 2)) g_gn_ctas = atoi(c);
 }
 void gn_set_bwd_fused(int on, int group_mb) {
   gn_read_env();
-  g_gn_fused = on == 2 ? 2 : (on ? 1 : 0);      // 2: the single-pass kernel whatever the tensor size (tests)
+  g_gn_fused = on == 2 ? 2 : (on ? 1 : 0);
   if (group_mb > 0) g_gn_group_mb = group_mb;
 }
 
+// rows per ring stage: the largest power of two whose x + da + gres rows fit GNR_STAGE_BYTES (at most 32)
+static int gn_ring_rows(int C, int xbytes) {
+  int rs = 32;
+  while (rs > 1 && (long long)rs * C * (xbytes + 4) > GNR_STAGE_BYTES) rs >>= 1;
+  return rs;
+}
+static bool gn_ring_ok(int HW, int C, int xbytes) {
+  if (C % 8 || GNR_CONSUMERS % (C / 8) || 2 * C > GNR_CONSUMERS * 16 || HW % GNR_UNIT_ROWS) return false;
+  const int rs = gn_ring_rows(C, xbytes), lanes = GNR_CONSUMERS / (C / 8);
+  return rs >= lanes && rs % lanes == 0 && GNR_UNIT_ROWS % rs == 0 && (long long)rs * C * (xbytes + 4) <= GNR_STAGE_BYTES;
+}
+
 template <typename TX>
-static int launch_gn_bwd_fused(const TX* x, const float* stats, const float* gamma, const float* beta,
-                               const __nv_bfloat16* da, const __nv_bfloat16* gres, int N, int HW, int C, int G, int act,
-                               __nv_bfloat16* dx, float* dgamma, float* dbeta, float* dx_colsum, float* ws,
-                               cudaStream_t stream) {
-  static int max_ctas[64] = {0};
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -1;
-  const size_t smem = (size_t)GNF_THREADS * 16 * sizeof(float);
-  if (max_ctas[dev] == 0) {
-    int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gn_bwd_fused_kernel<TX>, GNF_THREADS, smem) != cudaSuccess ||
-        per_sm < 1)
+static int launch_gn_bwd_ring(const TX* x, const float* stats, const float* gamma, const float* beta,
+                              const __nv_bfloat16* da, const __nv_bfloat16* gres, int N, int HW, int C, int G, int act,
+                              __nv_bfloat16* dx, float* dgamma, float* dbeta, float* dx_colsum, float* ws,
+                              cudaStream_t stream) {
+  static PerDeviceOnce attr_set;
+  if (attr_set.pending()) {
+    if (cudaFuncSetAttribute(gn_bwd_ring_kernel<TX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GNR_SMEM) != cudaSuccess)
       return -1;
-    max_ctas[dev] = num_sms() * (per_sm < g_gn_ctas ? per_sm : g_gn_ctas);    // all co-resident (cooperative launch)
+    attr_set.mark();
   }
-  int GNF_ROWS = g_gn_rows;
-  const int Kc = (HW + GNF_ROWS - 1) / GNF_ROWS;
+  const int Kc = HW / GNR_UNIT_ROWS;
   const long long per_sample = (long long)HW * C * (sizeof(TX) + 2);
   long long S = ((long long)g_gn_group_mb << 20) / per_sample;
   if (S < 1) S = 1;
   if (S > N) S = N;
-  int grid = max_ctas[dev];
+  int grid = num_sms();                       // one CTA per SM, all co-resident (cooperative launch)
   const long long units = 2ll * N * Kc;
   if (grid > units) grid = (int)units;
   if (grid > GNF_MAX_GRID) grid = GNF_MAX_GRID;
@@ -694,12 +691,13 @@ static int launch_gn_bwd_fused(const TX* x, const float* stats, const float* gam
   int* flags = tickets + N;
   if (cudaMemsetAsync(tickets, 0, 2ull * N * sizeof(int), stream) != cudaSuccess) return -1;
   int Si = (int)S;
+  int rs = gn_ring_rows(C, (int)sizeof(TX));
   float* cs_arg = dx_colsum ? cs_part : nullptr;
   void* args[] = {(void*)&x, (void*)&stats, (void*)&gamma, (void*)&beta, (void*)&da, (void*)&gres, (void*)&N, (void*)&HW,
-                  (void*)&C, (void*)&G, (void*)&act, (void*)&Si, (void*)&GNF_ROWS, (void*)&part, (void*)&ws, (void*)&tickets, (void*)&flags,
-                  (void*)&dx, (void*)&cs_arg};
-  if (cudaLaunchCooperativeKernel((const void*)gn_bwd_fused_kernel<TX>, dim3(grid), dim3(GNF_THREADS), args, smem, stream) !=
-      cudaSuccess)
+                  (void*)&C, (void*)&G, (void*)&act, (void*)&Si, (void*)&rs, (void*)&part, (void*)&ws, (void*)&tickets,
+                  (void*)&flags, (void*)&dx, (void*)&cs_arg};
+  if (cudaLaunchCooperativeKernel((const void*)gn_bwd_ring_kernel<TX>, dim3(grid), dim3(GNR_THREADS), args, GNR_SMEM,
+                                  stream) != cudaSuccess)
     return -1;
   gn_bwd_param_fast_kernel<<<(C + 31) / 32, 256, 0, stream>>>(ws, N, C, dgamma, dbeta);
   if (dx_colsum) {
@@ -721,16 +719,15 @@ int gn_act_bwd_fast(const void* xv, bool x_bf16, const float* stats, const float
   const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(xv);
   gn_read_env();
   // Tensors that fit the L2 anyway get their second pass from it with the two-kernel version; the persistent kernel
-  // is for the ones that do not (>= 96 MB of x + da), with at least a unit of work per sample
+  // is for the ones that do not (>= 96 MB of x + da)
   const long long bytes = (long long)N * HW * C * ((x_bf16 ? 2 : 4) + 2);
-  if (((g_gn_fused == 1 && bytes >= (96ll << 20)) || g_gn_fused == 2) && HW >= g_gn_rows && GNF_THREADS % (C / 8) == 0 &&
-      2 * C <= GNF_THREADS * 16) {
-    const int rc = x_bf16 ? launch_gn_bwd_fused(xb, stats, gamma, beta, da, gres, N, HW, C, G, act, dx, dgamma, dbeta,
-                                                dx_colsum, ws, stream)
-                          : launch_gn_bwd_fused(x, stats, gamma, beta, da, gres, N, HW, C, G, act, dx, dgamma, dbeta,
-                                                dx_colsum, ws, stream);
+  if (((g_gn_fused == 1 && bytes >= (96ll << 20)) || g_gn_fused == 2) && gn_ring_ok(HW, C, x_bf16 ? 2 : 4)) {
+    const int rc = x_bf16 ? launch_gn_bwd_ring(xb, stats, gamma, beta, da, gres, N, HW, C, G, act, dx, dgamma, dbeta,
+                                               dx_colsum, ws, stream)
+                          : launch_gn_bwd_ring(x, stats, gamma, beta, da, gres, N, HW, C, G, act, dx, dgamma, dbeta,
+                                               dx_colsum, ws, stream);
     if (rc == 0) return 0;
-    set_error("gn_bwd_fused: cooperative launch failed");
+    set_error("gn_bwd_ring: cooperative launch failed (%s)", cudaGetErrorString(cudaGetLastError()));
     return -1;
   }
   if (x_bf16)

@@ -18,6 +18,21 @@ int enter(const void* device_ptr);
     if (tvae::enter(ptr) != 0) return -4;    \
   } while (0)
 
+// Kernel attributes (e.g. the dynamic shared-memory limit) are PER DEVICE: a process that drives several GPUs must set
+// them once on each (a plain `static bool` set on device 0 leaves device 1 with the 48 KB default and the launch fails
+// with "invalid argument"). Setting an attribute twice is harmless, so no lock: check, set, then mark.
+struct PerDeviceOnce {
+  bool done[64] = {};
+  bool pending() const {
+    int d = 0;
+    return cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64 || !done[d];
+  }
+  void mark() {
+    int d = 0;
+    if (cudaGetDevice(&d) == cudaSuccess && d >= 0 && d < 64) done[d] = true;
+  }
+};
+
 // Encode a bf16 tiled tensor map with 128-byte swizzle and zero out-of-bounds fill.
 // dims/box are innermost-first; strides (bytes) are for dims 1..rank-1. Returns 0 on success.
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,

@@ -414,10 +414,10 @@ extern "C" int32_t tvae_wgrad_gemm(const tvae_wgrad_args* a, cudaStream_t stream
   p.part_row0 = 0;
   if (pair) {
     p.nq = (p.bn / 2 + 63) / 64;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_set;
+    if (attr_set.pending()) {
       TVAE_CUDA(cudaFuncSetAttribute(wgrad_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-      attr_set = true;
+      attr_set.mark();
     }
     const int total = (main_tiles / 2) * p.n_tiles * p.ntaps * p.splits;
     int grid = num_sms() / 2;
@@ -434,10 +434,10 @@ extern "C" int32_t tvae_wgrad_gemm(const tvae_wgrad_args* a, cudaStream_t stream
     TVAE_CUDA(cudaLaunchKernelEx(&cfg, wgrad_gemm_kernel<true>, maps, p));
   } else {
     p.nq = (p.bn + 63) / 64;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_set;
+    if (attr_set.pending()) {
       TVAE_CUDA(cudaFuncSetAttribute(wgrad_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-      attr_set = true;
+      attr_set.mark();
     }
     const int total = main_tiles * p.n_tiles * p.ntaps * p.splits;
     int grid = num_sms();
@@ -453,10 +453,10 @@ extern "C" int32_t tvae_wgrad_gemm(const tvae_wgrad_args* a, cudaStream_t stream
 
   // ---- odd last M tile: one CTA per SM, its own split-K factor and its own workspace region
   if (rem_tiles) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_set;
+    if (attr_set.pending()) {
       TVAE_CUDA(cudaFuncSetAttribute(wgrad_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-      attr_set = true;
+      attr_set.mark();
     }
     p.mt0 = main_tiles;
     p.m_tiles = 1;
