@@ -73,6 +73,10 @@ int32_t tvae_conv_gemm(const tvae_conv_args* args, tvae_stream_t stream);
  * that share one 256-row tcgen05 MMA (cta_group::2, each SM stages half of the weight tile, a third less operand
  * traffic per SM); 0 runs one CTA per SM. Returns the previous setting. Process-wide; for A/B measurements and tests. */
 int32_t tvae_conv_set_cta_pair(int32_t enable);
+/* Profiling aid: a per-tile timeline of the conv kernel's producer / MMA / epilogue warps (SM clock cycles, 8 u64 words
+ * per (unit, tile): see ConvParams::trace in csrc/conv_gemm.cu and tools/conv_trace.py). device_buffer = NULL turns it
+ * off (default); the buffer holds num_SMs * tiles_per_unit * 8 words. */
+int32_t tvae_conv_set_trace(void* device_buffer, int32_t tiles_per_unit);
 
 /* Weight gradient: grad[m][n][tap] (=|+=) sum_pixels P[pixel][m] * Q[pixel (+) tap][n].
  * Replaces autograd's weight-gradient of the same call sites.

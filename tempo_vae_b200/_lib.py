@@ -66,6 +66,7 @@ def _load():
         "tvae_abi_version": (i32, []),
         "tvae_conv_gemm": (i32, [C.POINTER(ConvArgs), vp]),
         "tvae_conv_set_cta_pair": (i32, [i32]),
+        "tvae_conv_set_trace": (i32, [vp, i32]),
         "tvae_wgrad_gemm": (i32, [C.POINTER(WgradArgs), vp]),
         "tvae_wgrad_set_cta_pair": (i32, [i32]),
         "tvae_wgrad_workspace_bytes": (i64, [i32, i32, i32, i32]),

@@ -67,6 +67,12 @@ struct ConvParams {
   int gs, G;           // group size (multiple of 16, divides BN), number of groups
   int split_chunk;     // first 16-column chunk handled by the second warp of each TMEM lane quarter
   int wide;            // bit 0/1/2: fp32 output / bf16 output / residual rows are 32-byte aligned => 256-bit accesses
+  // optional per-tile timeline (tools/conv_trace.py): trace[(unit * trace_cap + tile) * 8 + j], SM clock cycles:
+  // 0 MMA warp before the accumulator-free wait, 1 after it, 2 after the first operand stage arrived, 3 after the last
+  // K block was issued, 4 cycles spent waiting for the other operand stages, 5 epilogue: accumulator ready, 6 epilogue
+  // done, 7 producer: first load of the tile issued
+  unsigned long long* trace;
+  int trace_cap;
 };
 
 // PAIR = true: launched as clusters of two CTAs (one TPC). The pair owns two vertically adjacent M tiles and one
@@ -146,6 +152,10 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
         const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.bnimg;   // past the last image for the odd tail: zero fill
         const int brow = nt * p.bn + (PAIR ? (int)rank * (p.bn >> 1) : 0);
         int kb = 0;
+        if (p.trace && rank == 0 && lane == 0) {
+          const int ti = (t - unit0) / nunits;
+          if (ti < p.trace_cap) p.trace[((long long)unit0 * p.trace_cap + ti) * 8 + 7] = (unsigned long long)clock64();
+        }
         for (int tap = 0; tap < p.ntaps; ++tap) {
           const int hh = h0 + p.dh[tap], ww = w0 + p.dw[tap];
           for (int cb = 0; cb < p.cblks; ++cb, ++kb) {
@@ -185,15 +195,25 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
       int as = 0;
       uint32_t aphase = 0;
       for (int t = unit0; t < total_tiles; t += nunits) {
+        const bool tr = p.trace != nullptr;
+        long long tr0 = 0, tr1 = 0, tr2 = 0, trw = 0;
+        if (tr) tr0 = clock64();
         mbar_wait(&tempty_bar[as], aphase ^ 1, 2);
         tc_fence_after();
+        if (tr) tr1 = clock64();
         const uint32_t d_tmem = tmem_base + (uint32_t)as * 256u;
         int kb = 0;
         for (int tap = 0; tap < p.ntaps; ++tap) {
           for (int cb = 0; cb < p.cblks; ++cb, ++kb) {
             for (int seg = 0; seg < p.nseg; ++seg) {
+              long long trc = 0;
+              if (tr) trc = clock64();
               mbar_wait(&full_bar[stage], phase, 3);
               tc_fence_after();
+              if (tr) {
+                const long long now = clock64();
+                if (kb == 0 && seg == 0) tr2 = now; else trw += now - trc;
+              }
               const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
               const uint64_t da = make_smem_desc_sw128(sa, 16, 1024);
               const uint64_t db = make_smem_desc_sw128(sa + A_STAGE_BYTES, 16, 1024);
@@ -218,6 +238,13 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
             }
           }
         }
+        if (tr && lane == 0) {
+          const int ti = (t - unit0) / nunits;
+          if (ti < p.trace_cap) {
+            unsigned long long* rec = p.trace + ((long long)unit0 * p.trace_cap + ti) * 8;
+            rec[0] = tr0; rec[1] = tr1; rec[2] = tr2; rec[3] = clock64(); rec[4] = trw;
+          }
+        }
         as ^= 1;
         if (as == 0) aphase ^= 1;
       }
@@ -239,6 +266,11 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
       const int mt = m_tile_of(t), nt = t % p.n_tiles;
       mbar_wait(&tfull_bar[as], aphase, 4);
       tc_fence_after();
+      const bool etr = p.trace != nullptr && rank == 0 && warp == 2 && lane == 0;
+      if (etr) {
+        const int ti = (t - unit0) / nunits;
+        if (ti < p.trace_cap) p.trace[((long long)unit0 * p.trace_cap + ti) * 8 + 5] = (unsigned long long)clock64();
+      }
       const long long pix = (long long)mt * BM + row;
       const bool row_ok = pix < p.m_total;
       int col0 = nt * p.bn;   // column in the (tap, cout) / cout space
@@ -385,6 +417,10 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
       }
       tc_fence_before();
       __syncwarp();
+      if (etr) {
+        const int ti = (t - unit0) / nunits;
+        if (ti < p.trace_cap) p.trace[((long long)unit0 * p.trace_cap + ti) * 8 + 6] = (unsigned long long)clock64();
+      }
       if (lane == 0) {
         if (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[as]), 0));
         else mbar_arrive(&tempty_bar[as]);
@@ -411,6 +447,8 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
 // 96 B/clk/SM of operand traffic that the pair schedule cuts to 64 B/clk/SM.
 int g_conv_cta_pair = 1;
 int g_conv_lean_epilogue = 1;
+unsigned long long* g_conv_trace = nullptr;
+int g_conv_trace_cap = 0;
 
 int pick_bn(int cout) {
   if (cout <= 256) return (cout + 15) / 16 * 16;
@@ -541,6 +579,8 @@ extern "C" int32_t tvae_conv_gemm(const tvae_conv_args* a, cudaStream_t stream) 
   }
 
   p.stats_part = a->stats_part;
+  p.trace = g_conv_trace;
+  p.trace_cap = g_conv_trace_cap;
   if (p.stats_part) {
     p.G = a->stats_groups;
     TVAE_CHECK(p.G > 0 && a->Cout % p.G == 0, "tvae_conv_gemm: stats_groups must divide Cout");
@@ -618,6 +658,12 @@ extern "C" int32_t tvae_conv_gemm(const tvae_conv_args* a, cudaStream_t stream) 
     else conv_gemm_kernel<false, false><<<grid, NTHREADS, SMEM_BYTES, stream>>>(maps, p);
   }
   TVAE_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int32_t tvae_conv_set_trace(void* device_buffer, int32_t tiles_per_unit) {
+  g_conv_trace = reinterpret_cast<unsigned long long*>(device_buffer);
+  g_conv_trace_cap = device_buffer ? tiles_per_unit : 0;
   return 0;
 }
 
