@@ -83,7 +83,7 @@ struct ConvParams {
 // lives in the leader and collects the 16 epilogue warps of both CTAs.
 // LEAN = true: the epilogue of the data-gradient launches (bf16 output only: no fp32 output, residual, statistics,
 // split-bf16 half or pixel-shuffle scatter) with those feature paths compiled out.
-template <bool PAIR, bool LEAN>
+template <bool PAIR, bool LEAN, bool TRACE = false>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ ConvParams p) {
   constexpr int STAGES = PAIR ? PAIR_STAGES : tvae::STAGES;
@@ -152,7 +152,7 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
         const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.bnimg;   // past the last image for the odd tail: zero fill
         const int brow = nt * p.bn + (PAIR ? (int)rank * (p.bn >> 1) : 0);
         int kb = 0;
-        if (p.trace && rank == 0 && lane == 0) {
+        if (TRACE && p.trace && rank == 0 && lane == 0) {
           const int ti = (t - unit0) / nunits;
           if (ti < p.trace_cap) p.trace[((long long)unit0 * p.trace_cap + ti) * 8 + 7] = (unsigned long long)clock64();
         }
@@ -190,12 +190,18 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
     // tensor work) as long as the whole loop lived inside a single-lane branch.
     if (rank == 0) {
       const uint32_t idesc = make_idesc_bf16(PAIR ? 2 * BM : BM, p.bn, 0, 0);
+      // Shared-memory descriptors are advanced incrementally (start address field += stage bytes >> 4) and everything an
+      // MMA needs is pinned in registers BEFORE the wait on the operand stage: the ring is usually empty when the warp
+      // asks (profiles/conv_trace_r2.md), so every instruction between "stage arrived" and the first UTCHMMA is idle
+      // tensor time.
+      const uint64_t desc0 = make_smem_desc_sw128(smem_u32(smem), 16, 1024);
+      uint64_t da = desc0;
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
       for (int t = unit0; t < total_tiles; t += nunits) {
-        const bool tr = p.trace != nullptr;
+        const bool tr = TRACE && p.trace != nullptr;
         long long tr0 = 0, tr1 = 0, tr2 = 0, trw = 0;
         if (tr) tr0 = clock64();
         mbar_wait(&tempty_bar[as], aphase ^ 1, 2);
@@ -206,35 +212,52 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
         for (int tap = 0; tap < p.ntaps; ++tap) {
           for (int cb = 0; cb < p.cblks; ++cb, ++kb) {
             for (int seg = 0; seg < p.nseg; ++seg) {
+              const uint64_t db = da + (uint64_t)(A_STAGE_BYTES >> 4);
+              const int nk = (cb == p.cblks - 1) ? p.last_k16 : 4;
+              const bool last = (kb == p.num_kb - 1) && (seg == p.nseg - 1);
+              const uint32_t acc0 = (kb | seg) != 0 ? 1u : 0u;
+              uint64_t* const fb = &full_bar[stage];
+              uint64_t* const eb = &empty_bar[stage];
+              asm volatile("" ::"l"(da), "l"(db), "r"(nk), "r"(acc0), "l"(fb), "l"(eb));   // materialise before the wait
               long long trc = 0;
               if (tr) trc = clock64();
-              mbar_wait(&full_bar[stage], phase, 3);
+              mbar_wait(fb, phase, 3);
               tc_fence_after();
               if (tr) {
                 const long long now = clock64();
                 if (kb == 0 && seg == 0) tr2 = now; else trw += now - trc;
               }
-              const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-              const uint64_t da = make_smem_desc_sw128(sa, 16, 1024);
-              const uint64_t db = make_smem_desc_sw128(sa + A_STAGE_BYTES, 16, 1024);
-              const int nk = (cb == p.cblks - 1) ? p.last_k16 : 4;
-              const bool last = (kb == p.num_kb - 1) && (seg == p.nseg - 1);
               if (elect_one()) {
-                for (int k = 0; k < nk; ++k) {
+                if (nk == 4) {
                   // +32 B per K=16 step inside the 128-B swizzle row (descriptor address is in 16-B units)
-                  if (PAIR) umma_bf16_pair(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k | seg) != 0);
-                  else umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k | seg) != 0);
+                  if (PAIR) {
+                    umma_bf16_pair(d_tmem, da, db, idesc, acc0 != 0);
+                    umma_bf16_pair(d_tmem, da + 2, db + 2, idesc, true);
+                    umma_bf16_pair(d_tmem, da + 4, db + 4, idesc, true);
+                    umma_bf16_pair(d_tmem, da + 6, db + 6, idesc, true);
+                  } else {
+                    umma_bf16(d_tmem, da, db, idesc, acc0 != 0);
+                    umma_bf16(d_tmem, da + 2, db + 2, idesc, true);
+                    umma_bf16(d_tmem, da + 4, db + 4, idesc, true);
+                    umma_bf16(d_tmem, da + 6, db + 6, idesc, true);
+                  }
+                } else {
+                  for (int k = 0; k < nk; ++k) {
+                    if (PAIR) umma_bf16_pair(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (acc0 | (uint32_t)k) != 0);
+                    else umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (acc0 | (uint32_t)k) != 0);
+                  }
                 }
                 // commits track the MMAs of the issuing thread: same elected lane
-                if (PAIR) umma_commit_pair(&empty_bar[stage]);
-                else umma_commit(&empty_bar[stage]);
+                if (PAIR) umma_commit_pair(eb);
+                else umma_commit(eb);
                 if (last) {
                   if (PAIR) umma_commit_pair(&tfull_bar[as]);
                   else umma_commit(&tfull_bar[as]);
                 }
               }
               __syncwarp();
-              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+              da += (uint64_t)(STAGE_BYTES >> 4);
+              if (++stage == STAGES) { stage = 0; phase ^= 1; da = desc0; }
             }
           }
         }
@@ -266,7 +289,7 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
       const int mt = m_tile_of(t), nt = t % p.n_tiles;
       mbar_wait(&tfull_bar[as], aphase, 4);
       tc_fence_after();
-      const bool etr = p.trace != nullptr && rank == 0 && warp == 2 && lane == 0;
+      const bool etr = TRACE && p.trace != nullptr && rank == 0 && warp == 2 && lane == 0;
       if (etr) {
         const int ti = (t - unit0) / nunits;
         if (ti < p.trace_cap) p.trace[((long long)unit0 * p.trace_cap + ti) * 8 + 5] = (unsigned long long)clock64();
@@ -628,6 +651,8 @@ extern "C" int32_t tvae_conv_gemm(const tvae_conv_args* a, cudaStream_t stream) 
     if (attr_set.pending()) {
       TVAE_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
       TVAE_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      TVAE_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      TVAE_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
       attr_set.mark();
     }
     const int total = (p.m_tiles + 1) / 2 * p.n_tiles;
@@ -642,7 +667,10 @@ extern "C" int32_t tvae_conv_gemm(const tvae_conv_args* a, cudaStream_t stream) 
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    if (lean) TVAE_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<true, true>, maps, p));
+    // the timeline instantiations exist for the pair schedule only; production launches never carry the clock reads
+    if (p.trace && lean) TVAE_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<true, true, true>, maps, p));
+    else if (p.trace) TVAE_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<true, false, true>, maps, p));
+    else if (lean) TVAE_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<true, true>, maps, p));
     else TVAE_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<true, false>, maps, p));
   } else {
     static PerDeviceOnce attr_set;
