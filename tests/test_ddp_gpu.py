@@ -115,7 +115,7 @@ def test_model_on_cuda1_while_current_device_is_0():
             mean = model.get_latent(x).mean
         assert torch.cuda.current_device() == 0
         assert mean.device == dev and model.optimizer.flat_param.device == dev
-        out.append((float(loss), model.optimizer.flat_param.cpu().clone(), mean.cpu().clone()))
+        out.append((float(loss.detach()), model.optimizer.flat_param.cpu().clone(), mean.cpu().clone()))
     assert out[0][0] == out[1][0] and torch.equal(out[0][1], out[1][1]) and torch.equal(out[0][2], out[1][2])
     # the C ABI refuses a pointer that lives on another device instead of faulting inside the kernel
     from tempo_vae_b200 import _lib

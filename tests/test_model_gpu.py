@@ -785,3 +785,98 @@ def test_accumulated_micro_batches_equal_one_step_on_their_concatenation(tmp_pat
     assert abs(l1 - l2) / abs(l1) < 1e-6
     assert float((g2 / 2 - g1).norm() / g1.norm()) < 2e-3           # accumulated sum = 2 x the mean gradient
     assert float((p2 - p1).abs().max()) < 2.5e-4
+
+
+def test_default_size_l2_variant_with_shipped_head_vs_oracle_on_gpu(capsys):
+    """SURVEY 8a rows a14-a16 at the SHIPPED size: default model + the [512, 512] L2 head of
+    configs/training/train_vae_l2_supervised.yaml (the golden fixture uses a tiny model with a [64, 64] head). Checker: the
+    fp32 oracle evaluated on the same GPU (TF32 off). compute_loss: total / nll / kl / per-product losses and every
+    gradient; forward(): reconstruction and the four l2_predictions against the oracle applied to the z it returned."""
+    import tempo_vae_b200 as t
+    sys.path.insert(0, ROOT)
+    from bench import DEFAULT_MODEL
+    dev = torch.device("cuda")
+    cfg = orc.DEFAULT_CFG
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        B = 4
+        t.seed_all(42)
+        base = t.get_model(DEFAULT_MODEL, dev)
+        model = t.VAEWithL2Supervision(base.vae, latent_channels=32, mlp_hidden=[512, 512]).to(dev)
+        sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+        ref_sd = orc.init_state_dict(cfg, seed=42, l2_hidden=None)
+        assert all(torch.equal(sd[k], v) for k, v in ref_sd.items())            # the VAE part is the reference's seed-42 init
+        orc.rerandomize_zero_init(sd, seed=1234)
+        model.load_state_dict(sd)
+        opt = t.FusedAdamW(model.parameters(), lr=1e-4, betas=(0.9, 0.95), weight_decay=0.05)
+        sdg = {k: v.to(dev) for k, v in sd.items()}
+        g = torch.Generator().manual_seed(5)
+        batch = {"spectral": orc.structured_batch(B, cfg, seed=77).to(dev)}
+        for p in ("NO2", "O3TOT", "HCHO", "CLDO4"):
+            tg = torch.randn((B, 64, 64), generator=g)
+            tg[torch.rand((B, 64, 64), generator=g) < 0.15] = float("nan")
+            batch[p] = tg.to(dev)
+        batch["CLDO4"][:] = float("nan")                                         # a product without a single valid pixel
+        eps = torch.randn((B, 32, 16, 16), generator=g).to(dev)
+        eps2 = torch.randn((B, 32, 16, 16), generator=g).to(dev)
+        weights = {"NO2": 0.1, "O3TOT": 0.1, "HCHO": 0.1, "CLDO4": 0.1}
+        total, metrics = model.compute_loss(batch, l2_weights=weights, eps=eps, eps2=eps2)
+        opt.zero_grad()
+        total.backward()
+        grads, out = orc.grads_of(lambda leaves: orc.l2_supervised_loss(leaves, batch, eps, eps2, cfg, weights), sdg)
+        assert abs(total.item() - out["total"].item()) / out["total"].item() < 1e-4
+        assert abs(metrics["kl_loss"] - out["kl_loss"].item()) / out["kl_loss"].item() < 2e-2
+        assert "CLDO4_loss" not in metrics and set(metrics) == {"loss", "nll_loss", "kl_loss", "NO2_loss", "O3TOT_loss", "HCHO_loss"}
+        for p in ("NO2", "O3TOT", "HCHO"):
+            assert abs(metrics[f"{p}_loss"] - out["l2_losses"][p].item()) / out["l2_losses"][p].item() < 3e-2, p
+        named = dict(model.named_parameters())
+        gn = {k: float(v.norm()) for k, v in grads.items() if v is not None}
+        floor = 1e-5 * max(v for k, v in gn.items() if not k.endswith("logvar"))
+        errs = {k: rel(named[k].grad, v) for k, v in grads.items() if v is not None and gn[k] > floor}
+        vals = sorted(errs.values())
+        med, top = vals[len(vals) // 2], max(errs.items(), key=lambda kv: kv[1])
+        head = {k: v for k, v in errs.items() if k.startswith("l2_head")}
+        assert len(head) == 8 and max(head.values()) < 1e-1, head
+        assert med < 5e-2 and top[1] < 3e-1, (med, top)
+        # forward(): dict outputs against the oracle applied to the z the engine sampled
+        with torch.no_grad():
+            res = model(batch["spectral"])
+            z = res["z"]
+            ref_rec = orc.decode(sdg, z, cfg)
+            ref_pred = orc.l2_head(sdg, z)
+        assert rel(res["reconstruction"], ref_rec) < 1e-2
+        for i, p in enumerate(("NO2", "O3TOT", "HCHO", "CLDO4")):
+            assert res["l2_predictions"][p].shape == (B, 1, 16, 16)
+            assert rel(res["l2_predictions"][p], ref_pred[:, i:i + 1]) < 1e-2, p
+        assert rel(res["posterior"].mean, orc.encode(sdg, batch["spectral"], cfg)[0]) < 1e-2
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    with capsys.disabled():
+        print(f"\n[default-size L2 variant, [512,512] head, B={B}] total {total.item():.1f} (oracle {out['total'].item():.1f}); "
+              f"per-tensor gradient rel-L2 median {med:.3e}, worst {top[1]:.3e} at {top[0]}; L2-head tensors max {max(head.values()):.3e}")
+
+
+def test_validate_is_the_sample_weighted_mean_of_get_loss(tmp_path):
+    """Trainer.validate (src/train_utils.py:185-212): `val_<k>` = sum_k metric * batch_size / total samples over n_batches
+    batches of get_loss under no_grad, here with unequal batch sizes and compared value by value."""
+    import tempo_vae_b200 as t
+    cfg = orc.TINY_CFG
+    model = build(cfg, gold("tiny_train.pt")["state_dict"])
+    tr = t.Trainer(model, model.optimizer, torch.device("cuda"), tmp_path)
+    tr.step = 1
+    batches = [orc.structured_batch(b, cfg, seed=50 + b) for b in (2, 5, 3, 4)]
+    t.seed_all(7)
+    val = tr.validate(batches, n_batches=3)
+    t.seed_all(7)
+    acc = {"kl_loss": 0.0, "nll_loss": 0.0, "loss": 0.0}
+    with torch.no_grad():
+        for x in batches[:3]:
+            _, m = model.get_loss(x.cuda())
+            for k in acc:
+                acc[k] += float(m[k]) * x.shape[0]
+    assert set(val) == {"val_kl_loss", "val_nll_loss", "val_loss"}
+    for k, v in acc.items():
+        assert abs(val[f"val_{k}"] - v / 10) / abs(v / 10) < 1e-6, k
+    assert not model.training
