@@ -324,9 +324,14 @@ extern "C" int32_t tvae_wgrad_splits(int32_t cm, int32_t cn, int32_t ntaps, int6
   const int bn = wgrad_bn(cn);
   const int m_tiles = (cm + BM - 1) / BM, n_tiles = (cn + bn - 1) / bn;
   const long long nblocks = (pixels + BKP - 1) / BKP;
-  if (g_wgrad_cta_pair && m_tiles >= 2)    // main launch: pairs of M tiles on pairs of SMs
-    return pick_splits((m_tiles / 2) * n_tiles * ntaps, num_sms() / 2, nblocks, 16);
-  return pick_splits(m_tiles * n_tiles * ntaps, num_sms(), nblocks, 16);
+  // tiny GEMMs (the 1x1 convolutions of the 16x16 level: ONE unit per split) may cut the pixel range into up to 64
+  // pieces, or 15 CTAs do all the work while 133 SMs idle (46 TFLOP/s, 48 us per call measured)
+  if (g_wgrad_cta_pair && m_tiles >= 2) {   // main launch: pairs of M tiles on pairs of SMs
+    const int base = (m_tiles / 2) * n_tiles * ntaps;
+    return pick_splits(base, num_sms() / 2, nblocks, base <= 4 ? 64 : 16);
+  }
+  const int base = m_tiles * n_tiles * ntaps;
+  return pick_splits(base, num_sms(), nblocks, base <= 8 ? 64 : 16);
 }
 
 extern "C" int32_t tvae_wgrad_set_cta_pair(int32_t enable) {

@@ -24,7 +24,7 @@ STEPS = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 
 class TimedLib:
     def __init__(self, lib):
-        self._lib, self.events, self.on = lib, [], False
+        self._lib, self.events, self.on, self.shapes = lib, [], False, []
 
     def __getattr__(self, name):
         fn = getattr(self._lib, name)
@@ -39,6 +39,20 @@ class TimedLib:
             rc = fn(*a)
             e1.record()
             self.events.append((name, e0, e1))
+            if name in ("tvae_conv_gemm", "tvae_wgrad_gemm"):       # per-shape table of the GEMM calls
+                g = a[0]._obj                                       # ctypes.byref(struct)
+                if name == "tvae_conv_gemm":
+                    px = g.N * g.H * g.W // (4 if g.kind == 1 else 1)
+                    taps = g.R * g.R if g.kind == 0 else 4
+                    key = ("conv", px, g.C, g.Cout, g.kind, g.R, int(g.flip), "f32" * bool(g.out_f32) + "+bf16" * bool(g.out_bf16)
+                           + "+res" * bool(g.residual) + "+stats" * bool(g.stats_part))
+                    flops = 2.0 * px * g.C * g.Cout * (taps if g.kind != 2 else 1) * (4 if g.kind == 2 else 1)
+                else:
+                    px = g.N * g.H * g.W
+                    taps = g.R * g.R if g.kind == 0 else 4
+                    key = ("wgrad", px, g.Cm, g.Cn, g.kind, g.R, int(g.flip), "")
+                    flops = 2.0 * px * g.Cm * g.Cn * taps
+                self.shapes.append((key, flops, e0, e1))
             return rc
         return call
 
@@ -73,3 +87,13 @@ print(f"B={B}: {total:.2f} ms/step live (with {len(proxy.events) // STEPS} event
 print("| entry point | calls/step | ms/step | share |\n|---|---|---|---|")
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     print(f"| `{k}` | {v[0] / STEPS:.0f} | {v[1] / STEPS:.2f} | {100 * v[1] / STEPS / total:.1f} % |")
+
+print("\n| GEMM call (pixels, Cin|Cm, Cout|Cn, kind, R, flip, outputs) | calls/step | ms/step | TFLOP/s (algorithmic) |\n|---|---|---|---|")
+sh = collections.defaultdict(lambda: [0, 0.0, 0.0])
+for key, flops, e0, e1 in proxy.shapes:
+    a = sh[key]
+    a[0] += 1
+    a[1] += e0.elapsed_time(e1)
+    a[2] += flops
+for k, v in sorted(sh.items(), key=lambda kv: -kv[1][1]):
+    print(f"| {k} | {v[0] / STEPS:.0f} | {v[1] / STEPS:.2f} | {v[2] / v[1] / 1e9:.0f} |")
