@@ -85,12 +85,15 @@ gn_act_fwd_fast_kernel(const TX* __restrict__ x, const float* __restrict__ stats
 // cs_part (optional): per-block column sums of dx (before its bf16 rounding), [n][chunk][C] -- dx is the output
 // gradient of the conv that produced x, so its column sums are that conv's bias gradient and the separate pass over
 // dx (tvae_colsum_bf16) disappears.
-template <typename TX>
+// FROM_DY: the row-sum pass already left dy = da * act'(y) (bf16) in the dx buffer; this pass reads it back element by
+// element (each thread overwrites exactly what it read), so act' is evaluated once per element instead of twice and
+// `da` is not read again.
+template <typename TX, bool FROM_DY>
 __global__ void __launch_bounds__(256)
 gn_bwd_apply_fast_kernel(const TX* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gamma,
                          const float* __restrict__ beta, const __nv_bfloat16* __restrict__ da,
                          const __nv_bfloat16* __restrict__ gres, const float* __restrict__ gmeans, int HW, int C, int G,
-                         int act, int rpb, __nv_bfloat16* __restrict__ dx, float* __restrict__ cs_part) {
+                         int act, int rpb, __nv_bfloat16* dx, float* __restrict__ cs_part) {
   __shared__ float cs_sm[256 * 8];
   const int U = C >> 3, lanes = 256 / U;
   const int u = threadIdx.x % U, lane = threadIdx.x / U;
@@ -118,7 +121,7 @@ gn_bwd_apply_fast_kernel(const TX* __restrict__ x, const float* __restrict__ sta
     const long long off = base + (long long)r * C;
     float xv[8], dv[8], rv[8];
     load8x(x + off, xv);
-    load8_bf16(da + off, dv);
+    load8_bf16((FROM_DY ? dx : da) + off, dv);
     if (gres) {
       load8_bf16(gres + off, rv);
     } else {
@@ -129,7 +132,7 @@ gn_bwd_apply_fast_kernel(const TX* __restrict__ x, const float* __restrict__ sta
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float dy = dv[j];
-      if (act) dy *= act_grad_fast(fmaf(xv[j], sc[j], sh[j]), act);
+      if (!FROM_DY && act) dy *= act_grad_fast(fmaf(xv[j], sc[j], sh[j]), act);
       o[j] = fmaf(dy, gr[j], rv[j]) - fmaf(xv[j], ta, tb);
       cs[j] += o[j];
     }
@@ -186,7 +189,7 @@ __global__ void __launch_bounds__(256, 4)
 gn_bwd_rowsum_fast_kernel(const TX* __restrict__ x, const float* __restrict__ stats,
                           const float* __restrict__ gamma, const float* __restrict__ beta,
                           const __nv_bfloat16* __restrict__ da, int HW, int C, int G, int act, int rpb,
-                          float* __restrict__ part) {
+                          float* __restrict__ part, __nv_bfloat16* __restrict__ dy_out) {
   extern __shared__ float sm[];  // [256][16]
   const int U = C >> 3, lanes = 256 / U;
   const int u = threadIdx.x % U, lane = threadIdx.x / U;
@@ -217,7 +220,9 @@ gn_bwd_rowsum_fast_kernel(const TX* __restrict__ x, const float* __restrict__ st
       if (act) dy *= act_grad_fast(fmaf(xa[j], sc[j], sh[j]), act);
       s1[j] += dy;
       s2[j] = fmaf(dy, xa[j], s2[j]);
+      da_[j] = dy;
     }
+    if (dy_out) store8_bf16(dy_out + base + (long long)r * C, da_);   // consumed in place by the apply pass (FROM_DY)
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) s2[j] = (s2[j] - mean * s1[j]) * rstd;     // sum dy*x  ->  sum dy*xhat
@@ -634,8 +639,11 @@ long long gn_bwd_fast_ws_floats(int N, int HW, int C, int G) {
 // L2-resident group.
 static int g_gn_fused = -1;
 static int g_gn_group_mb = 24;
+static int g_gn_store_dy = 1;       // TVAE_GN_STORE_DY=0: the apply pass recomputes act' from da (round-1 behaviour)
 static void gn_read_env() {
   if (g_gn_fused >= 0) return;
+  const char* d = getenv("TVAE_GN_STORE_DY");
+  if (d && d[0] == '0') g_gn_store_dy = 0;
   // Default OFF. Measured on B200, [256,64,64,512] (profiles/gn_bwd_single_pass_r2.md): the single pass moves 5.39 GB
   // instead of 8.67 GB (ncu dram bytes -- the L2 hand-over works) but takes 2.05 ms against 1.59 ms for the two kernels:
   // it is bound by instruction issue, not by bytes (same time for 5.4 GB fp32+gres and 3.2 GB bf16 inputs; 2.73 ms with
@@ -730,21 +738,30 @@ int gn_act_bwd_fast(const void* xv, bool x_bf16, const float* stats, const float
     set_error("gn_bwd_ring: cooperative launch failed (%s)", cudaGetErrorString(cudaGetLastError()));
     return -1;
   }
+  // dy hand-over (g_gn_store_dy, default on): with an activation the row-sum pass writes dy = da * act'(y) into dx and the
+  // apply pass starts from it. +2 B/element of traffic, -16 instructions/element: inside the train step these kernels run
+  // at the power-capped SM clock (1.3-1.5 GHz) and are issue-bound, not bandwidth-bound.
+  const bool hand_over = g_gn_store_dy != 0 && act != 0;
+  __nv_bfloat16* dy_out = hand_over ? dx : nullptr;
   if (x_bf16)
     gn_bwd_rowsum_fast_kernel<<<grid, 256, 256 * 16 * sizeof(float), stream>>>(xb, stats, gamma, beta, da, HW, C, G,
-                                                                              act, rpb, part);
+                                                                              act, rpb, part, dy_out);
   else
     gn_bwd_rowsum_fast_kernel<<<grid, 256, 256 * 16 * sizeof(float), stream>>>(x, stats, gamma, beta, da, HW, C, G,
-                                                                              act, rpb, part);
+                                                                              act, rpb, part, dy_out);
   gn_bwd_finalize_fast_kernel<<<N, 256, 2 * C * sizeof(float), stream>>>(part, gamma, chunks, HW, C, G, N, ws, nullptr);
   gn_bwd_param_fast_kernel<<<(C + 31) / 32, 256, 0, stream>>>(ws, N, C, dgamma, dbeta);
   // the row-sum partials are consumed by now (stream order): their region is reused for the column sums of dx
-  if (x_bf16)
-    gn_bwd_apply_fast_kernel<<<grid, 256, 0, stream>>>(xb, stats, gamma, beta, da, gres, ws + 2ll * N * C, HW, C, G, act,
-                                                       rpb, dx, dx_colsum ? part : nullptr);
+  float* csp = dx_colsum ? part : nullptr;
+  const float* gm = ws + 2ll * N * C;
+  if (x_bf16 && hand_over)
+    gn_bwd_apply_fast_kernel<__nv_bfloat16, true><<<grid, 256, 0, stream>>>(xb, stats, gamma, beta, da, gres, gm, HW, C, G, act, rpb, dx, csp);
+  else if (x_bf16)
+    gn_bwd_apply_fast_kernel<__nv_bfloat16, false><<<grid, 256, 0, stream>>>(xb, stats, gamma, beta, da, gres, gm, HW, C, G, act, rpb, dx, csp);
+  else if (hand_over)
+    gn_bwd_apply_fast_kernel<float, true><<<grid, 256, 0, stream>>>(x, stats, gamma, beta, da, gres, gm, HW, C, G, act, rpb, dx, csp);
   else
-    gn_bwd_apply_fast_kernel<<<grid, 256, 0, stream>>>(x, stats, gamma, beta, da, gres, ws + 2ll * N * C, HW, C, G, act,
-                                                       rpb, dx, dx_colsum ? part : nullptr);
+    gn_bwd_apply_fast_kernel<float, false><<<grid, 256, 0, stream>>>(x, stats, gamma, beta, da, gres, gm, HW, C, G, act, rpb, dx, csp);
   if (dx_colsum) {
     float* slices = part + (long long)N * chunks * 2 * C;
     colsum_rows_slice_kernel<<<dim3((C + 31) / 32, CS_SLICES), 256, 0, stream>>>(part, N * chunks, C, slices);
