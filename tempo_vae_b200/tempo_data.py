@@ -299,9 +299,8 @@ class HostTileStore:
     def __init__(self, H: int, W: int, C: int, capacity: int, pin: bool = True):
         self.H, self.W, self.C = H, W, C
         self.pitch = (C + 7) // 8 * 8
-        self.data = torch.zeros((capacity, H, W, self.pitch), dtype=torch.bfloat16)
-        if pin and torch.cuda.is_available():
-            self.data = self.data.pin_memory()
+        pinned = bool(pin and torch.cuda.is_available())         # allocated pinned directly: no pageable copy of the split
+        self.data = torch.zeros((capacity, H, W, self.pitch), dtype=torch.bfloat16, pin_memory=pinned)
         self.n = 0
         self.h2d_bytes = 0
 
