@@ -366,7 +366,7 @@ def test_groupnorm_bwd_single_pass_matches_two_pass(N, H, W, C, x_bf16, with_gre
     # the two schedules differ in the summation order of the row sums and in ONE bf16 rounding: the two-pass kernels hand
     # dy = da * act'(y) from the row-sum pass to the apply pass as bf16 (in the dx buffer), the single pass keeps it in
     # fp32 -- a 2^-9 change of dy flips the final bf16 rounding of dx for a fraction of the elements (one ulp = 2^-8)
-    assert rel_err(one[0].float(), two[0].float()) < 5e-3
+    assert rel_err(one[0].float(), two[0].float()) < 8e-3
     assert rel_err(one[1], two[1]) < 1e-5 and rel_err(one[2], two[2]) < 1e-5
 
 
