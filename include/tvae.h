@@ -178,6 +178,19 @@ int32_t tvae_gn_act_bwd(const void* x, int32_t x_is_bf16, const float* stats, co
                         void* dx_bf16, float* dgamma, float* dbeta, float* dx_colsum, float* workspace,
                         tvae_stream_t stream);
 
+/* The same two calls with the activation derivative handed from forward to backward: tvae_gn_act_fwd2 also stores
+ * act'(gamma * xhat + beta) as bf16 (act_grad, same shape as out; optional -- NULL = tvae_gn_act_fwd; needs act != 0, the
+ * vectorised geometry (C / G a multiple of 8, C / 8 dividing 256) and no split-bf16 output); tvae_gn_act_bwd2 given that
+ * tensor never evaluates the activation: dy = da * act_grad. Value and derivative of GELU come out of the same Phi / phi
+ * evaluation, so the forward pays one FMA and 2 B per element for what costs the backward 16 instructions per element. */
+int32_t tvae_gn_act_fwd2(const void* x, int32_t x_is_bf16, const float* stats, const float* gamma, const float* beta,
+                         int32_t N, int32_t HW, int32_t C, int32_t G, int32_t act, void* out_bf16, void* out_lo,
+                         void* act_grad_bf16, tvae_stream_t stream);
+int32_t tvae_gn_act_bwd2(const void* x, int32_t x_is_bf16, const float* stats, const float* gamma, const float* beta,
+                         const void* da_bf16, const void* gres_bf16, const void* act_grad_bf16, int32_t N, int32_t HW,
+                         int32_t C, int32_t G, int32_t act, void* dx_bf16, float* dgamma, float* dbeta, float* dx_colsum,
+                         float* workspace, tvae_stream_t stream);
+
 /* Scheduling switch of tvae_gn_act_bwd (results agree up to the summation order of the row sums): on = 0 (default) runs
  * the two-pass kernels (row sums, then apply: x and da are read from DRAM twice); on = 1 uses ONE persistent pass for
  * tensors that do not fit the L2 (cp.async.bulk ring; x and da are read from DRAM once, the second read is served by the

@@ -83,6 +83,8 @@ def _load():
         "tvae_gn_stats": (i32, [vp, i32, i32, i32, i32, f32, vp, vp]),
         "tvae_gn_stats_finalize": (i32, [vp, i32, i32, i32, C.c_double, f32, vp, vp]),
         "tvae_gn_act_fwd": (i32, [vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp]),
+        "tvae_gn_act_fwd2": (i32, [vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp]),
+        "tvae_gn_act_bwd2": (i32, [vp, i32, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]),
         "tvae_gn_bwd_workspace_bytes": (i64, [i32, i32, i32, i32]),
         "tvae_gn_act_bwd": (i32, [vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]),
         "tvae_gn_set_bwd_fused": (i32, [i32, i32]),

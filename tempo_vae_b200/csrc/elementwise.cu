@@ -740,14 +740,22 @@ extern "C" int32_t tvae_gn_stats_finalize(const float* part, int32_t spi, int32_
 extern "C" int32_t tvae_gn_act_fwd(const void* xv, int32_t x_is_bf16, const float* stats, const float* gamma,
                                    const float* beta, int32_t N, int32_t HW, int32_t C, int32_t G, int32_t act,
                                    void* out, void* out_lo, cudaStream_t stream) {
+  return tvae_gn_act_fwd2(xv, x_is_bf16, stats, gamma, beta, N, HW, C, G, act, out, out_lo, nullptr, stream);
+}
+
+extern "C" int32_t tvae_gn_act_fwd2(const void* xv, int32_t x_is_bf16, const float* stats, const float* gamma,
+                                    const float* beta, int32_t N, int32_t HW, int32_t C, int32_t G, int32_t act,
+                                    void* out, void* out_lo, void* act_grad, cudaStream_t stream) {
   TVAE_ENTER(xv);
   TVAE_CHECK(xv && stats && gamma && beta && out, "tvae_gn_act_fwd: null pointer");
   TVAE_CHECK(G > 0 && C % G == 0, "tvae_gn_act_fwd: C %% G != 0");
   const long long rows = (long long)N * HW;
   const int gs = C / G;
+  TVAE_CHECK(!act_grad || (gn_fast_ok(C, G) && out_lo == nullptr && act != 0),
+             "tvae_gn_act_fwd2: act_grad needs an activation, the fast-path geometry and no split-bf16 output");
   if (gn_fast_ok(C, G) && out_lo == nullptr) {   // the split-bf16 ("fp32 mode") output uses the generic kernel
     gn_act_fwd_fast(xv, x_is_bf16 != 0, stats, gamma, beta, N, HW, C, G, act, reinterpret_cast<__nv_bfloat16*>(out),
-                    stream);
+                    reinterpret_cast<__nv_bfloat16*>(act_grad), stream);
     TVAE_CUDA(cudaGetLastError());
     return 0;
   }
@@ -775,6 +783,14 @@ extern "C" int32_t tvae_gn_act_bwd(const void* xv, int32_t x_is_bf16, const floa
                                    const float* beta, const void* da, const void* gres, int32_t N, int32_t HW, int32_t C, int32_t G,
                                    int32_t act, void* dx, float* dgamma, float* dbeta, float* dx_colsum, float* ws,
                                    cudaStream_t stream) {
+  return tvae_gn_act_bwd2(xv, x_is_bf16, stats, gamma, beta, da, gres, nullptr, N, HW, C, G, act, dx, dgamma, dbeta,
+                          dx_colsum, ws, stream);
+}
+
+extern "C" int32_t tvae_gn_act_bwd2(const void* xv, int32_t x_is_bf16, const float* stats, const float* gamma,
+                                    const float* beta, const void* da, const void* gres, const void* act_grad, int32_t N,
+                                    int32_t HW, int32_t C, int32_t G, int32_t act, void* dx, float* dgamma, float* dbeta,
+                                    float* dx_colsum, float* ws, cudaStream_t stream) {
   TVAE_ENTER(xv);
   TVAE_CHECK(xv && stats && gamma && beta && da && dx && dgamma && dbeta && ws, "tvae_gn_act_bwd: null pointer");
   TVAE_CHECK(G > 0 && C % G == 0, "tvae_gn_act_bwd: C %% G != 0");
@@ -785,8 +801,8 @@ extern "C" int32_t tvae_gn_act_bwd(const void* xv, int32_t x_is_bf16, const floa
   __nv_bfloat16* dxp = reinterpret_cast<__nv_bfloat16*>(dx);
   const float* gmeans = ws + 2ll * N * C;
   if (gn_fast_ok(C, G)) {
-    gn_act_bwd_fast(xv, x_is_bf16 != 0, stats, gamma, beta, dap, grp, N, HW, C, G, act, dxp, dgamma, dbeta, dx_colsum,
-                    ws, stream);
+    gn_act_bwd_fast(xv, x_is_bf16 != 0, stats, gamma, beta, dap, grp, reinterpret_cast<const __nv_bfloat16*>(act_grad), N,
+                    HW, C, G, act, dxp, dgamma, dbeta, dx_colsum, ws, stream);
     TVAE_CUDA(cudaGetLastError());
     return 0;
   }

@@ -38,11 +38,25 @@ __device__ __forceinline__ void store8_bf16(__nv_bfloat16* p, const float (&v)[8
 }
 
 // grid (row chunks, N); 256 threads = (256/U) row lanes x U channel-octets, U = C/8
-template <typename TX>
+// value and derivative of the activation in one evaluation (GELU: both come out of the same Phi / phi pair)
+__device__ __forceinline__ void act_and_grad_fast(float y, int act, float& a, float& g) {
+  if (act == 1) {
+    float Phi, pe;
+    gelu_phi(y, Phi, pe);
+    a = y * Phi;
+    g = fmaf(y, pe, Phi);
+  } else {
+    a = act_f(y, act);
+    g = act_grad_f(y, act);
+  }
+}
+
+// GP: also store act'(y) (bf16) for the backward pass, which then never evaluates the activation again
+template <typename TX, bool GP>
 __global__ void __launch_bounds__(256)
 gn_act_fwd_fast_kernel(const TX* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gamma,
                        const float* __restrict__ beta, int HW, int C, int G, int act, int rpb,
-                       __nv_bfloat16* __restrict__ out) {
+                       __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ gp_out) {
   const int U = C >> 3, lanes = 256 / U;
   const int u = threadIdx.x % U, lane = threadIdx.x / U;
   const int c = u << 3, n = blockIdx.y;
@@ -60,24 +74,35 @@ gn_act_fwd_fast_kernel(const TX* __restrict__ x, const float* __restrict__ stats
   const int r1 = min(r0 + rpb, HW);
   const long long base = (long long)n * HW * C + c;
   int r = r0 + lane;
-  for (; r + lanes < r1; r += 2 * lanes) {
-    float a[8], b[8];
-    load8x(x + base + (long long)r * C, a);
-    load8x(x + base + (long long)(r + lanes) * C, b);
+  if (GP) {
+    for (; r < r1; r += lanes) {
+      float a[8], g[8];
+      load8x(x + base + (long long)r * C, a);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      a[j] = act_fast(fmaf(a[j], sc[j], sh[j]), act);
-      b[j] = act_fast(fmaf(b[j], sc[j], sh[j]), act);
+      for (int j = 0; j < 8; ++j) act_and_grad_fast(fmaf(a[j], sc[j], sh[j]), act, a[j], g[j]);
+      store8_bf16(out + base + (long long)r * C, a);
+      store8_bf16(gp_out + base + (long long)r * C, g);
     }
-    store8_bf16(out + base + (long long)r * C, a);
-    store8_bf16(out + base + (long long)(r + lanes) * C, b);
-  }
-  if (r < r1) {
-    float a[8];
-    load8x(x + base + (long long)r * C, a);
+  } else {
+    for (; r + lanes < r1; r += 2 * lanes) {
+      float a[8], b[8];
+      load8x(x + base + (long long)r * C, a);
+      load8x(x + base + (long long)(r + lanes) * C, b);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) a[j] = act_fast(fmaf(a[j], sc[j], sh[j]), act);
-    store8_bf16(out + base + (long long)r * C, a);
+      for (int j = 0; j < 8; ++j) {
+        a[j] = act_fast(fmaf(a[j], sc[j], sh[j]), act);
+        b[j] = act_fast(fmaf(b[j], sc[j], sh[j]), act);
+      }
+      store8_bf16(out + base + (long long)r * C, a);
+      store8_bf16(out + base + (long long)(r + lanes) * C, b);
+    }
+    if (r < r1) {
+      float a[8];
+      load8x(x + base + (long long)r * C, a);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] = act_fast(fmaf(a[j], sc[j], sh[j]), act);
+      store8_bf16(out + base + (long long)r * C, a);
+    }
   }
 }
 
@@ -189,7 +214,8 @@ __global__ void __launch_bounds__(256, 4)
 gn_bwd_rowsum_fast_kernel(const TX* __restrict__ x, const float* __restrict__ stats,
                           const float* __restrict__ gamma, const float* __restrict__ beta,
                           const __nv_bfloat16* __restrict__ da, int HW, int C, int G, int act, int rpb,
-                          float* __restrict__ part, __nv_bfloat16* __restrict__ dy_out) {
+                          float* __restrict__ part, __nv_bfloat16* __restrict__ dy_out,
+                          const __nv_bfloat16* __restrict__ gp) {
   extern __shared__ float sm[];  // [256][16]
   const int U = C >> 3, lanes = 256 / U;
   const int u = threadIdx.x % U, lane = threadIdx.x / U;
@@ -214,13 +240,25 @@ gn_bwd_rowsum_fast_kernel(const TX* __restrict__ x, const float* __restrict__ st
     float xa[8], da_[8];
     load8x(x + base + (long long)r * C, xa);
     load8_bf16(da + base + (long long)r * C, da_);
+    if (gp) {            // act'(y) saved by the forward pass: no activation arithmetic here at all
+      float gv[8];
+      load8_bf16(gp + base + (long long)r * C, gv);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float dy = da_[j];
-      if (act) dy *= act_grad_fast(fmaf(xa[j], sc[j], sh[j]), act);
-      s1[j] += dy;
-      s2[j] = fmaf(dy, xa[j], s2[j]);
-      da_[j] = dy;
+      for (int j = 0; j < 8; ++j) {
+        const float dy = da_[j] * gv[j];
+        s1[j] += dy;
+        s2[j] = fmaf(dy, xa[j], s2[j]);
+        da_[j] = dy;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float dy = da_[j];
+        if (act) dy *= act_grad_fast(fmaf(xa[j], sc[j], sh[j]), act);
+        s1[j] += dy;
+        s2[j] = fmaf(dy, xa[j], s2[j]);
+        da_[j] = dy;
+      }
     }
     if (dy_out) store8_bf16(dy_out + base + (long long)r * C, da_);   // consumed in place by the apply pass (FROM_DY)
   }
@@ -612,15 +650,18 @@ bool gn_fast_ok(int C, int G) {
 }
 
 int gn_act_fwd_fast(const void* x, bool x_bf16, const float* stats, const float* gamma, const float* beta, int N,
-                    int HW, int C, int G, int act, __nv_bfloat16* out, cudaStream_t stream) {
+                    int HW, int C, int G, int act, __nv_bfloat16* out, __nv_bfloat16* gp_out, cudaStream_t stream) {
   const int rpb = rows_per_block(HW);
   dim3 grid((HW + rpb - 1) / rpb, N);
-  if (x_bf16)
-    gn_act_fwd_fast_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), stats, gamma, beta, HW,
-                                                     C, G, act, rpb, out);
-  else
-    gn_act_fwd_fast_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const float*>(x), stats, gamma, beta, HW, C, G,
-                                                     act, rpb, out);
+  const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x);
+  const float* xf = reinterpret_cast<const float*>(x);
+  if (gp_out) {
+    if (x_bf16) gn_act_fwd_fast_kernel<__nv_bfloat16, true><<<grid, 256, 0, stream>>>(xb, stats, gamma, beta, HW, C, G, act, rpb, out, gp_out);
+    else gn_act_fwd_fast_kernel<float, true><<<grid, 256, 0, stream>>>(xf, stats, gamma, beta, HW, C, G, act, rpb, out, gp_out);
+  } else {
+    if (x_bf16) gn_act_fwd_fast_kernel<__nv_bfloat16, false><<<grid, 256, 0, stream>>>(xb, stats, gamma, beta, HW, C, G, act, rpb, out, nullptr);
+    else gn_act_fwd_fast_kernel<float, false><<<grid, 256, 0, stream>>>(xf, stats, gamma, beta, HW, C, G, act, rpb, out, nullptr);
+  }
   return 0;
 }
 
@@ -716,8 +757,8 @@ static int launch_gn_bwd_ring(const TX* x, const float* stats, const float* gamm
 }
 
 int gn_act_bwd_fast(const void* xv, bool x_bf16, const float* stats, const float* gamma, const float* beta,
-                    const __nv_bfloat16* da, const __nv_bfloat16* gres, int N, int HW, int C, int G, int act,
-                    __nv_bfloat16* dx, float* dgamma, float* dbeta, float* dx_colsum, float* ws,
+                    const __nv_bfloat16* da, const __nv_bfloat16* gres, const __nv_bfloat16* gp, int N, int HW, int C,
+                    int G, int act, __nv_bfloat16* dx, float* dgamma, float* dbeta, float* dx_colsum, float* ws,
                     cudaStream_t stream) {
   const int rpb = rows_per_block(HW);
   const int chunks = (HW + rpb - 1) / rpb;
@@ -743,12 +784,15 @@ int gn_act_bwd_fast(const void* xv, bool x_bf16, const float* stats, const float
   // at the power-capped SM clock (1.3-1.5 GHz) and are issue-bound, not bandwidth-bound.
   const bool hand_over = g_gn_store_dy != 0 && act != 0;
   __nv_bfloat16* dy_out = hand_over ? dx : nullptr;
+  // act'(y) saved by the forward pass (tvae_gn_act_fwd2) is only usable together with the hand-over: the apply pass
+  // must not need act' either
+  const __nv_bfloat16* gp_in = hand_over ? gp : nullptr;
   if (x_bf16)
     gn_bwd_rowsum_fast_kernel<<<grid, 256, 256 * 16 * sizeof(float), stream>>>(xb, stats, gamma, beta, da, HW, C, G,
-                                                                              act, rpb, part, dy_out);
+                                                                              act, rpb, part, dy_out, gp_in);
   else
     gn_bwd_rowsum_fast_kernel<<<grid, 256, 256 * 16 * sizeof(float), stream>>>(x, stats, gamma, beta, da, HW, C, G,
-                                                                              act, rpb, part, dy_out);
+                                                                              act, rpb, part, dy_out, gp_in);
   gn_bwd_finalize_fast_kernel<<<N, 256, 2 * C * sizeof(float), stream>>>(part, gamma, chunks, HW, C, G, N, ws, nullptr);
   gn_bwd_param_fast_kernel<<<(C + 31) / 32, 256, 0, stream>>>(ws, N, C, dgamma, dbeta);
   // the row-sum partials are consumed by now (stream order): their region is reused for the column sums of dx

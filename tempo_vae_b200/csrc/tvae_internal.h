@@ -45,10 +45,10 @@ bool pixel_box(int H, int W, int rows, int* bw, int* bh, int* bn);
 bool gn_fast_ok(int C, int G);
 long long gn_bwd_fast_ws_floats(int N, int HW, int C, int G);
 int gn_act_fwd_fast(const void* x, bool x_bf16, const float* stats, const float* gamma, const float* beta, int N,
-                    int HW, int C, int G, int act, __nv_bfloat16* out, cudaStream_t stream);
+                    int HW, int C, int G, int act, __nv_bfloat16* out, __nv_bfloat16* gp_out, cudaStream_t stream);
 int gn_act_bwd_fast(const void* x, bool x_bf16, const float* stats, const float* gamma, const float* beta, const __nv_bfloat16* da,
-                    const __nv_bfloat16* gres, int N, int HW, int C, int G, int act, __nv_bfloat16* dx, float* dgamma,
-                    float* dbeta, float* dx_colsum, float* ws, cudaStream_t stream);
+                    const __nv_bfloat16* gres, const __nv_bfloat16* gp, int N, int HW, int C, int G, int act,
+                    __nv_bfloat16* dx, float* dgamma, float* dbeta, float* dx_colsum, float* ws, cudaStream_t stream);
 
 // A/B switch of the single-pass GroupNorm backward (gn_fast.cu); group_mb <= 0 keeps the current group size
 void gn_set_bwd_fused(int on, int group_mb);

@@ -400,7 +400,18 @@ def _conv_dgrad(mod, kind, R, Cin, Cout, dy_bf16, dgrad, dgrad_residual):
     return of if dgrad == "f32" else ob
 
 
-def norm_act_fwd(norm, h_f32, act_code, stats=None):
+class NormStats:
+    """(mean, rstd) statistics of a GroupNorm input, plus -- when the forward ran with save=True -- the activation
+    derivative act'(y) it stored for the backward pass (bf16, or None). Travels in the saved-activation tuples where the
+    bare statistics tensor used to."""
+
+    __slots__ = ("stats", "act_grad")
+
+    def __init__(self, stats, act_grad=None):
+        self.stats, self.act_grad = stats, act_grad
+
+
+def norm_act_fwd(norm, h_f32, act_code, stats=None, save=False):
     C = norm.num_channels
     gamma, beta = norm.affine_params()
     if stats is not None and stats[0] == norm.num_groups and stats[1] == norm.eps:
@@ -409,8 +420,11 @@ def norm_act_fwd(norm, h_f32, act_code, stats=None):
         if h_f32.dtype != torch.float32:
             raise RuntimeError("a bf16 GroupNorm input needs statistics from the producing conv's epilogue")
         st = ops.gn_stats(h_f32, C, norm.num_groups, norm.eps)
+    if save and act_code != 0:
+        a, gp = ops.gn_act_fwd(h_f32, st, gamma, beta, norm.num_groups, act_code, want_act_grad=True)
+        return a, NormStats(st, gp)
     a = ops.gn_act_fwd(h_f32, st, gamma, beta, norm.num_groups, act_code)
-    return a, st
+    return a, NormStats(st)
 
 
 def norm_act_bwd(norm, h_f32, stats, da_bf16, gres_bf16, act_code):
@@ -428,13 +442,16 @@ def norm_act_bwd(norm, h_f32, stats, da_bf16, gres_bf16, act_code):
         dg = torch.empty((C,), dtype=torch.float32, device=dev)
         db = torch.empty((C,), dtype=torch.float32, device=dev)
         acc_g = acc_b = False
+    gp = None
+    if isinstance(stats, NormStats):
+        stats, gp = stats.stats, stats.act_grad
     if acc_g or acc_b:
         tg, tb = torch.empty_like(dg), torch.empty_like(db)
-        dx = ops.gn_act_bwd(h_f32, stats, gamma, beta, da_bf16, gres_bf16, norm.num_groups, act_code, tg, tb, cs)
+        dx = ops.gn_act_bwd(h_f32, stats, gamma, beta, da_bf16, gres_bf16, norm.num_groups, act_code, tg, tb, cs, gp)
         dg.add_(tg)
         db.add_(tb)
     else:
-        dx = ops.gn_act_bwd(h_f32, stats, gamma, beta, da_bf16, gres_bf16, norm.num_groups, act_code, dg, db, cs)
+        dx = ops.gn_act_bwd(h_f32, stats, gamma, beta, da_bf16, gres_bf16, norm.num_groups, act_code, dg, db, cs, gp)
     if train_affine:
         _grad_done(gamma)
         _grad_done(beta)
@@ -524,7 +541,7 @@ class AttnBlock(nn.Module):
     def fwd(self, h, save, next_norm=None):
         C = self.in_channels
         N, H, W, _ = h.f32.shape
-        hn, stats = norm_act_fwd(self.norm, h.f32, 0, h.stats)
+        hn, stats = norm_act_fwd(self.norm, h.f32, 0, h.stats, save)
         qkv = torch.empty((N, H, W, 3 * C), dtype=torch.float32, device=h.f32.device)
         for i, m in enumerate((self.q, self.k, self.v)):
             conv_fwd(m, hn, C, out_f32=qkv[..., i * C:(i + 1) * C])
@@ -582,7 +599,7 @@ class ResNetBlock(nn.Module):
 
     def fwd(self, h, save, want_bf16=False, next_norm=None):
         act = self.net1[1].code
-        a1, st1 = norm_act_fwd(self.net1[0], h.f32, act, h.stats)
+        a1, st1 = norm_act_fwd(self.net1[0], h.f32, act, h.stats, save)
         # h1 only feeds net2's GroupNorm (it is not on the fp32 residual stream): when its statistics come out of the
         # conv epilogue (taken from the fp32 accumulators) it is stored as bf16 -- half the bytes for the conv
         # epilogue, the norm's forward and both passes of its backward
@@ -592,7 +609,7 @@ class ResNetBlock(nn.Module):
                    and ops.fused_stats_ok(N_, H_, W_, self.ch_out, n2.num_groups, 0, H_, W_))
         r1 = conv_fwd(self.net1[2], a1, self.ch_in, stats_for=n2, want_f32=not h1_bf16, want_bf16=h1_bf16)
         h1 = r1[1] if h1_bf16 else r1[0]
-        a2, st2 = norm_act_fwd(n2, h1, self.net2[1].code, r1.stats)
+        a2, st2 = norm_act_fwd(n2, h1, self.net2[1].code, r1.stats, save)
         if self.ch_in != self.ch_out:
             xb = h.as_bf16()
             res, _ = conv_fwd(self.skip_conv, xb, self.ch_in)
@@ -795,7 +812,7 @@ class Encoder(nn.Module):
         if self.mid_attn:
             h, saved["attn"] = self.mid_attn1.fwd(h, save, next_norm=self.mid2.net1[0])
         h, saved["mid2"] = self.mid2.fwd(h, save, next_norm=self.norm_out)
-        a, st = norm_act_fwd(self.norm_out, h.f32, self.act_out.code, h.stats)
+        a, st = norm_act_fwd(self.norm_out, h.f32, self.act_out.code, h.stats, save)
         saved["out"] = (h.f32, st, a) if save else None
         Cz = self.conv_out.out_channels
         of, ob = conv_fwd(self.conv_out, a, self.norm_out.num_channels, want_f32=not tail_bf16, want_bf16=tail_bf16)
@@ -871,7 +888,7 @@ class Decoder(nn.Module):
             h, s = up.fwd(h, save, no_up=last, next_norm=nxt_norm)
             levels.append(s)
         saved["levels"] = levels
-        a, st = norm_act_fwd(self.norm_out, h.f32, self.act_out.code, h.stats)
+        a, st = norm_act_fwd(self.norm_out, h.f32, self.act_out.code, h.stats, save)
         saved["out"] = (h.f32, st, a) if save else None
         of, _ = conv_fwd(self.conv_out, a, self.norm_out.num_channels)
         return A(f32=of, C=self.in_channels), (saved if save else None)

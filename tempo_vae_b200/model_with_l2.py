@@ -49,7 +49,7 @@ class L2PredictionHead(nn.Module):
             conv, norm, act = mods[i], mods[i + 1], mods[i + 2]
             r = conv_fwd(conv, h, cin, stats_for=norm)
             f32 = r[0]
-            a, st = norm_act_fwd(norm, f32, act.code, r.stats)
+            a, st = norm_act_fwd(norm, f32, act.code, r.stats, save)
             saved.append((h, f32, st))
             h, cin = a, conv.out_channels
         pred, _ = conv_fwd(mods[-1], h, cin)

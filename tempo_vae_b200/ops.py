@@ -469,35 +469,54 @@ def gn_fast_ok(Cc, G):
     return 1 <= U <= 256 and 256 % U == 0 and 256 % (Cc // G // 8) == 0
 
 
+# Handing the activation derivative from forward to backward (tvae_gn_act_fwd2 / _bwd2) removes GELU' from the backward
+# row-sum pass (16 of its 24 instructions per element) for 2 B/element written by the forward and read by the backward.
+# Measured inside the live B=256 step (two A/B pairs, one box): gn_act_bwd 0.95 -> 0.61 ms per large call, gn_act_fwd
+# 0.33 -> 0.43 ms, i.e. -2.5 ms of kernel time per step -- and the STEP got 1.2 ms slower (110.3 -> 111.6 ms). The board
+# sits at its 1 kW power cap for the whole step: what bounds the step is energy, and 4 B/element of extra DRAM traffic
+# costs about as much energy as the 16 instructions it saves, so the GEMMs that follow simply clock lower. OFF by
+# default (TVAE_GN_SAVE_ACT_GRAD=1 turns it on); kept because on an uncapped part the trade goes the other way.
+SAVE_ACT_GRAD = [os.environ.get("TVAE_GN_SAVE_ACT_GRAD", "0") == "1"]
+
+
 @_on_device
-def gn_act_fwd(x, stats, gamma, beta, G, act):
-    """x: the GroupNorm input, dense NHWC, fp32 or bf16 (see tvae_gn_act_fwd)."""
+def gn_act_fwd(x, stats, gamma, beta, G, act, want_act_grad=False):
+    """x: the GroupNorm input, dense NHWC, fp32 or bf16 (see tvae_gn_act_fwd). With want_act_grad (training, an
+    activation, the vectorised geometry, bf16 mode) returns (out, act'(y) as bf16), else out."""
     N, H, W, Cc = x.shape
     assert x.is_contiguous() and x.dtype in (torch.float32, torch.bfloat16)
     out = torch.empty((N, H, W, Cc), dtype=torch.bfloat16, device=x.device)
     lo = _lo_like(out)
-    _timed("gn_act_fwd", x.numel() * (x.element_size() + 2),
-           lambda: check(lib.tvae_gn_act_fwd(x.data_ptr(), int(x.dtype == torch.bfloat16), stats.data_ptr(),
-                                             gamma.data_ptr(), beta.data_ptr(), N, H * W, Cc, G, int(act),
-                                             out.data_ptr(), _ptr(lo), _stream()), "tvae_gn_act_fwd"))
+    gp = None
+    if want_act_grad and (SAVE_ACT_GRAD[0] or want_act_grad == "force") and act != 0 and lo is None and gn_fast_ok(Cc, G):
+        gp = torch.empty((N, H, W, Cc), dtype=torch.bfloat16, device=x.device)
+    _timed("gn_act_fwd", x.numel() * (x.element_size() + 2 + (2 if gp is not None else 0)),
+           lambda: check(lib.tvae_gn_act_fwd2(x.data_ptr(), int(x.dtype == torch.bfloat16), stats.data_ptr(),
+                                              gamma.data_ptr(), beta.data_ptr(), N, H * W, Cc, G, int(act),
+                                              out.data_ptr(), _ptr(lo), _ptr(gp), _stream()), "tvae_gn_act_fwd"))
+    if want_act_grad:
+        return _pair(out, lo), gp
     return _pair(out, lo)
 
 
 @_on_device
-def gn_act_bwd(x, stats, gamma, beta, da, gres, G, act, dgamma, dbeta, dx_colsum=None):
-    """dx_colsum (optional fp32 [C]): receives the column sums of dx (= bias gradient of the conv that produced x)."""
+def gn_act_bwd(x, stats, gamma, beta, da, gres, G, act, dgamma, dbeta, dx_colsum=None, act_grad=None):
+    """dx_colsum (optional fp32 [C]): receives the column sums of dx (= bias gradient of the conv that produced x).
+    act_grad (optional bf16, from gn_act_fwd(want_act_grad=True)): the backward then never evaluates the activation."""
     N, H, W, Cc = x.shape
     da, gres = hi_of(da), hi_of(gres)
     assert da.shape[-1] == Cc and da.dtype == torch.bfloat16
     dx = torch.empty((N, H, W, Cc), dtype=torch.bfloat16, device=x.device)
     ws = _workspace(lib.tvae_gn_bwd_workspace_bytes(N, H * W, Cc, G), x.device, "gn")
     assert x.is_contiguous() and x.dtype in (torch.float32, torch.bfloat16)
-    # algorithmic bytes of ONE pass: x + da (+ the residual-branch gradient) read, dx written
-    _timed("gn_act_bwd", x.numel() * (x.element_size() + 2 + (2 if gres is not None else 0) + 2),
-           lambda: check(lib.tvae_gn_act_bwd(x.data_ptr(), int(x.dtype == torch.bfloat16), stats.data_ptr(),
-                                             gamma.data_ptr(), beta.data_ptr(), da.data_ptr(), _ptr(gres), N, H * W, Cc,
-                                             G, int(act), dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(),
-                                             _ptr(dx_colsum), ws.data_ptr(), _stream()), "tvae_gn_act_bwd"))
+    # algorithmic bytes of ONE pass: x + da (+ the residual-branch gradient, + the saved act') read, dx written
+    nbytes = x.numel() * (x.element_size() + 2 + (2 if gres is not None else 0) + (2 if act_grad is not None else 0) + 2)
+    _timed("gn_act_bwd", nbytes,
+           lambda: check(lib.tvae_gn_act_bwd2(x.data_ptr(), int(x.dtype == torch.bfloat16), stats.data_ptr(),
+                                              gamma.data_ptr(), beta.data_ptr(), da.data_ptr(), _ptr(gres),
+                                              _ptr(act_grad), N, H * W, Cc, G, int(act), dx.data_ptr(),
+                                              dgamma.data_ptr(), dbeta.data_ptr(), _ptr(dx_colsum), ws.data_ptr(),
+                                              _stream()), "tvae_gn_act_bwd"))
     if dx_colsum is not None:
         KERNEL_LAUNCHES[0] += 2
     return dx

@@ -320,6 +320,51 @@ def test_groupnorm_bf16_input(N, H, W, C, G, act):
                      torch.zeros((1, 2, 2), device="cuda"), torch.ones(4, device="cuda"), torch.zeros(4, device="cuda"), 2, 1)
 
 
+@pytest.mark.parametrize("N,H,W,C,act,x_bf16", [(3, 16, 16, 128, 1, False), (2, 64, 64, 512, 1, True), (2, 8, 8, 256, 3, False),
+                                                 (2, 16, 16, 128, 2, False)])
+def test_groupnorm_saved_activation_gradient(N, H, W, C, act, x_bf16):
+    """tvae_gn_act_fwd2 / _bwd2: the forward also stores act'(y) (bf16) and the backward starts from it instead of
+    re-evaluating the activation. The stored derivative is checked against torch, the backward against the recomputing
+    path (same inputs) and against fp32 autograd."""
+    o = ops()
+    G = 8
+    g = torch.Generator(device="cuda").manual_seed(31)
+    x = bf16_round(torch.randn((N, H, W, C), device="cuda", generator=g) * 1.7 + 0.3)
+    gamma = torch.randn((C,), device="cuda", generator=g) * 0.5 + 1.0
+    beta = torch.randn((C,), device="cuda", generator=g) * 0.2
+    da = torch.randn((N, H, W, C), device="cuda", generator=g).to(torch.bfloat16)
+    gres = torch.randn((N, H, W, C), device="cuda", generator=g).to(torch.bfloat16)
+    stats = o.gn_stats(x, C, G, 1e-6)
+    xin = x.to(torch.bfloat16) if x_bf16 else x
+    a_plain = o.gn_act_fwd(xin, stats, gamma, beta, G, act)
+    a, gp = o.gn_act_fwd(xin, stats, gamma, beta, G, act, want_act_grad="force")     # (off by default in the model)
+    assert gp is not None and gp.dtype == torch.bfloat16 and gp.shape == a.shape
+    assert torch.equal(a, a_plain)
+    fn = {1: F.gelu, 2: F.relu, 3: F.silu}[act]
+    y = F.group_norm(x.permute(0, 3, 1, 2), G, gamma, beta, 1e-6).detach().requires_grad_(True)
+    fn(y).sum().backward()
+    ref_gp = y.grad.permute(0, 2, 3, 1)
+    if act == 2:     # ReLU': ignore the elements whose pre-activation rounds across 0
+        keep = y.detach().permute(0, 2, 3, 1).abs() > 1e-3
+        assert torch.equal(gp.float()[keep], ref_gp[keep])
+    else:
+        assert float((gp.float() - ref_gp).abs().max()) < 8e-3          # bf16 storage of a value in [-0.2, 1.2]
+    outs = []
+    for use in (None, gp):
+        dg, db, cs = (torch.full((C,), float("nan"), device="cuda") for _ in range(3))
+        dx = o.gn_act_bwd(xin, stats, gamma, beta, da, gres, G, act, dg, db, cs, use)
+        outs.append((dx, dg, db, cs))
+    torch.cuda.synchronize()
+    xr = x.permute(0, 3, 1, 2).clone().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    fn(F.group_norm(xr, G, gr, br, 1e-6)).backward(da.float().permute(0, 3, 1, 2))
+    ref_dx = xr.grad.permute(0, 2, 3, 1) + gres.float()
+    for dx, dg, db, cs in outs:
+        assert rel_err(dx.float(), ref_dx) < 1e-2
+        assert rel_err(dg, gr.grad) < 3e-3 and rel_err(db, br.grad) < 3e-3
+    assert rel_err(outs[1][0].float(), outs[0][0].float()) < 8e-3
+
+
 @pytest.mark.parametrize("N,H,W,C,x_bf16,with_gres,group_mb", [(7, 64, 64, 512, False, True, 30), (5, 64, 64, 512, True, False, 20),
                                                                (37, 32, 32, 256, False, True, 8), (3, 16, 16, 128, False, True, 1)])
 def test_groupnorm_bwd_single_pass_matches_two_pass(N, H, W, C, x_bf16, with_gres, group_mb):
