@@ -101,6 +101,11 @@ typedef struct {
    * side of encoder.conv_in sit on the GEMM's M dimension (9 row tiles, 11 % padding) instead of its N dimension
    * (5 column tiles of 208 with 23 % wasted operand loads). */
   int32_t flip;
+  /* Sub-block of a larger parameter: the GEMM covers only Cm x Cn of a parameter whose INNER channel dimension (Cn without
+   * flip, Cm with flip) has grad_ld entries, starting at grad_off. 0 / 0 = the parameter is exactly Cm x Cn. Lets a
+   * 1028-channel weight gradient be computed as a 1024-channel GEMM (whole 128-row tiles) plus a skinny 4-channel one
+   * with the 4 channels on the N side (16-column MMAs) instead of a 128-row tile that is 97 % padding. */
+  int32_t grad_ld, grad_off;
 } tvae_wgrad_args;
 int32_t tvae_wgrad_gemm(const tvae_wgrad_args* args, tvae_stream_t stream);
 /* Scheduling switch like tvae_conv_set_cta_pair: 1 (default) pairs adjacent 128-row M tiles on CTA pairs (cta_group::2);

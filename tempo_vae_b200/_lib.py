@@ -51,6 +51,7 @@ class WgradArgs(C.Structure):
         ("grad", C.c_void_p),
         ("accumulate", C.c_int32),
         ("flip", C.c_int32),
+        ("grad_ld", C.c_int32), ("grad_off", C.c_int32),
     ]
 
 

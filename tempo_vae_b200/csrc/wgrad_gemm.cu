@@ -266,7 +266,7 @@ int g_wgrad_cta_pair = 1;
 // the GEMM ran with the operand roles exchanged (GEMM row = the parameter's second index): grad[n][m][tap].
 __global__ void wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ grad, int cm, int cn,
                                     int ntaps, int cn_pitch, int splits, int accumulate, int swapped, int row0,
-                                    int nrows, long long split_stride) {
+                                    int nrows, long long split_stride, int ld, int off) {
   const long long total = (long long)nrows * cn * ntaps;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -277,11 +277,11 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, float* __res
     if (!swapped) {            // parameter [cm][cn][tap]: consecutive threads write consecutive elements
       n = (int)(rc % cn);
       ml = (int)(rc / cn);
-      dst = ((long long)(row0 + ml) * cn + n) * ntaps + tap;
+      dst = ((long long)(row0 + ml) * ld + off + n) * ntaps + tap;
     } else {                   // parameter [cn][cm][tap]
       ml = (int)(rc % nrows);
       n = (int)(rc / nrows);
-      dst = ((long long)n * cm + row0 + ml) * ntaps + tap;
+      dst = ((long long)n * ld + off + row0 + ml) * ntaps + tap;
     }
     const float* src = part + ((long long)ml * ntaps + tap) * cn_pitch + n;
     float s = 0.f;
@@ -347,6 +347,8 @@ extern "C" int32_t tvae_wgrad_gemm(const tvae_wgrad_args* a, cudaStream_t stream
   TVAE_CHECK(a->p_pitch % 8 == 0 && a->q_pitch % 8 == 0, "tvae_wgrad_gemm: pitches must be multiples of 8");
   TVAE_CHECK(a->splits >= 1, "tvae_wgrad_gemm: splits must be >= 1");
   TVAE_CHECK(!a->flip || a->kind == 0, "tvae_wgrad_gemm: flip (exchanged operand roles) is for stride-1 convs only");
+  TVAE_CHECK(a->grad_ld == 0 || (a->grad_off >= 0 && a->grad_off + (a->flip ? a->Cm : a->Cn) <= a->grad_ld),
+             "tvae_wgrad_gemm: grad_off + channels exceeds grad_ld");
 
   WgradMaps maps;
   WgradParams p;
@@ -406,8 +408,9 @@ extern "C" int32_t tvae_wgrad_gemm(const tvae_wgrad_args* a, cudaStream_t stream
     const long long total_out = (long long)nrows * a->Cn * p.ntaps;
     int rgrid = (int)((total_out + 255) / 256);
     if (rgrid > 148 * 16) rgrid = 148 * 16;
+    const int ld = a->grad_ld > 0 ? a->grad_ld : (a->flip ? a->Cm : a->Cn);
     wgrad_reduce_kernel<<<rgrid, 256, 0, stream>>>(part, a->grad, a->Cm, a->Cn, p.ntaps, p.cn_pitch, splits,
-                                                  a->accumulate, a->flip, row0, nrows, split_stride);
+                                                  a->accumulate, a->flip, row0, nrows, split_stride, ld, a->grad_off);
   };
 
   // ---- main launch

@@ -336,7 +336,7 @@ def _workspace(nbytes, device, key="ws"):
 
 
 @_on_device
-def wgrad_gemm(p, Cm, q, Cn, *, kind, R, grad, accumulate=False, splits=0, flip=False):
+def wgrad_gemm(p, Cm, q, Cn, *, kind, R, grad, accumulate=False, splits=0, flip=False, grad_ld=0, grad_off=0):
     """grad[m][n][tap] (+)= sum_pixels p[pixel][m] * q[pixel (+) tap][n]; p: bf16 [N,H,W,pitch] (the dense grid).
     flip=True (stride-1 only): p = x, q = dY read at pixel (-) tap, grad written as [n][m][tap] (see include/tvae.h)."""
     p, q = hi_of(p), hi_of(q)
@@ -347,13 +347,18 @@ def wgrad_gemm(p, Cm, q, Cn, *, kind, R, grad, accumulate=False, splits=0, flip=
         splits = lib.tvae_wgrad_splits(Cm, Cn, taps, N * H * W)
     nbytes = lib.tvae_wgrad_workspace_bytes(Cm, Cn, taps, splits)
     ws = _workspace(nbytes, p.device, "wgrad")
-    assert grad.is_contiguous() and grad.dtype == torch.float32 and grad.numel() == Cm * Cn * taps
+    assert grad.is_contiguous() and grad.dtype == torch.float32
+    if grad_ld:          # the GEMM fills a sub-block of the parameter's inner channel dimension (see tvae_wgrad_args)
+        assert grad.numel() == (Cn if flip else Cm) * grad_ld * taps and grad_off + (Cm if flip else Cn) <= grad_ld
+    else:
+        assert grad.numel() == Cm * Cn * taps
     a = WgradArgs()
     a.p = p.data_ptr(); a.p_pitch = pp; a.Cm = Cm
     a.q = q.data_ptr(); a.q_pitch = pitch_of(q); a.Cn = Cn
     a.N, a.H, a.W = N, H, W
     a.kind, a.R, a.splits = kind, R, splits
     a.workspace = ws.data_ptr(); a.grad = grad.data_ptr(); a.accumulate = int(accumulate); a.flip = int(flip)
+    a.grad_ld, a.grad_off = int(grad_ld), int(grad_off)
     m_tiles = (Cm + 127) // 128
     if WGRAD_CTA_PAIR[0] and m_tiles >= 3 and m_tiles % 2 == 1:
         KERNEL_LAUNCHES[0] += 2       # the odd last M tile runs as its own GEMM + reduce launch (see tvae_wgrad_gemm)

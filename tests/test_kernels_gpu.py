@@ -320,6 +320,35 @@ def test_groupnorm_bf16_input(N, H, W, C, G, act):
                      torch.zeros((1, 2, 2), device="cuda"), torch.ones(4, device="cuda"), torch.zeros(4, device="cuda"), 2, 1)
 
 
+def test_wgrad_sub_block_split_matches_single_gemm():
+    """tvae_wgrad_args.grad_ld / grad_off: a 132-channel weight gradient computed as a 128-channel GEMM (whole tile) plus a
+    4-channel skinny GEMM with the leftover channels on the N side, on the input-channel side (conv_in-like, written with
+    an inner-dimension offset) and on the output-channel side (conv_out-like, a contiguous row block), against the single
+    padded GEMM."""
+    o = ops()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    N, H, W, Cw, Cn = 2, 16, 16, 132, 128
+    xw = torch.randn((N, H, W, 136), device="cuda", generator=g).to(torch.bfloat16)        # 132 channels, pitch 136
+    dy = torch.randn((N, H, W, Cn), device="cuda", generator=g).to(torch.bfloat16)
+    # conv_in-like: weight [Cout=128][Cin=132][3][3]
+    ref = torch.empty((Cn, Cw, 3, 3), device="cuda")
+    o.wgrad_gemm(xw[..., :Cw], Cw, dy, Cn, kind=0, R=3, grad=ref, flip=True)
+    got = torch.full((Cn, Cw, 3, 3), float("nan"), device="cuda")
+    o.wgrad_gemm(xw[..., :128], 128, dy, Cn, kind=0, R=3, grad=got, flip=True, grad_ld=Cw, grad_off=0)
+    o.wgrad_gemm(dy, Cn, xw[..., 128:Cw], Cw - 128, kind=0, R=3, grad=got, grad_ld=Cw, grad_off=128)
+    torch.cuda.synchronize()
+    assert torch.isfinite(got).all() and rel_err(got, ref) < 1e-5
+    # conv_out-like: weight [Cout=132][Cin=128][3][3], dY has the 132 channels
+    ref2 = torch.empty((Cw, Cn, 3, 3), device="cuda")
+    o.wgrad_gemm(xw[..., :Cw], Cw, dy, Cn, kind=0, R=3, grad=ref2)
+    got2 = torch.full((Cw, Cn, 3, 3), float("nan"), device="cuda")
+    flat = got2.view(-1)
+    o.wgrad_gemm(xw[..., :128], 128, dy, Cn, kind=0, R=3, grad=flat[:128 * Cn * 9])
+    o.wgrad_gemm(dy, Cn, xw[..., 128:Cw], Cw - 128, kind=0, R=3, grad=flat[128 * Cn * 9:], flip=True)
+    torch.cuda.synchronize()
+    assert torch.isfinite(got2).all() and rel_err(got2, ref2) < 1e-5
+
+
 @pytest.mark.parametrize("N,H,W,C,act,x_bf16", [(3, 16, 16, 128, 1, False), (2, 64, 64, 512, 1, True), (2, 8, 8, 256, 3, False),
                                                  (2, 16, 16, 128, 2, False)])
 def test_groupnorm_saved_activation_gradient(N, H, W, C, act, x_bf16):
