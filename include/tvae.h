@@ -223,9 +223,12 @@ int32_t tvae_attn_bwd(const float* q, const float* k, const float* v, int32_t pi
                       const float* d_out, const float* lse, int32_t B, int32_t T, int32_t C, int32_t heads,
                       void* dqkv_bf16, float* workspace, tvae_stream_t stream);
 
-/* Tensor-core (mma.sync TF32, fp32 accumulate) variants of the two calls above for head dimension 32 (C == 32*heads);
+/* Tensor-core (TF32 operands, fp32 accumulate) variants of the two calls above for head dimension 32 (C == 32*heads);
  * same arguments, same layouts, any T. ~5e-4 relative error on the logits; the exact kernels above stay the path
- * for other head sizes and for the fp32 mode. */
+ * for other head sizes and for the fp32 mode. Default implementation: tcgen05.mma kind::tf32 with the scores,
+ * probabilities and output accumulators in TMEM (attention_sm100.cu); tvae_attn_set_tcgen05(0) selects the
+ * mma.sync.m16n8k8 kernels instead (returns the previous setting; a negative argument only queries). */
+int32_t tvae_attn_set_tcgen05(int32_t enable);
 int32_t tvae_attn_fwd_tc(const float* q, const float* k, const float* v, int32_t pitch, int32_t B, int32_t T,
                          int32_t C, int32_t heads, void* out_bf16, float* out_f32, float* lse, tvae_stream_t stream);
 int32_t tvae_attn_bwd_tc(const float* q, const float* k, const float* v, int32_t pitch, const float* o,

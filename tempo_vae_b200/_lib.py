@@ -93,6 +93,7 @@ def _load():
         "tvae_colsum_bf16": (i32, [vp, i64, i32, i32, vp, vp, vp]),
         "tvae_attn_fwd": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp]),
         "tvae_attn_bwd": (i32, [vp, vp, vp, i32, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp]),
+        "tvae_attn_set_tcgen05": (i32, [i32]),
         "tvae_attn_fwd_tc": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp]),
         "tvae_attn_bwd_tc": (i32, [vp, vp, vp, i32, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp]),
         "tvae_reparam_fwd": (i32, [vp, vp, u64, u64, i32, i32, i32, vp, i32, vp, vp, vp, vp, vp]),
@@ -131,6 +132,8 @@ if os.environ.get("TVAE_WGRAD_CTA_PAIR") in ("0", "1"):
     lib.tvae_wgrad_set_cta_pair(int(os.environ["TVAE_WGRAD_CTA_PAIR"]))
 if os.environ.get("TVAE_CONV_CTA_PAIR") in ("0", "1"):     # A/B switch of the conv schedule (results are bit-identical)
     lib.tvae_conv_set_cta_pair(int(os.environ["TVAE_CONV_CTA_PAIR"]))
+if os.environ.get("TVAE_ATTN_TCGEN05") in ("0", "1"):      # A/B switch: tcgen05 kind::tf32 attention vs the mma.sync kernels
+    lib.tvae_attn_set_tcgen05(int(os.environ["TVAE_ATTN_TCGEN05"]))
 
 
 def last_error() -> str:

@@ -351,12 +351,22 @@ constexpr size_t SMEM_DKV = SMEM_FWD + 2 * TILE * sizeof(float);
 
 using namespace tvae;
 
+// 1 (default): tcgen05 kind::tf32 kernels of attention_sm100.cu; 0: the mma.sync kernels of this file. Same precision
+// class (TF32 operands, fp32 accumulation), different summation order.
+static int g_attn_tcgen05 = 1;
+extern "C" int32_t tvae_attn_set_tcgen05(int32_t enable) {
+  const int old = g_attn_tcgen05;
+  if (enable >= 0) g_attn_tcgen05 = enable ? 1 : 0;
+  return old;
+}
+
 extern "C" int32_t tvae_attn_fwd_tc(const float* q, const float* k, const float* v, int32_t pitch, int32_t B, int32_t T,
                                     int32_t C, int32_t heads, void* out_bf16, float* out_f32, float* lse,
                                     cudaStream_t stream) {
   TVAE_ENTER(q);
   TVAE_CHECK(q && k && v && (out_bf16 || out_f32), "tvae_attn_fwd_tc: null pointer");
   TVAE_CHECK(heads > 0 && C == HD * heads, "tvae_attn_fwd_tc: head dimension must be 32 (C = %d, heads = %d)", C, heads);
+  if (g_attn_tcgen05) return attn_fwd_sm100(q, k, v, pitch, B, T, heads, out_bf16, out_f32, lse, stream);
   const float scale = 1.0f / sqrtf((float)HD);
   TVAE_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_FWD));
   dim3 grid((T + WARPS * 16 - 1) / (WARPS * 16), B * heads);
@@ -372,6 +382,7 @@ extern "C" int32_t tvae_attn_bwd_tc(const float* q, const float* k, const float*
   TVAE_ENTER(q);
   TVAE_CHECK(q && k && v && o && d_out && lse && dqkv_bf16 && workspace, "tvae_attn_bwd_tc: null pointer");
   TVAE_CHECK(heads > 0 && C == HD * heads, "tvae_attn_bwd_tc: head dimension must be 32 (C = %d, heads = %d)", C, heads);
+  if (g_attn_tcgen05) return attn_bwd_sm100(q, k, v, pitch, o, d_out, lse, B, T, heads, dqkv_bf16, workspace, stream);
   const float scale = 1.0f / sqrtf((float)HD);
   __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(dqkv_bf16);
   dim3 grid((T + WARPS * 16 - 1) / (WARPS * 16), B * heads);

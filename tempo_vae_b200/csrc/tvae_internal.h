@@ -50,6 +50,12 @@ int gn_act_bwd_fast(const void* x, bool x_bf16, const float* stats, const float*
                     const __nv_bfloat16* gres, const __nv_bfloat16* gp, int N, int HW, int C, int G, int act,
                     __nv_bfloat16* dx, float* dgamma, float* dbeta, float* dx_colsum, float* ws, cudaStream_t stream);
 
+// tcgen05 (kind::tf32) attention for head dimension 32 (attention_sm100.cu); arguments as tvae_attn_fwd_tc / _bwd_tc
+int attn_fwd_sm100(const float* q, const float* k, const float* v, int pitch, int B, int T, int heads, void* out_bf16,
+                   float* out_f32, float* lse, cudaStream_t stream);
+int attn_bwd_sm100(const float* q, const float* k, const float* v, int pitch, const float* o, const float* d_out,
+                   const float* lse, int B, int T, int heads, void* dqkv_bf16, float* workspace, cudaStream_t stream);
+
 // A/B switch of the single-pass GroupNorm backward (gn_fast.cu); group_mb <= 0 keeps the current group size
 void gn_set_bwd_fused(int on, int group_mb);
 

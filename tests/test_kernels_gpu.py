@@ -458,14 +458,48 @@ def test_colsum(rows, C, pitch):
                                             (2, 100, 32, 4, False), (2, 100, 128, 4, True), (1, 700, 64, 2, True),
                                             (3, 256, 128, 4, False)])
 def test_attention_fwd_bwd(B, T, C, heads, tc):
-    """tc=True: TF32 tensor-core kernels (head dim 32), tolerance 3e-3 of the max; tc=False: exact fp32 kernels, 1e-4."""
+    """tc=True: TF32 tensor-core kernels (head dim 32; tcgen05 kind::tf32 by default, then the mma.sync kernels behind
+    tvae_attn_set_tcgen05(0)), tolerance 3e-3 of the max; tc=False: exact fp32 kernels, 1e-4."""
     o = ops()
     o.ATTN_TENSOR_CORES[0] = tc
     assert o.attn_uses_tensor_cores(C, heads) == (tc and C == 32 * heads)
     try:
+        assert o.lib.tvae_attn_set_tcgen05(-1) == 1          # the tcgen05 kernels are the default
         _attention_case(o, B, T, C, heads, 3e-3 if tc else 1e-4)
+        if tc:
+            o.lib.tvae_attn_set_tcgen05(0)
+            _attention_case(o, B, T, C, heads, 3e-3)
     finally:
         o.ATTN_TENSOR_CORES[0] = True
+        o.lib.tvae_attn_set_tcgen05(1)
+
+
+@pytest.mark.parametrize("B,T,heads", [(2, 256, 4), (1, 200, 4), (2, 64, 1), (1, 2048, 2), (1, 1, 4), (1, 129, 3)])
+def test_attention_tcgen05_matches_mma_sync(B, T, heads):
+    """The two TF32 implementations (tcgen05 + TMEM vs mma.sync) agree to TF32 rounding on every output, including the
+    saved log-sum-exp, on ragged / tiny / multi-tile token counts; the tcgen05 kernels are run-to-run bit-identical."""
+    o = ops()
+    C = 32 * heads
+    g = torch.Generator(device="cuda").manual_seed(T)
+    qkv = torch.randn((B * T, 3 * C), device="cuda", generator=g) * 1.5
+    d_out = torch.randn((B * T, C), device="cuda", generator=g)
+    res = {}
+    try:
+        for impl in (1, 0, 1):
+            o.lib.tvae_attn_set_tcgen05(impl)
+            ob, of, lse = o.attn_fwd(qkv, C, heads, B, T)
+            dqkv = o.attn_bwd(qkv, of, d_out, lse, C, heads, B, T)
+            torch.cuda.synchronize()
+            res.setdefault(impl, []).append((ob.clone(), of.clone(), lse.clone(), dqkv.clone()))
+    finally:
+        o.lib.tvae_attn_set_tcgen05(1)
+    a, a2, b = res[1][0], res[1][1], res[0][0]
+    for x, y in zip(a, a2):
+        assert torch.equal(x, y)
+    assert rel_err(a[1], b[1]) < 2e-3 and rel_err(a[0].float(), b[0].float()) < 1e-2
+    assert (a[2] - b[2]).abs().max().item() < 2e-3
+    assert rel_err(a[3].float(), b[3].float()) < 1e-2
+    assert all(torch.isfinite(t.float()).all() for t in a)
 
 
 def _attention_case(o, B, T, C, heads, tol):
