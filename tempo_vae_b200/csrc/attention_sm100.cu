@@ -35,11 +35,10 @@ constexpr int COL_TILE_BYTES = CT * 128;
 constexpr int OPITCH = 33;             // floats per row of the output transposition buffer (bank-conflict free)
 constexpr float LOG2E = 1.4426950408889634f;
 
-__device__ __forceinline__ uint32_t tf32_rna(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
-}
+// Round to TF32 (10 mantissa bits), ties away from zero, as two integer instructions. cvt.rna.tf32.f32 lowers to a
+// five-instruction sequence with an Inf/NaN check; every operand element passes through here, and none of them is
+// Inf/NaN unless the inputs already were.
+__device__ __forceinline__ uint32_t tf32_rna(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
 
 // kind::tf32, fp32 accumulate (InstrDescriptor of cute/arch/mma_sm100_desc.hpp: a/b format 2 = TF32)
 __device__ __forceinline__ uint32_t make_idesc_tf32(int M, int N, int a_mn_major, int b_mn_major) {
@@ -111,25 +110,49 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// Stage `rows` token rows of head h (channels d * heads + h) starting at global row `row0` as tf32 into a K-major tile
-// (dst_k: element (r, d) at r * 128 + ((d / 4) ^ (r & 7)) * 16 + (d & 3) * 4) and / or an MN-major tile (dst_mn:
-// r * 128 + ((d / 8) ^ (r & 3)) * 32 + (d & 7) * 4). Rows >= valid are zero. One warp per row, lane = d: the 32
-// loads of a row cover 32 * heads * 4 contiguous bytes, the 32 stores hit 32 different banks.
-__device__ __forceinline__ void stage_tile(uint8_t* __restrict__ dst_k, uint8_t* __restrict__ dst_mn,
-                                           const float* __restrict__ src, long long pitch, long long row0, int valid,
-                                           int rows, int heads, int h, float scale) {
+// Staging of `ROWS` token rows of head h (channels d * heads + h) starting at global row `row0`, split into the global
+// loads (into registers: issued one tile AHEAD so their L2 latency hides behind the MMAs and the softmax of the
+// current tile -- with two to three CTAs of four warps per SM nothing else would hide it) and the tf32 stores into a
+// K-major tile (dst_k: element (r, d) at r * 128 + ((d / 4) ^ (r & 7)) * 16 + (d & 3) * 4) and / or an MN-major tile
+// (dst_mn: r * 128 + ((d / 8) ^ (r & 3)) * 32 + (d & 7) * 4). Rows >= valid are zero. One warp per row, lane = d: the
+// 32 loads of a row cover 32 * heads * 4 contiguous bytes, the 32 stores hit 32 different banks.
+template <int ROWS>
+__device__ __forceinline__ void load_tile(float (&regs)[ROWS / 4], const float* __restrict__ src, long long pitch,
+                                          long long row0, int valid, int heads, int h) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float* p = src + row0 * pitch + lane * heads + h;
+  const float* p = src + (row0 + warp) * pitch + lane * heads + h;
+  const uint32_t step = 4u * (uint32_t)pitch;     // a tile spans < 2^31 elements: 32-bit offsets from one base pointer
+  if (valid >= ROWS) {
+#pragma unroll
+    for (int i = 0; i < ROWS / 4; ++i) regs[i] = __ldg(p + (uint32_t)i * step);
+  } else {
+#pragma unroll
+    for (int i = 0; i < ROWS / 4; ++i) {
+      regs[i] = 0.f;
+      if (warp + 4 * i < valid) regs[i] = __ldg(p + (uint32_t)i * step);
+    }
+  }
+}
+template <int ROWS>
+__device__ __forceinline__ void store_tile(const float (&regs)[ROWS / 4], uint8_t* __restrict__ dst_k,
+                                           uint8_t* __restrict__ dst_mn, float scale) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t c16 = (uint32_t)(lane >> 2), w16 = (uint32_t)(lane & 3) << 2;
   const uint32_t c32 = (uint32_t)(lane >> 3), w32 = (uint32_t)(lane & 7) << 2;
-#pragma unroll 8
-  for (int r = warp; r < rows; r += NT / 32) {
-    float v = 0.f;
-    if (r < valid) v = __ldg(p + (long long)r * pitch) * scale;
-    const uint32_t t = tf32_rna(v);
+#pragma unroll
+  for (int i = 0; i < ROWS / 4; ++i) {
+    const int r = warp + 4 * i;
+    const uint32_t t = tf32_rna(regs[i] * scale);
     if (dst_k) *reinterpret_cast<uint32_t*>(dst_k + r * 128 + (((c16 ^ (uint32_t)(r & 7)) << 4) | w16)) = t;
     if (dst_mn) *reinterpret_cast<uint32_t*>(dst_mn + r * 128 + (((c32 ^ (uint32_t)(r & 3)) << 5) | w32)) = t;
   }
+}
+__device__ __forceinline__ void stage_tile(uint8_t* __restrict__ dst_k, uint8_t* __restrict__ dst_mn,
+                                           const float* __restrict__ src, long long pitch, long long row0, int valid,
+                                           int heads, int h, float scale) {
+  float regs[RT / 4];
+  load_tile<RT>(regs, src, pitch, row0, valid, heads, h);
+  store_tile<RT>(regs, dst_k, dst_mn, scale);
 }
 
 // Each thread hands over its row of 32 values; they are written out as out[(grow0 + r) * opitch + d * heads + h] with
@@ -153,8 +176,6 @@ __device__ __forceinline__ void write_rows(float* __restrict__ buf, const float 
     }
   }
 }
-
-__device__ float* g_dbg = nullptr;   // TEMPORARY debug dump
 
 struct Smem {
   uint8_t* base;       // 1024-byte aligned
@@ -196,7 +217,7 @@ attn_fwd_sm100_kernel(const float* __restrict__ q, const float* __restrict__ k, 
     mbar_init(&sm.bars[1], 1);
     fence_mbar_init();
   }
-  stage_tile(sQ, nullptr, q, pitch, base + row0, rvalid, RT, heads, h, scale * LOG2E);
+  stage_tile(sQ, nullptr, q, pitch, base + row0, rvalid, heads, h, scale * LOG2E);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -213,10 +234,13 @@ attn_fwd_sm100_kernel(const float* __restrict__ q, const float* __restrict__ k, 
 #pragma unroll
   for (int d = 0; d < HD; ++d) o[d] = 0.f;
   uint32_t phase = 0;
+  float rk[CT / 4], rv[CT / 4];
+  load_tile<CT>(rk, k, pitch, base, min(CT, T), heads, h);
+  load_tile<CT>(rv, v, pitch, base, min(CT, T), heads, h);
   for (int k0 = 0; k0 < T; k0 += CT) {
     const int kvalid = min(CT, T - k0);
-    stage_tile(sK, nullptr, k, pitch, base + k0, kvalid, CT, heads, h, 1.0f);
-    stage_tile(nullptr, sV, v, pitch, base + k0, kvalid, CT, heads, h, 1.0f);
+    store_tile<CT>(rk, sK, nullptr, 1.0f);
+    store_tile<CT>(rv, nullptr, sV, 1.0f);
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -229,15 +253,16 @@ attn_fwd_sm100_kernel(const float* __restrict__ q, const float* __restrict__ k, 
       }
       __syncwarp();
     }
+    if (k0 + CT < T) {   // next tile's loads fly during this tile's MMAs and softmax
+      load_tile<CT>(rk, k, pitch, base + k0 + CT, min(CT, T - k0 - CT), heads, h);
+      load_tile<CT>(rv, v, pitch, base + k0 + CT, min(CT, T - k0 - CT), heads, h);
+    }
     mbar_wait(&sm.bars[0], phase, 31);
     tc_fence_after();
     uint32_t s[CT];
     tmem_ld32(tlane, s);
     tmem_ld32(tlane + 32, s + 32);
     tmem_ld_wait();
-    if (g_dbg && blockIdx.x == 0 && blockIdx.y == 0 && k0 == 0) {
-      for (int c = 0; c < CT; ++c) g_dbg[threadIdx.x * CT + c] = __uint_as_float(s[c]);
-    }
     float mx = -INFINITY;
     if (kvalid < CT) {
 #pragma unroll
@@ -277,13 +302,6 @@ attn_fwd_sm100_kernel(const float* __restrict__ q, const float* __restrict__ k, 
     uint32_t ot[HD];
     tmem_ld32(tlane + CT, ot);
     tmem_ld_wait();
-    if (g_dbg && blockIdx.x == 0 && blockIdx.y == 0 && k0 == 0) {
-      for (int d = 0; d < HD; ++d) g_dbg[RT * CT + threadIdx.x * HD + d] = __uint_as_float(ot[d]);
-      uint32_t pb[32];
-      tmem_ld32(tlane, pb);
-      tmem_ld_wait();
-      for (int c = 0; c < 32; ++c) g_dbg[RT * CT + RT * HD + threadIdx.x * 32 + c] = __uint_as_float(pb[c]);
-    }
 #pragma unroll
     for (int d = 0; d < HD; ++d) o[d] = fmaf(o[d], alpha, __uint_as_float(ot[d]));
     phase ^= 1;
@@ -335,7 +353,7 @@ attn_bwd_dq_sm100_kernel(const float* __restrict__ q, const float* __restrict__ 
     mbar_init(&sm.bars[1], 1);
     fence_mbar_init();
   }
-  stage_tile(sQ, nullptr, q, pitch, base + row0, rvalid, RT, heads, h, scale * LOG2E);
+  stage_tile(sQ, nullptr, q, pitch, base + row0, rvalid, heads, h, scale * LOG2E);
   {
     // dO tile, and D = rowsum(dO * O) from the same loads (one warp per row, lane = d)
     const float* pd = dout + (base + row0) * C + lane * heads + h;
@@ -370,10 +388,13 @@ attn_bwd_dq_sm100_kernel(const float* __restrict__ q, const float* __restrict__ 
   const uint64_t dKmn = make_smem_desc_mn32(smem_u32(sKmn), 1024, 512);
 
   uint32_t phase = 0;
+  float rk[CT / 4], rv[CT / 4];
+  load_tile<CT>(rk, k, pitch, base, min(CT, T), heads, h);
+  load_tile<CT>(rv, v, pitch, base, min(CT, T), heads, h);
   for (int k0 = 0; k0 < T; k0 += CT) {
     const int kvalid = min(CT, T - k0);
-    stage_tile(sK, sKmn, k, pitch, base + k0, kvalid, CT, heads, h, 1.0f);
-    stage_tile(sV, nullptr, v, pitch, base + k0, kvalid, CT, heads, h, 1.0f);
+    store_tile<CT>(rk, sK, sKmn, 1.0f);
+    store_tile<CT>(rv, sV, nullptr, 1.0f);
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -387,6 +408,10 @@ attn_bwd_dq_sm100_kernel(const float* __restrict__ q, const float* __restrict__ 
         umma_commit(&sm.bars[0]);
       }
       __syncwarp();
+    }
+    if (k0 + CT < T) {
+      load_tile<CT>(rk, k, pitch, base + k0 + CT, min(CT, T - k0 - CT), heads, h);
+      load_tile<CT>(rv, v, pitch, base + k0 + CT, min(CT, T - k0 - CT), heads, h);
     }
     mbar_wait(&sm.bars[0], phase, 33);
     tc_fence_after();
@@ -464,8 +489,8 @@ attn_bwd_dkv_sm100_kernel(const float* __restrict__ q, const float* __restrict__
     mbar_init(&sm.bars[1], 1);
     fence_mbar_init();
   }
-  stage_tile(sK, nullptr, k, pitch, base + row0, rvalid, RT, heads, h, scale * LOG2E);
-  stage_tile(sV, nullptr, v, pitch, base + row0, rvalid, RT, heads, h, 1.0f);
+  stage_tile(sK, nullptr, k, pitch, base + row0, rvalid, heads, h, scale * LOG2E);
+  stage_tile(sV, nullptr, v, pitch, base + row0, rvalid, heads, h, 1.0f);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -481,15 +506,17 @@ attn_bwd_dkv_sm100_kernel(const float* __restrict__ q, const float* __restrict__
   const uint64_t dDOmn = make_smem_desc_mn32(smem_u32(sDOmn), 1024, 512);
 
   uint32_t phase = 0;
+  float rq[CT / 4], rdo[CT / 4], rl = 0.f, rd = 0.f;
+  const long long stat0 = ((long long)b * heads + h) * T;
+  load_tile<CT>(rq, q, pitch, base, min(CT, T), heads, h);
+  load_tile<CT>(rdo, dout, C, base, min(CT, T), heads, h);
+  if ((int)threadIdx.x < min(CT, T)) { rl = lse[stat0 + threadIdx.x]; rd = dsum[stat0 + threadIdx.x]; }
   for (int q0 = 0; q0 < T; q0 += CT) {
-    const int qvalid = min(CT, T - q0);
-    stage_tile(sQ, sQmn, q, pitch, base + q0, qvalid, CT, heads, h, 1.0f);
-    stage_tile(sDO, sDOmn, dout, C, base + q0, qvalid, CT, heads, h, 1.0f);
+    store_tile<CT>(rq, sQ, sQmn, 1.0f);
+    store_tile<CT>(rdo, sDO, sDOmn, 1.0f);
     if ((int)threadIdx.x < CT) {
-      const bool ok = (int)threadIdx.x < qvalid;
-      const long long i = ((long long)b * heads + h) * T + q0 + threadIdx.x;
-      sL[threadIdx.x] = ok ? lse[i] * LOG2E : 0.f;
-      sD[threadIdx.x] = ok ? dsum[i] : 0.f;
+      sL[threadIdx.x] = rl * LOG2E;
+      sD[threadIdx.x] = rd;
     }
     fence_proxy_async_smem();
     tc_fence_before();
@@ -504,6 +531,13 @@ attn_bwd_dkv_sm100_kernel(const float* __restrict__ q, const float* __restrict__
         umma_commit(&sm.bars[0]);
       }
       __syncwarp();
+    }
+    if (q0 + CT < T) {
+      const int nvalid = min(CT, T - q0 - CT);
+      load_tile<CT>(rq, q, pitch, base + q0 + CT, nvalid, heads, h);
+      load_tile<CT>(rdo, dout, C, base + q0 + CT, nvalid, heads, h);
+      rl = rd = 0.f;
+      if ((int)threadIdx.x < nvalid) { rl = lse[stat0 + q0 + CT + threadIdx.x]; rd = dsum[stat0 + q0 + CT + threadIdx.x]; }
     }
     mbar_wait(&sm.bars[0], phase, 35);
     tc_fence_after();
@@ -563,7 +597,7 @@ attn_bwd_dkv_sm100_kernel(const float* __restrict__ q, const float* __restrict__
 
 // Dynamic shared memory: the tiles + 1 KB alignment slack, padded so that exactly as many CTAs fit an SM (227 KB) as
 // its 512 TMEM columns can serve -- a CTA that is resident but blocked in tcgen05.alloc would only hold shared memory.
-constexpr int SMEM_FWD = 56 * 1024;     // 4 per SM (actual need 32 KB + 1 KB + barriers)
+constexpr int SMEM_FWD = 44 * 1024;     // 4 per SM with the 1 KB per-CTA reserve (actual need 32 KB + 1 KB + barriers)
 constexpr int SMEM_BWD = 100 * 1024;    // 2 per SM (actual need 64 KB + 1 KB + barriers + per-column L, D)
 static_assert(FWD_TILE_BYTES + 1024 + 64 <= SMEM_FWD && RT * OPITCH * 4 <= FWD_TILE_BYTES, "forward shared memory");
 static_assert(BWD_TILE_BYTES + 1024 + BWD_EXTRA_BYTES + 64 <= SMEM_BWD && RT * OPITCH * 4 <= BWD_TILE_BYTES, "backward shared memory");
@@ -574,87 +608,15 @@ int set_attrs() {
   TVAE_CUDA(cudaFuncSetAttribute(attn_fwd_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD));
   TVAE_CUDA(cudaFuncSetAttribute(attn_bwd_dq_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BWD));
   TVAE_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BWD));
+  TVAE_CUDA(cudaFuncSetAttribute(attn_fwd_sm100_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  TVAE_CUDA(cudaFuncSetAttribute(attn_bwd_dq_sm100_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  TVAE_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_sm100_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   g_attr_once.mark();
   return 0;
 }
 
 
-// TEMPORARY: D[128 x 32] = A[128 x 64] * B[64 x 32], mode bit0: A from TMEM, bit1: B MN-major
-__global__ void __launch_bounds__(NT) dbg_mma_kernel(const float* A, const float* Bm, float* D, int mode, int lbo, int sbo) {
-  extern __shared__ uint8_t smraw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smraw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* sA = base;                 // 2 blocks [128 rows][128 B]
-  uint8_t* sBk = sA + 32768;          // 2 blocks [32 n][128 B]
-  uint8_t* sBmn = sBk + 8192;         // [64 k][128 B]
-  uint64_t* bar = reinterpret_cast<uint64_t*>(sBmn + 8192);
-  uint32_t* tptr = reinterpret_cast<uint32_t*>(bar + 1);
-  const int warp = threadIdx.x >> 5;
-  if (warp == 0) tmem_alloc(tptr, 128);
-  if (threadIdx.x == 0) { mbar_init(bar, 1); fence_mbar_init(); }
-  for (int i = threadIdx.x; i < 128 * 64; i += NT) {
-    const int r = i >> 6, kk = i & 63, blk = kk >> 5, d = kk & 31;
-    *reinterpret_cast<uint32_t*>(sA + blk * 16384 + r * 128 + ((((d >> 2) ^ (r & 7)) << 4) | ((d & 3) << 2))) = tf32_rna(A[i]);
-  }
-  for (int i = threadIdx.x; i < 64 * 32; i += NT) {
-    const int kk = i >> 5, n = i & 31;
-    const uint32_t val = tf32_rna(Bm[i]);
-    if (mode & 4) *reinterpret_cast<uint32_t*>(sBmn + kk * 128 + ((((n >> 3) ^ (kk & 3)) << 5) | ((n & 7) << 2))) = val;
-    else *reinterpret_cast<uint32_t*>(sBmn + kk * 128 + ((((n >> 2) ^ (kk & 7)) << 4) | ((n & 3) << 2))) = val;
-    const int blk = kk >> 5, d = kk & 31;
-    *reinterpret_cast<uint32_t*>(sBk + blk * 4096 + n * 128 + ((((d >> 2) ^ (n & 7)) << 4) | ((d & 3) << 2))) = val;
-  }
-  fence_proxy_async_smem();
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tptr;
-  const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
-  if (mode & 1) {
-    uint32_t a[64];
-    for (int c = 0; c < 64; ++c) a[c] = tf32_rna(A[threadIdx.x * 64 + c]);
-    tmem_st32(tlane, a);
-    tmem_st32(tlane + 32, a + 32);
-    tmem_st_wait();
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) {
-    tc_fence_after();
-    if (elect_one()) {
-      const uint32_t idesc = make_idesc_tf32(128, 32, 0, (mode >> 1) & 1);
-      for (int ks = 0; ks < 8; ++ks) {
-        const uint64_t db = (mode & 4) ? make_smem_desc_mn32(smem_u32(sBmn) + ks * 1024, lbo, sbo)
-                            : (mode & 2) ? make_smem_desc_sw128(smem_u32(sBmn) + ks * 1024, lbo, sbo)
-                                       : make_smem_desc_sw128(smem_u32(sBk) + (ks >> 2) * 4096 + (ks & 3) * 32, 16, 1024);
-        if (mode & 1) umma_tf32_ts(tmem + 64, tmem + ks * 8, db, idesc, ks > 0);
-        else umma_tf32_ss(tmem + 64, make_smem_desc_sw128(smem_u32(sA) + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024), db, idesc, ks > 0);
-      }
-      umma_commit(bar);
-    }
-    __syncwarp();
-  }
-  mbar_wait(bar, 0, 77);
-  tc_fence_after();
-  uint32_t o[32];
-  tmem_ld32(tlane + 64, o);
-  tmem_ld_wait();
-  for (int d = 0; d < 32; ++d) D[threadIdx.x * 32 + d] = __uint_as_float(o[d]);
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, 128);
-}
-
 }  // namespace
-}  // namespace tvae
-extern "C" int tvae_attn_debug_mma(const float* A, const float* B, float* D, int mode, int lbo, int sbo) {
-  cudaFuncSetAttribute(tvae::dbg_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-  tvae::dbg_mma_kernel<<<1, 128, 64 * 1024>>>(A, B, D, mode, lbo, sbo);
-  return (int)cudaDeviceSynchronize();
-}
-extern "C" int tvae_attn_debug_buffer(float* p) {
-  return (int)cudaMemcpyToSymbol(tvae::g_dbg, &p, sizeof(p));
-}
-namespace tvae {
 
 int attn_fwd_sm100(const float* q, const float* k, const float* v, int pitch, int B, int T, int heads, void* out_bf16,
                    float* out_f32, float* lse, cudaStream_t stream) {
