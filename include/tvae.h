@@ -115,6 +115,23 @@ int32_t tvae_wgrad_set_cta_pair(int32_t enable);
 int64_t tvae_wgrad_workspace_bytes(int32_t Cm, int32_t Cn, int32_t ntaps, int32_t splits);
 int32_t tvae_wgrad_splits(int32_t Cm, int32_t Cn, int32_t ntaps, int64_t pixels);
 
+/* Weight gradient of the last 1..4 channels of a wide, awkward channel count (1028 = 8 x 128 + 4: the input channels
+ * of encoder.conv_in, the output channels of decoder.conv_out; src/model.py:424-431, 634-640) for a 3x3 stride-1,
+ * zero-padded convolution -- the part of autograd's convolution_backward (weight) that tvae_wgrad_gemm would pay a
+ * whole padded 128-row tile for:
+ *   grad[c * stride_c + n * stride_n + tap] (+)= sum_pixels wide[pixel][n] * skinny[pixel + shift_sign * tap][c]
+ * wide: bf16 NHWC [N*H*W][wide_pitch], Cw channels (multiple of 64, <= 512); skinny: bf16 [N*H*W][skinny_pitch], Cs
+ * channels starting at the pointer. shift_sign = +1: the tap shifts the skinny operand (conv_in: wide = dY, skinny =
+ * x[..., 1024:], grad = dW[n][1024 + c][tap]: stride_c = 9, stride_n = 9 * Cin, grad pointer advanced by 9 * 1024);
+ * -1: it shifts the wide one (conv_out: wide = x, skinny = dY[..., 1024:], grad = dW[1024 + c][n][tap]: stride_c =
+ * 9 * Cin, stride_n = 9). The wide operand is read once (taps on the GEMM's M side), partial sums per CTA are added in
+ * fixed order (bit-reproducible). workspace: tvae_wgrad_skinny_workspace_bytes(Cw). */
+int64_t tvae_wgrad_skinny_workspace_bytes(int32_t Cw);
+int32_t tvae_wgrad_skinny(const void* wide_bf16, int32_t Cw, int32_t wide_pitch, const void* skinny_bf16, int32_t Cs,
+                          int32_t skinny_pitch, int32_t N, int32_t H, int32_t W, int32_t shift_sign, float* grad,
+                          int64_t stride_c, int64_t stride_n, int32_t accumulate, float* workspace,
+                          tvae_stream_t stream);
+
 /* out[(tr*Crow + cr)][tk*c_pad + c] = bf16(w[cr*s_row + c*s_col + (tr+tk)*s_tap]), zero for c in [C, c_pad).
  * One of TR, TK is 1. Row pitch of `out` is TK*c_pad. out_lo (optional, same layout) = bf16(w - out): the low-order
  * half for the split-bf16 "fp32 mode" (every *_lo argument below has the same meaning; NULL = not produced). */

@@ -72,6 +72,8 @@ def _load():
         "tvae_wgrad_set_cta_pair": (i32, [i32]),
         "tvae_wgrad_workspace_bytes": (i64, [i32, i32, i32, i32]),
         "tvae_wgrad_splits": (i32, [i32, i32, i32, i64]),
+        "tvae_wgrad_skinny_workspace_bytes": (i64, [i32]),
+        "tvae_wgrad_skinny": (i32, [vp, i32, i32, vp, i32, i32, i32, i32, i32, i32, vp, i64, i64, i32, vp, vp]),
         "tvae_pack_chunk_elems": (i32, []),
         "tvae_pack_weights_batched": (i32, [vp, vp, i32, i64, vp]),
         "tvae_pack_weight": (i32, [vp, vp, i32, i32, i32, i32, i32, i64, i64, i64, vp, vp]),

@@ -52,11 +52,11 @@ class _Engine:
         # every weight pack that an optimiser step made stale is rebuilt by ONE launch (TVAE_BATCHED_PACKING=0: one
         # launch per pack, on first use)
         self.batched_packing = os.environ.get("TVAE_BATCHED_PACKING", "1") != "0"
-        # 1028-channel weight gradients as a 1024-channel GEMM + a skinny 4-channel one (see conv_bwd). Measured (B=256,
-        # profiles/wgrad_split_r2.txt): the whole-tile part runs at 1,520-1,570 TFLOP/s instead of 1,180-1,250, but the
-        # skinny GEMM (4 channels on the N side, 16-column MMAs) is operand-bound and takes the 1.7 ms the padded 9th tile
-        # took; the step does not move (108.5 vs 108.5, 107.5 vs 109.1 ms). Off by default.
-        self.split_wide_wgrad = os.environ.get("TVAE_SPLIT_WIDE_WGRAD", "0") == "1"
+        # 1028-channel weight gradients as a 1024-channel tcgen05 GEMM (whole 128-row tiles: 1,520-1,570 TFLOP/s instead of
+        # 1,180-1,250 with the padded 9th tile) + the 4 leftover channels by tvae_wgrad_skinny (taps on the M side, the
+        # wide operand read once). Round-2 history: with the leftover as a 16-column tcgen05 GEMM the split bought nothing
+        # (operand-bound, 1.7 ms per launch; profiles/wgrad_split_r2.txt). TVAE_SPLIT_WIDE_WGRAD=0 restores the single GEMM.
+        self.split_wide_wgrad = os.environ.get("TVAE_SPLIT_WIDE_WGRAD", "1") != "0"
         self._packs = []
         # Weight packs are refreshed at the start of EVERY top-level forward (one batched launch, 0.34 ms): writes that
         # autograd cannot see (`p.data.copy_(ema)`, `nn.init.*_(p.data)`, weight surgery) are honoured like the
@@ -364,25 +364,26 @@ def conv_bwd(mod, dy_bf16, x_bf16, Cin, *, dgrad=None, dgrad_residual=None, bias
         def wg(dst, acc):
             if kind == 2:   # ConvTranspose2d [Cin][Cout][2][2]: P = x (coarse), Q = dy (fine)
                 ops.wgrad_gemm(x_bf16, Cin, dy_bf16, Cout, kind=1, R=2, grad=dst, accumulate=acc)
-            elif kind == 0 and ENGINE.split_wide_wgrad and Cin > 256 and 0 < Cin % 128 <= 16 and Cout % 128 == 0:
+            elif (kind == 0 and R == 3 and ENGINE.split_wide_wgrad and Cin > 256 and 0 < Cin % 128 <= 4
+                  and Cout % 64 == 0 and Cout <= 512):
                 # encoder.conv_in (1028 -> 512): 1028 = 8 x 128 + 4. A 9th 128-row tile for 4 channels is 97 % padding
                 # (a full MMA sweep, 1.3-1.8 ms per launch); instead the whole tiles run with x[:, :1024] on M and the 4
-                # leftover channels run as a skinny GEMM with THEM on the N side (16-column MMAs, 1/16 of the tensor work)
+                # leftover channels go through tvae_wgrad_skinny (dW[n][1024 + c][tap] = sum dY[px][n] x[px + tap][1024 + c])
                 main = Cin - Cin % 128
                 ops.wgrad_gemm(x_bf16[..., :main], main, dy_bf16, Cout, kind=0, R=R, grad=dst, flip=True, accumulate=acc,
                                grad_ld=Cin, grad_off=0)
-                ops.wgrad_gemm(dy_bf16, Cout, x_bf16[..., main:Cin], Cin - main, kind=0, R=R, grad=dst, accumulate=acc,
-                               grad_ld=Cin, grad_off=main)
-            elif kind == 0 and ENGINE.split_wide_wgrad and Cout > 256 and 0 < Cout % 128 <= 16 and Cin % 128 == 0:
+                ops.wgrad_skinny(dy_bf16, Cout, x_bf16[..., main:Cin], Cin - main, sign=+1, grad=dst.view(-1)[main * 9:],
+                                 stride_c=9, stride_n=9 * Cin, accumulate=acc)
+            elif (kind == 0 and R == 3 and ENGINE.split_wide_wgrad and Cout > 256 and 0 < Cout % 128 <= 4
+                  and Cin % 64 == 0 and Cin <= 512):
                 # decoder.conv_out (512 -> 1028): the same split on the output-channel side; both pieces are contiguous row
-                # blocks of the [Cout][Cin][3][3] parameter
+                # blocks of the [Cout][Cin][3][3] parameter (dW[1024 + c][n][tap] = sum x[px'][n] dY[px' - tap][1024 + c])
                 main = Cout - Cout % 128
-                taps = R * R
                 flat = dst.view(-1)
-                ops.wgrad_gemm(dy_bf16[..., :main], main, x_bf16, Cin, kind=0, R=R, grad=flat[:main * Cin * taps],
+                ops.wgrad_gemm(dy_bf16[..., :main], main, x_bf16, Cin, kind=0, R=R, grad=flat[:main * Cin * 9],
                                accumulate=acc)
-                ops.wgrad_gemm(x_bf16, Cin, dy_bf16[..., main:Cout], Cout - main, kind=0, R=R,
-                               grad=flat[main * Cin * taps:], flip=True, accumulate=acc)
+                ops.wgrad_skinny(x_bf16, Cin, dy_bf16[..., main:Cout], Cout - main, sign=-1, grad=flat[main * Cin * 9:],
+                                 stride_c=9 * Cin, stride_n=9, accumulate=acc)
             elif kind == 0 and Cin > 256 and Cin % 256 and Cout % 128 == 0:
                 # a wide, awkward channel count (1028) goes on the GEMM's M side: operand roles exchanged. (Measured:
                 # the opposite choice, N = 1028 as 5 tiles of 208, pads less (1.2 % vs 12 %) but is 3 ms per launch

@@ -77,7 +77,7 @@ def _timed(name, nbytes, call):
 _KERNELS_PER_CALL = {
     "tvae_pack_weight": 1, "tvae_pack_weights_batched": 1, "tvae_conv_gemm": 1, "tvae_wgrad_gemm": 2, "tvae_nchw_f32_to_nhwc_bf16": 1,
     "tvae_nhwc_f32_to_nchw_f32": 1, "tvae_nhwc_f32_to_nhwc_bf16": 1, "tvae_normalize_radiance": 1, "tvae_recon_metrics": 2, "tvae_nhwc_bf16_to_nchw_f32": 1, "tvae_f32_to_bf16": 1, "tvae_gn_stats": 1,
-    "tvae_gn_act_fwd": 1, "tvae_gn_stats_finalize": 1, "tvae_gn_act_bwd": 4, "tvae_colsum_bf16": 2, "tvae_attn_fwd": 1, "tvae_attn_bwd": 2, "tvae_attn_fwd_tc": 1, "tvae_attn_bwd_tc": 2,
+    "tvae_gn_act_fwd": 1, "tvae_gn_stats_finalize": 1, "tvae_gn_act_bwd": 4, "tvae_colsum_bf16": 2, "tvae_attn_fwd": 1, "tvae_attn_bwd": 2, "tvae_attn_fwd_tc": 1, "tvae_attn_bwd_tc": 2, "tvae_wgrad_skinny": 2,
     "tvae_reparam_fwd": 1, "tvae_reparam_bwd": 1, "tvae_nll_fwd": 2, "tvae_vae_loss_finalize": 1,
     "tvae_l2head_loss_fwd": 1, "tvae_l2head_loss_bwd": 1, "tvae_l2head_finalize": 1, "tvae_sumsq": 2, "tvae_adamw": 1,
     "tvae_gather_rows": 1, "tvae_extract_tiles": 1, "tvae_spectrum_stats_accum": 2, "tvae_spectrum_stats_finalize": 1,
@@ -534,6 +534,20 @@ def colsum_bf16(x, Cc, out):
     ws = _workspace(lib.tvae_colsum_workspace_bytes(rows, Cc), x.device, "colsum")
     check(lib.tvae_colsum_bf16(x.data_ptr(), rows, Cc, pitch_of(x), out.data_ptr(), ws.data_ptr(), _stream()),
           "tvae_colsum_bf16")
+
+
+@_on_device
+def wgrad_skinny(wide, Cw, skinny, Cs, *, sign, grad, stride_c, stride_n, accumulate=False):
+    """grad[c * stride_c + n * stride_n + tap] (+)= sum_pixels wide[pixel][n] * skinny[pixel + sign * tap][c] for a 3x3
+    stride-1 convolution: the weight gradient of <= 4 tail channels (1028 = 8 x 128 + 4) with the nine taps on the M side of
+    a 36 x Cw x pixels GEMM, so the wide operand is read once (tvae_wgrad_skinny). wide / skinny: bf16 [N,H,W,*] views."""
+    wide, skinny = hi_of(wide), hi_of(skinny)
+    N, H, W, _ = wide.shape
+    assert skinny.shape[:3] == wide.shape[:3] and grad.dtype == torch.float32 and grad.is_contiguous()
+    ws = _workspace(lib.tvae_wgrad_skinny_workspace_bytes(Cw), wide.device, "wgrad_skinny")
+    check(lib.tvae_wgrad_skinny(wide.data_ptr(), Cw, pitch_of(wide), skinny.data_ptr(), Cs, pitch_of(skinny), N, H, W,
+                                int(sign), grad.data_ptr(), int(stride_c), int(stride_n), int(accumulate), ws.data_ptr(),
+                                _stream()), "tvae_wgrad_skinny")
 
 
 # ----------------------------------------------------------------------------------------------- attention

@@ -349,6 +349,55 @@ def test_wgrad_sub_block_split_matches_single_gemm():
     assert torch.isfinite(got2).all() and rel_err(got2, ref2) < 1e-5
 
 
+@pytest.mark.parametrize("N,H,W,Cn,tail,accumulate", [(2, 16, 16, 128, 4, False), (3, 8, 24, 64, 3, True), (1, 64, 64, 512, 4, False),
+                                                      (2, 5, 7, 192, 1, False), (148, 16, 16, 256, 4, True)])
+def test_wgrad_skinny_tail_channels(N, H, W, Cn, tail, accumulate):
+    """tvae_wgrad_skinny (taps on the M side, wide operand read once) for the leftover channels of a 128 + tail channel
+    count, on the input-channel side (conv_in-like: inner-dimension offset) and the output-channel side (conv_out-like:
+    contiguous row block): against fp32 autograd of F.conv2d on the same bf16 operands, run-to-run bit-identical, and with
+    everything around the written block untouched. Ragged pixel counts (not a multiple of the 64-pixel chunk), non-square
+    images and more chunks than CTAs are covered."""
+    o = ops()
+    g = torch.Generator(device="cuda").manual_seed(N * 100 + tail)
+    Cw = 128 + tail
+    pitch = 136
+    xw = torch.randn((N, H, W, pitch), device="cuda", generator=g).to(torch.bfloat16)
+    dy = torch.randn((N, H, W, Cn), device="cuda", generator=g).to(torch.bfloat16)
+
+    def conv_wgrad(x_nhwc, dy_nhwc):      # weight gradient [Cout][Cin][3][3] of a 3x3 / pad 1 convolution, fp32
+        xx = x_nhwc.float().permute(0, 3, 1, 2)
+        w = torch.zeros((dy_nhwc.shape[-1], xx.shape[1], 3, 3), device="cuda", requires_grad=True)
+        torch.nn.functional.conv2d(xx, w, padding=1).backward(dy_nhwc.float().permute(0, 3, 1, 2))
+        return w.grad
+    with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+        ref_in = conv_wgrad(xw[..., :Cw], dy)                 # [Cn][Cw][3][3]
+        ref_out = conv_wgrad(dy, xw[..., :Cw])                # [Cw][Cn][3][3]: xw plays dY here, dy plays x
+    base = 0.5 if accumulate else float("nan")
+    # conv_in-like: the tail input channels of dW[n][128 + c][tap]
+    got = torch.full((Cn, Cw, 3, 3), base, device="cuda")
+    runs = []
+    for _ in range(2):
+        got.fill_(base)
+        o.wgrad_skinny(dy, Cn, xw[..., 128:Cw], tail, sign=+1, grad=got.view(-1)[128 * 9:], stride_c=9, stride_n=9 * Cw,
+                       accumulate=accumulate)
+        torch.cuda.synchronize()
+        runs.append(got.clone())
+    assert torch.equal(runs[0][:, 128:], runs[1][:, 128:])
+    want = ref_in[:, 128:] + (base if accumulate else 0.0)
+    assert rel_err(got[:, 128:], want) < 1e-4      # fp32 sums over up to 38 K pixels in two different orders
+    untouched = got[:, :128]
+    assert (untouched == base).all() if accumulate else torch.isnan(untouched).all()
+    # conv_out-like: the tail output channels dW[128 + c][n][tap]
+    got2 = torch.full((Cw, Cn, 3, 3), base, device="cuda")
+    o.wgrad_skinny(dy, Cn, xw[..., 128:Cw], tail, sign=-1, grad=got2.view(-1)[128 * Cn * 9:], stride_c=9 * Cn, stride_n=9,
+                   accumulate=accumulate)
+    torch.cuda.synchronize()
+    want2 = ref_out[128:] + (base if accumulate else 0.0)
+    assert rel_err(got2[128:], want2) < 1e-4
+    untouched = got2[:128]
+    assert (untouched == base).all() if accumulate else torch.isnan(untouched).all()
+
+
 @pytest.mark.parametrize("N,H,W,C,act,x_bf16", [(3, 16, 16, 128, 1, False), (2, 64, 64, 512, 1, True), (2, 8, 8, 256, 3, False),
                                                  (2, 16, 16, 128, 2, False)])
 def test_groupnorm_saved_activation_gradient(N, H, W, C, act, x_bf16):
