@@ -35,7 +35,7 @@ constexpr int PAIR_STAGES = 6;
 static_assert(PAIR_STAGES * PAIR_STAGE_BYTES == STAGES * STAGE_BYTES, "both variants use the same shared-memory budget");
 constexpr int NTHREADS = 320;                    // warp0: TMA, warp1: MMA + TMEM alloc, warps 2-9: epilogue
 constexpr int TMEM_COLS = 512;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*stats*/;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*stats*/ + 2048 /*bias*/;
 
 struct ConvMaps {
   CUtensorMap a[4];
@@ -98,6 +98,7 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float2* stat_sm = reinterpret_cast<float2*>(smem + STAGES * STAGE_BYTES + 256);   // [2 acc stages][4 warps][16 groups]
+  float* bias_sm = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256 + 1024);  // [2 acc stages][256 columns]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -287,6 +288,18 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
     uint32_t aphase = 0;
     for (int t = unit0; t < total_tiles; t += nunits) {
       const int mt = m_tile_of(t), nt = t % p.n_tiles;
+      int col0 = nt * p.bn;   // column in the (tap, cout) / cout space
+      const int tap = (!LEAN && p.up_mode) ? col0 / p.cout_per_tap : 0;
+      if (!LEAN && p.up_mode) col0 -= tap * p.cout_per_tap;
+      if (!LEAN && p.bias) {
+        // The tile's bias slice goes through shared memory, fetched while the MMAs of the tile are still running. (It
+        // used to be four __ldg per 16-column chunk issued right before their use: 14 % of all stall samples of the
+        // epilogue-bound K = 256 layers sat on that load.) Buffer `as` was last read two tiles ago, and every warp has
+        // passed the barrier of the tile in between since.
+        const int e = (warp - 2) * 32 + lane;
+        bias_sm[as * 256 + e] = (e < p.bn && col0 + e < p.n_valid) ? __ldg(p.bias + col0 + e) : 0.f;
+        asm volatile("bar.sync 2, 256;" ::: "memory");   // the 8 epilogue warps only
+      }
       mbar_wait(&tfull_bar[as], aphase, 4);
       tc_fence_after();
       const bool etr = TRACE && p.trace != nullptr && rank == 0 && warp == 2 && lane == 0;
@@ -296,11 +309,8 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
       }
       const long long pix = (long long)mt * BM + row;
       const bool row_ok = pix < p.m_total;
-      int col0 = nt * p.bn;   // column in the (tap, cout) / cout space
       long long opix = pix;
       if (!LEAN && p.up_mode) {
-        const int tap = col0 / p.cout_per_tap;
-        col0 -= tap * p.cout_per_tap;
         const int hw = p.up_H * p.up_W;
         const int n = (int)(pix / hw);
         const int rem = (int)(pix - (long long)n * hw);
@@ -310,6 +320,11 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * 256u;
       const bool do_stats = !LEAN && p.stats_part != nullptr;
       float st1 = 0.f, st2 = 0.f;
+      // group bookkeeping without a division per chunk (gs % 16 == 0 and a warp's chunk range starts on a group
+      // boundary or inside ONE group -- fused_stats_ok on the host side)
+      const int chunks_per_group = do_stats ? (p.gs >> 4) : 1;
+      int gslot = do_stats ? (cbeg << 4) / p.gs : 0;
+      int gchunk = do_stats ? cbeg - gslot * chunks_per_group : 0;
       const float* res_row = (!LEAN && p.res) ? p.res + opix * p.ld_res : nullptr;
 
       uint32_t r[16];
@@ -348,16 +363,12 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
         }
         if (row_ok && col < p.n_valid) {
           const bool full = (col + 16 <= p.n_valid);
-          if (p.bias) {
-            if (full) {
+          if (!LEAN && p.bias) {      // columns >= n_valid hold 0 in bias_sm
+            const float4* b4 = reinterpret_cast<const float4*>(bias_sm + as * 256 + c);
 #pragma unroll
-              for (int j = 0; j < 16; j += 4) {
-                const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + col + j));
-                v[j] += bb.x; v[j + 1] += bb.y; v[j + 2] += bb.z; v[j + 3] += bb.w;
-              }
-            } else {
-              for (int j = 0; j < 16; ++j)
-                if (col + j < p.n_valid) v[j] += __ldg(p.bias + col + j);
+            for (int j = 0; j < 4; ++j) {
+              const float4 bb = b4[j];
+              v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
             }
           }
           if (res_row) {
@@ -413,10 +424,12 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
             }
           }
         }
-        if (do_stats && ((c + 16) % p.gs) == 0) {   // a group's columns are complete: reduce over the warp's 32 rows
+        if (do_stats && ++gchunk == chunks_per_group) {   // a group's columns are complete: reduce over the warp's 32 rows
           const float w1 = warp_sum(st1), w2 = warp_sum(st2);
-          if (lane == 0) stat_sm[(as * 4 + q) * 16 + c / p.gs] = make_float2(w1, w2);
+          if (lane == 0) stat_sm[(as * 4 + q) * 16 + gslot] = make_float2(w1, w2);
           st1 = 0.f; st2 = 0.f;
+          gchunk = 0;
+          ++gslot;
         }
       }
       if (do_stats) {
