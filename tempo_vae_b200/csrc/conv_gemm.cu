@@ -291,7 +291,7 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
       int col0 = nt * p.bn;   // column in the (tap, cout) / cout space
       const int tap = (!LEAN && p.up_mode) ? col0 / p.cout_per_tap : 0;
       if (!LEAN && p.up_mode) col0 -= tap * p.cout_per_tap;
-      if (!LEAN && p.bias) {
+      if (p.bias) {
         // The tile's bias slice goes through shared memory, fetched while the MMAs of the tile are still running. (It
         // used to be four __ldg per 16-column chunk issued right before their use: 14 % of all stall samples of the
         // epilogue-bound K = 256 layers sat on that load.) Buffer `as` was last read two tiles ago, and every warp has
@@ -363,7 +363,7 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
         }
         if (row_ok && col < p.n_valid) {
           const bool full = (col + 16 <= p.n_valid);
-          if (!LEAN && p.bias) {      // columns >= n_valid hold 0 in bias_sm
+          if (p.bias) {      // columns >= n_valid hold 0 in bias_sm
             const float4* b4 = reinterpret_cast<const float4*>(bias_sm + as * 256 + c);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {

@@ -94,6 +94,11 @@ def test_conv_fwd(N, H, W, Cin, Cout, R):
     assert rel_err(got, ref) < 2e-3
     gotb = ob[..., :Cout].float().permute(0, 3, 1, 2)
     assert rel_err(gotb, ref) < 1e-2
+    # bf16-only output WITH a bias and nothing else: the LEAN epilogue instantiation on a forward layer (inference paths
+    # whose geometry rules out fused statistics take it; a dropped bias there once went unnoticed by this file)
+    _, ob2 = o.conv_gemm(xp, Cin, wp, kind=0, R=R, Cout=Cout, bias=b, want_f32=False, want_bf16=True)
+    torch.cuda.synchronize()
+    assert rel_err(ob2[..., :Cout].float().permute(0, 3, 1, 2), ref - res) < 1e-2
 
 
 @pytest.mark.usefixtures("conv_sched")
