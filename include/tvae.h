@@ -67,8 +67,23 @@ typedef struct {
   const void* x_lo;
   const void* w_lo;
   void* out_bf16_lo;
+  /* Optional fused reconstruction loss for decoder.conv_out under AutoencoderKL.get_loss (src/model.py:656-663): with
+   * nll_x = the target (bf16 NHWC [pixels][nll_x_pitch], Cout channels) the epilogue forms d = (conv + bias) - target
+   * straight from the fp32 accumulators, accumulates sum |d| (nll_loss_type 0, "l1") or sum d^2 (1, "l2") and sum d^2,
+   * and writes the loss gradient wrt the reconstruction, exp(-logvar) / nll_batch * sign(d) resp. * 2 d, as the bf16
+   * output (pad lanes up to out_bf16_pitch zeroed) -- the reconstruction itself never reaches HBM (4 B/element less
+   * written, and the separate pass of tvae_nll_fwd, 8 B/element, disappears). Requires kind 0, flip 0, out_bf16 only.
+   * nll_sums: double[3] like tvae_nll_fwd's; nll_workspace: tvae_conv_nll_workspace_bytes(pixels, Cout). NULL = off. */
+  const void* nll_x;
+  int32_t nll_x_pitch;
+  int32_t nll_loss_type;
+  const float* nll_logvar;
+  int32_t nll_batch;
+  float* nll_workspace;
+  double* nll_sums;
 } tvae_conv_args;
 int32_t tvae_conv_gemm(const tvae_conv_args* args, tvae_stream_t stream);
+int64_t tvae_conv_nll_workspace_bytes(int64_t pixels, int32_t Cout);
 /* Scheduling switch (results are bit-identical either way): 1 (default) runs tvae_conv_gemm as clusters of two CTAs
  * that share one 256-row tcgen05 MMA (cta_group::2, each SM stages half of the weight tile, a third less operand
  * traffic per SM); 0 runs one CTA per SM. Returns the previous setting. Process-wide; for A/B measurements and tests. */

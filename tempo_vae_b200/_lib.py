@@ -35,6 +35,13 @@ class ConvArgs(C.Structure):
         ("x_lo", C.c_void_p),
         ("w_lo", C.c_void_p),
         ("out_bf16_lo", C.c_void_p),
+        ("nll_x", C.c_void_p),
+        ("nll_x_pitch", C.c_int32),
+        ("nll_loss_type", C.c_int32),
+        ("nll_logvar", C.c_void_p),
+        ("nll_batch", C.c_int32),
+        ("nll_workspace", C.c_void_p),
+        ("nll_sums", C.c_void_p),
     ]
 
 
@@ -66,6 +73,7 @@ def _load():
         "tvae_last_error": (C.c_char_p, []),
         "tvae_abi_version": (i32, []),
         "tvae_conv_gemm": (i32, [C.POINTER(ConvArgs), vp]),
+        "tvae_conv_nll_workspace_bytes": (i64, [i64, i32]),
         "tvae_conv_set_cta_pair": (i32, [i32]),
         "tvae_conv_set_trace": (i32, [vp, i32]),
         "tvae_wgrad_gemm": (i32, [C.POINTER(WgradArgs), vp]),

@@ -66,6 +66,11 @@ struct ConvParams {
   float* stats_part;   // [slots][G][2], slot = m_tile (x4 + tap for the transposed conv); NULL = off
   int gs, G;           // group size (multiple of 16, divides BN), number of groups
   int split_chunk;     // first 16-column chunk handled by the second warp of each TMEM lane quarter
+  // fused reconstruction loss (decoder.conv_out under get_loss): the output never reaches HBM as fp32; see tvae_conv_args
+  const __nv_bfloat16* nll_x;
+  int nll_x_pitch, nll_l2, nll_batch;
+  const float* nll_logvar;
+  float* nll_part;     // [m_tile][n_tile][8 epilogue warps][2] = (sum of |d| or d^2, sum of d^2)
   int wide;            // bit 0/1/2: fp32 output / bf16 output / residual rows are 32-byte aligned => 256-bit accesses
   // optional per-tile timeline (tools/conv_trace.py): trace[(unit * trace_cap + tile) * 8 + j], SM clock cycles:
   // 0 MMA warp before the accumulator-free wait, 1 after it, 2 after the first operand stage arrived, 3 after the last
@@ -326,6 +331,10 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
       int gslot = do_stats ? (cbeg << 4) / p.gs : 0;
       int gchunk = do_stats ? cbeg - gslot * chunks_per_group : 0;
       const float* res_row = (!LEAN && p.res) ? p.res + opix * p.ld_res : nullptr;
+      const bool do_nll = !LEAN && p.nll_x != nullptr;
+      const __nv_bfloat16* x_row = do_nll ? p.nll_x + opix * p.nll_x_pitch : nullptr;
+      const float ngs = do_nll ? expf(-__ldg(p.nll_logvar)) / (float)p.nll_batch : 0.f;
+      float nrec = 0.f, nsq = 0.f;
 
       uint32_t r[16];
       float rs[16];
@@ -349,6 +358,11 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
       for (int ch = cbeg; ch < cend; ++ch) {
         const int c = ch << 4;
         const int col = col0 + c;
+        uint4 xq0 = make_uint4(0u, 0u, 0u, 0u), xq1 = xq0;
+        if (do_nll && row_ok && col + 16 <= p.n_valid) {      // the target's 16 values: in flight during the TMEM wait
+          xq0 = __ldg(reinterpret_cast<const uint4*>(x_row + col));
+          xq1 = __ldg(reinterpret_cast<const uint4*>(x_row + col + 8));
+        }
         tmem_ld_wait();
         float v[16];
 #pragma unroll
@@ -378,6 +392,33 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
             } else {
               for (int j = 0; j < 16; ++j)
                 if (col + j < p.n_valid) v[j] += res_row[col + j];
+            }
+          }
+          if (do_nll) {
+            // d = reconstruction - target; v becomes the loss gradient wrt the reconstruction (src/model.py:656-663)
+            float xv[16];
+            if (full) {
+              const uint32_t xw[8] = {xq0.x, xq0.y, xq0.z, xq0.w, xq1.x, xq1.y, xq1.z, xq1.w};
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                xv[2 * j] = bf16_bits_to_f(xw[j] & 0xffffu);
+                xv[2 * j + 1] = bf16_bits_to_f(xw[j] >> 16);
+              }
+            } else {
+              for (int j = 0; j < 16; ++j) xv[j] = (col + j < p.n_valid) ? __bfloat162float(x_row[col + j]) : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float d = (full || col + j < p.n_valid) ? v[j] - xv[j] : 0.f;
+              const float sq = d * d;
+              nsq += sq;
+              if (p.nll_l2) {
+                nrec += sq;
+                v[j] = 2.0f * d * ngs;
+              } else {
+                nrec += fabsf(d);
+                v[j] = (d > 0.f) ? ngs : ((d < 0.f) ? -ngs : 0.f);
+              }
             }
           }
           if (do_stats) {   // host guarantees full 16-column chunks (Cout % gs == 0, gs % 16 == 0)
@@ -414,8 +455,10 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
                 *reinterpret_cast<uint4*>(op + 8) = make_uint4(w8[4], w8[5], w8[6], w8[7]);
               }
             } else {
-              for (int j = 0; j < 16; ++j)
+              for (int j = 0; j < 16; ++j) {
                 if (col + j < p.n_valid) op[j] = __float2bfloat16(v[j]);
+                else if (do_nll && col + j < p.ld_bf16) op[j] = __float2bfloat16(0.f);   // pad lanes of the gradient rows
+              }
             }
             if (!LEAN && p.out_bf16_lo) {     // residual of the bf16 rounding, for split-bf16 consumers
               __nv_bfloat16* ol = p.out_bf16_lo + opix * p.ld_bf16 + col;
@@ -430,6 +473,13 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
           st1 = 0.f; st2 = 0.f;
           gchunk = 0;
           ++gslot;
+        }
+      }
+      if (do_nll) {
+        const float w1 = warp_sum(nrec), w2 = warp_sum(nsq);
+        if (lane == 0 && mt < p.m_tiles) {
+          float* dst = p.nll_part + (((long long)mt * p.n_tiles + nt) * 8 + (warp - 2)) * 2;
+          dst[0] = w1; dst[1] = w2;
         }
       }
       if (do_stats) {
@@ -482,6 +532,18 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
 // at 1.64 PFLOP/s (3.01 ms) against 1.1-1.2 PFLOP/s for the single-CTA schedule, which is then limited by the
 // 96 B/clk/SM of operand traffic that the pair schedule cuts to 64 B/clk/SM.
 int g_conv_cta_pair = 1;
+// sums[0] = sum of |d| (l1) or d^2 (l2), sums[1] = sum of d^2, sums[2] = 0: the layout tvae_nll_fwd produces; the
+// per-(tile, warp) fp32 partials are added in fixed order in fp64
+__global__ void __launch_bounds__(1024) conv_nll_final_kernel(const float* __restrict__ part, long long n,
+                                                              double* __restrict__ sums) {
+  __shared__ double red[32];
+  double a = 0.0, b = 0.0;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) { a += (double)part[2 * i]; b += (double)part[2 * i + 1]; }
+  const double t1 = block_sum(a, red);
+  const double t2 = block_sum(b, red);
+  if (threadIdx.x == 0) { sums[0] = t1; sums[1] = t2; sums[2] = 0.0; }
+}
+
 int g_conv_lean_epilogue = 1;
 unsigned long long* g_conv_trace = nullptr;
 int g_conv_trace_cap = 0;
@@ -637,6 +699,20 @@ extern "C" int32_t tvae_conv_gemm(const tvae_conv_args* a, cudaStream_t stream) 
   }
   p.out_f32 = a->out_f32; p.ld_f32 = a->out_f32_pitch;
   p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(a->out_bf16); p.ld_bf16 = a->out_bf16_pitch;
+  p.nll_x = reinterpret_cast<const __nv_bfloat16*>(a->nll_x);
+  if (p.nll_x) {
+    TVAE_CHECK(a->kind == 0 && !a->flip && p.out_bf16 && !p.out_f32 && !p.res && !p.stats_part && !a->out_bf16_lo && !split,
+               "tvae_conv_gemm: the fused reconstruction loss needs a stride-1 forward conv with the bf16 output only");
+    TVAE_CHECK(a->nll_logvar && a->nll_workspace && a->nll_sums && a->nll_batch > 0 && (a->nll_loss_type == 0 || a->nll_loss_type == 1),
+               "tvae_conv_gemm: incomplete nll_* arguments");
+    TVAE_CHECK(a->nll_x_pitch % 8 == 0 && (reinterpret_cast<uintptr_t>(a->nll_x) & 15) == 0 && a->nll_x_pitch >= a->Cout,
+               "tvae_conv_gemm: nll_x must be 16-byte aligned with a pitch that is a multiple of 8 and >= Cout");
+    p.nll_x_pitch = a->nll_x_pitch;
+    p.nll_l2 = a->nll_loss_type;
+    p.nll_batch = a->nll_batch;
+    p.nll_logvar = a->nll_logvar;
+    p.nll_part = a->nll_workspace;
+  }
   p.out_bf16_lo = reinterpret_cast<__nv_bfloat16*>(a->out_bf16_lo);
   TVAE_CHECK(!p.out_bf16_lo || p.out_bf16, "tvae_conv_gemm: out_bf16_lo needs out_bf16");
   p.bias = a->bias;
@@ -658,7 +734,7 @@ extern "C" int32_t tvae_conv_gemm(const tvae_conv_args* a, cudaStream_t stream) 
     }
   }
   const bool lean = g_conv_lean_epilogue && p.out_bf16 && !p.out_f32 && !p.res && !p.stats_part && !p.out_bf16_lo &&
-                    !p.up_mode;
+                    !p.up_mode && !p.nll_x;
   if (pair) {
     static PerDeviceOnce attr_set;
     if (attr_set.pending()) {
@@ -699,7 +775,16 @@ extern "C" int32_t tvae_conv_gemm(const tvae_conv_args* a, cudaStream_t stream) 
     else conv_gemm_kernel<false, false><<<grid, NTHREADS, SMEM_BYTES, stream>>>(maps, p);
   }
   TVAE_CUDA(cudaGetLastError());
+  if (p.nll_x) {
+    conv_nll_final_kernel<<<1, 1024, 0, stream>>>(p.nll_part, (long long)p.m_tiles * p.n_tiles * 8, a->nll_sums);
+    TVAE_CUDA(cudaGetLastError());
+  }
   return 0;
+}
+
+// upper bound for any N-tile choice: n_tiles <= ceil(Cout / 16)
+extern "C" int64_t tvae_conv_nll_workspace_bytes(int64_t pixels, int32_t Cout) {
+  return ((pixels + BM - 1) / BM) * (int64_t)((Cout + 15) / 16) * 8 * 2 * (int64_t)sizeof(float);
 }
 
 extern "C" int32_t tvae_conv_set_trace(void* device_buffer, int32_t tiles_per_unit) {

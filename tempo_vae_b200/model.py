@@ -48,6 +48,10 @@ class _Engine:
         # Measured on B200 (B=256, alternating runs): 116.0-117.1 ms vs 117.1-117.3 ms per step -- the board is
         # power-capped, so co-scheduling does not buy the time it would on an unconstrained part. Off by default.
         self.wgrad_overlap = os.environ.get("TVAE_WGRAD_OVERLAP", "0") == "1"
+        # ... but the SMALL layers (32x32 and 16x16 at B=256: ~35 weight-gradient GEMMs of 30-80 us each) are bound by
+        # launch latency and fixed per-kernel cost, not by power: those can hide behind the main stream's chain.
+        # TVAE_WGRAD_OVERLAP_MAX_PIXELS: overlap only GEMMs over at most this many pixels (0 = off).
+        self.wgrad_overlap_max_pixels = int(os.environ.get("TVAE_WGRAD_OVERLAP_MAX_PIXELS", "0"))
         self._side, self._main, self._side_busy = {}, {}, set()
         # every weight pack that an optimiser step made stale is rebuilt by ONE launch (TVAE_BATCHED_PACKING=0: one
         # launch per pack, on first use)
@@ -57,6 +61,10 @@ class _Engine:
         # wide operand read once). Round-2 history: with the leftover as a 16-column tcgen05 GEMM the split bought nothing
         # (operand-bound, 1.7 ms per launch; profiles/wgrad_split_r2.txt). TVAE_SPLIT_WIDE_WGRAD=0 restores the single GEMM.
         self.split_wide_wgrad = os.environ.get("TVAE_SPLIT_WIDE_WGRAD", "1") != "0"
+        # decoder.conv_out under get_loss(): the reconstruction loss, its sums and its gradient come out of the conv epilogue;
+        # the fp32 reconstruction is never written (4 B/element) and the separate loss pass (8 B/element, 1.7 ms per B=256
+        # step) disappears. TVAE_FUSE_NLL=0 restores conv -> tvae_nll_fwd.
+        self.fuse_nll = os.environ.get("TVAE_FUSE_NLL", "1") != "0"
         self._packs = []
         # Weight packs are refreshed at the start of EVERY top-level forward (one batched launch, 0.34 ms): writes that
         # autograd cannot see (`p.data.copy_(ema)`, `nn.init.*_(p.data)`, weight surgery) are honoured like the
@@ -391,7 +399,7 @@ def conv_bwd(mod, dy_bf16, x_bf16, Cin, *, dgrad=None, dgrad_residual=None, bias
                 ops.wgrad_gemm(x_bf16, Cin, dy_bf16, Cout, kind=0, R=R, grad=dst, flip=True, accumulate=acc)
             else:
                 ops.wgrad_gemm(dy_bf16, Cout, x_bf16, Cin, kind=kind, R=R, grad=dst, accumulate=acc)
-        if ENGINE.wgrad_overlap:
+        if ENGINE.wgrad_overlap or dy_bf16.numel() // dy_bf16.shape[-1] <= ENGINE.wgrad_overlap_max_pixels:
             side = ENGINE.side_stream(dy_bf16.device)
             with torch.cuda.stream(side):
                 _write_grad(w, wg, native_accumulate=True)
@@ -896,7 +904,7 @@ class Decoder(nn.Module):
         self.conv_out = get_conv(in_channels=ch_out, out_channels=self.in_channels, dim=self.dim, init=zero_init,
                                  **conv_params)
 
-    def fwd(self, z_bf16, save):
+    def fwd(self, z_bf16, save, nll=None):
         self.last_z_shape = (z_bf16.shape[0], self.z_channels, z_bf16.shape[1], z_bf16.shape[2])
         saved = {}
         r = conv_fwd(self.conv_in, z_bf16, self.z_channels, stats_for=self.mid1.net1[0])
@@ -915,6 +923,14 @@ class Decoder(nn.Module):
         saved["levels"] = levels
         a, st = norm_act_fwd(self.norm_out, h.f32, self.act_out.code, h.stats, save)
         saved["out"] = (h.f32, st, a) if save else None
+        if nll is not None:     # get_loss(): the loss and its gradient come out of this conv's epilogue (tvae_conv_args.nll_*)
+            Cout = self.conv_out.out_channels
+            kind, R = self.conv_out.conv_kind()
+            _, g = ops.conv_gemm(a, self.norm_out.num_channels, self.conv_out.packed("fwd"), kind=kind, R=R, Cout=Cout,
+                                 bias=self.conv_out.bias, want_f32=False, want_bf16=True, bf16_pitch=ops.round_up(Cout, 8),
+                                 nll=nll)
+            nll["dxhat"] = g
+            return A(C=self.in_channels), (saved if save else None)
         of, _ = conv_fwd(self.conv_out, a, self.norm_out.num_channels)
         return A(f32=of, C=self.in_channels), (saved if save else None)
 
@@ -1021,10 +1037,10 @@ class _DecodeProgram:
     def in_channels_api(self):
         return self.vae.post_quant_conv.in_channels
 
-    def program_fwd(self, zb, save):
+    def program_fwd(self, zb, save, nll=None):
         v = self.vae
         _, pq = conv_fwd(v.post_quant_conv, zb, v.post_quant_conv.in_channels, want_f32=False, want_bf16=True)
-        out, s = v.decoder.fwd(pq, save)
+        out, s = v.decoder.fwd(pq, save, nll=nll)
         return out, ((s, zb) if save else None)
 
     def program_bwd(self, gb, saved, need):
@@ -1060,9 +1076,16 @@ class _VAELossFn(torch.autograd.Function):
             z_bf16, _, eps_used, kl = ops.reparam_fwd(mom.f32, Z, seed=ENGINE.rng_seed, sample_offset=off)
         else:
             z_bf16, _, eps_used, kl = ops.reparam_fwd(mom.f32, Z, eps=eps)
-        xhat, dec_saved = dec.program_fwd(z_bf16, train)
         loss_type = 0 if vae.nll_loss_type == "l1" else 1
-        sums, dxhat = ops.nll_fwd(xb, xhat.f32, C, loss_type, vae.logvar.detach(), B, train)
+        if (ENGINE.fuse_nll and train and not extra.get("keep_xhat") and not ops.SPLIT_BF16[0]
+                and vae.decoder.conv_out.conv_kind()[0] == 0):
+            # training: loss sums and d loss / d reconstruction straight from decoder.conv_out's epilogue
+            nll = {"x": xb, "loss_type": loss_type, "logvar": vae.logvar.detach(), "batch": B}
+            xhat, dec_saved = dec.program_fwd(z_bf16, train, nll=nll)
+            sums, dxhat = nll["sums"], nll["dxhat"]
+        else:
+            xhat, dec_saved = dec.program_fwd(z_bf16, train)
+            sums, dxhat = ops.nll_fwd(xb, xhat.f32, C, loss_type, vae.logvar.detach(), B, train)
         n_elem = float(x.numel())
         scal = ops.vae_loss_finalize(sums, kl, vae.logvar.detach(), n_elem, vae.kl_weight)
         # optional L2-product supervision on a SECOND posterior sample (src/model_with_l2.py:124-168)

@@ -257,10 +257,12 @@ def fused_stats_ok(N, oH, oW, Cout, G, kind, H, W):
 
 @_on_device
 def conv_gemm(x, C_in, wp, *, kind, R, Cout, flip=False, bias=None, residual=None, want_f32=True, want_bf16=False,
-              bf16_pitch=None, bn=0, out_f32=None, out_bf16=None, stats=None, split_out=True):
+              bf16_pitch=None, bn=0, out_f32=None, out_bf16=None, stats=None, split_out=True, nll=None):
     """x: bf16 [N,H,W,pitch]. Returns (out_f32 or None, out_bf16 or None) as NHWC tensors; with stats=(G, eps) the
     GroupNorm statistics [N, G, 2] of the output are produced by the epilogue and returned as a third value
-    (None when the geometry does not allow it)."""
+    (None when the geometry does not allow it). nll = {"x": target bf16 NHWC, "loss_type", "logvar", "batch"}: the fused
+    reconstruction loss of tvae_conv_args.nll_* -- the bf16 output is then the loss gradient wrt the reconstruction and
+    nll["sums"] receives the fp64[3] sums of tvae_nll_fwd."""
     x_lo = x.lo if isinstance(x, Pair) else None
     x = hi_of(x)
     N, H, W, _ = x.shape
@@ -295,6 +297,16 @@ def conv_gemm(x, C_in, wp, *, kind, R, Cout, flip=False, bias=None, residual=Non
     if out_bf16 is not None and SPLIT_BF16[0] and want_bf16 and split_out:
         out_lo = torch.empty_like(out_bf16)
         a.out_bf16_lo = out_lo.data_ptr()
+    if nll is not None:
+        tgt = hi_of(nll["x"])
+        assert kind == 0 and not flip and out_f32 is None and out_bf16 is not None and residual is None and stats is None
+        assert tgt.shape[:3] == (N, oH, oW)
+        nll["sums"] = torch.empty((3,), dtype=torch.float64, device=dev)
+        nws = _workspace(lib.tvae_conv_nll_workspace_bytes(N * oH * oW, Cout), dev, "conv_nll")
+        a.nll_x, a.nll_x_pitch = tgt.data_ptr(), pitch_of(tgt)
+        a.nll_loss_type, a.nll_logvar, a.nll_batch = int(nll["loss_type"]), nll["logvar"].data_ptr(), int(nll["batch"])
+        a.nll_workspace, a.nll_sums = nws.data_ptr(), nll["sums"].data_ptr()
+        KERNEL_LAUNCHES[0] += 1
     part = None
     if stats is not None and fused_stats_ok(N, oH, oW, Cout, stats[0], kind, H, W):
         grid_px = (H * W) if kind == 2 else (oH * oW)
@@ -326,10 +338,15 @@ _wgrad_ws = {}
 
 
 def _workspace(nbytes, device, key="ws"):
-    """Grow-only scratch buffer per (device, key); stream-ordered reuse on the current stream."""
-    k = (device, key)
+    """Grow-only scratch buffer per (device, key, stream): reuse is ordered by the stream it is used on, so kernels on
+    different streams (weight gradients on the side stream) must not share one. A replaced (too small) buffer may still
+    be in use by kernels already enqueued: the caching allocator is told which stream that is."""
+    stream = torch.cuda.current_stream(device)
+    k = (device, key, stream.cuda_stream)
     buf = _wgrad_ws.get(k)
     if buf is None or buf.numel() < nbytes:
+        if buf is not None:
+            buf.record_stream(stream)
         buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
         _wgrad_ws[k] = buf
     return buf

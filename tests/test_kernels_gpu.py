@@ -102,6 +102,37 @@ def test_conv_fwd(N, H, W, Cin, Cout, R):
 
 
 @pytest.mark.usefixtures("conv_sched")
+@pytest.mark.parametrize("N,H,W,Cin,Cout,loss_type", [(2, 16, 16, 64, 132, 0), (3, 16, 16, 64, 132, 1), (2, 64, 64, 128, 1028, 0),
+                                                       (3, 8, 8, 64, 48, 0)])
+def test_conv_fused_reconstruction_loss(N, H, W, Cin, Cout, loss_type):
+    """tvae_conv_args.nll_*: decoder.conv_out with the reconstruction loss in its epilogue (sums + the gradient wrt the
+    reconstruction as the bf16 output, pad lanes zeroed) against conv -> fp32 -> tvae_nll_fwd on the same operands. The
+    gradient must be IDENTICAL (same fp32 d = conv + bias - target in both paths); the sums differ only by summation order.
+    Ragged channel counts (132, 1028 = 4 x 208 + 196, 48) and a ragged last pixel tile are covered."""
+    o = ops()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = bf16_round(torch.randn((N, Cin, H, W), device="cuda", generator=g))
+    w = bf16_round(torch.randn((Cout, Cin, 3, 3), device="cuda", generator=g) / math.sqrt(Cin * 9))
+    b = torch.randn((Cout,), device="cuda", generator=g)
+    xp = nhwc_bf16(x, o.round_up(Cin, 8))
+    wp = o.pack_weight(w, "fwd")
+    pitch = o.round_up(Cout, 8)
+    target = torch.randn((N, H, W, pitch), device="cuda", generator=g).to(torch.bfloat16)
+    logvar = torch.tensor([0.3], device="cuda")
+    of, _ = o.conv_gemm(xp, Cin, wp, kind=0, R=3, Cout=Cout, bias=b, want_f32=True)
+    sums_ref, dx_ref = o.nll_fwd(target[..., :Cout], of, Cout, loss_type, logvar, N, True)
+    nll = {"x": target[..., :Cout], "loss_type": loss_type, "logvar": logvar, "batch": N}
+    out = torch.full((N, H, W, pitch), float("nan"), device="cuda", dtype=torch.bfloat16)
+    _, dx = o.conv_gemm(xp, Cin, wp, kind=0, R=3, Cout=Cout, bias=b, want_f32=False, want_bf16=True, out_bf16=out, nll=nll)
+    torch.cuda.synchronize()
+    assert dx.shape == dx_ref.shape and torch.equal(dx[..., :Cout], dx_ref[..., :Cout])
+    assert (dx[..., Cout:] == 0).all()
+    rel = ((nll["sums"] - sums_ref).abs() / sums_ref.abs().clamp_min(1e-30)).max().item()
+    assert rel < 1e-6, (nll["sums"], sums_ref)
+    assert float(nll["sums"][2]) == 0.0
+
+
+@pytest.mark.usefixtures("conv_sched")
 @pytest.mark.parametrize("N,H,W,Cin,Cout,R", [(2, 16, 16, 64, 128, 3), (2, 32, 32, 256, 512, 3), (1, 64, 64, 1028, 512, 3),
                                                (2, 16, 16, 128, 128, 1)])
 def test_conv_dgrad(N, H, W, Cin, Cout, R):

@@ -151,7 +151,7 @@ def test_struct_layouts_match_header_order():
             decl = decl.replace("typedef struct {", "").strip()
             if not decl:
                 continue
-            decl = re.sub(r"^(const\s+)?(void|float|int32_t|int64_t)\s*\*?", "", decl).strip()
+            decl = re.sub(r"^(const\s+)?(void|float|double|int32_t|int64_t)\s*\*?", "", decl).strip()
             names += [n.strip().lstrip("*") for n in decl.split(",")]
         assert names == [f[0] for f in cls._fields_], struct
 
