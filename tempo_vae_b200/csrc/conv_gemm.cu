@@ -533,14 +533,28 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
 // 96 B/clk/SM of operand traffic that the pair schedule cuts to 64 B/clk/SM.
 int g_conv_cta_pair = 1;
 // sums[0] = sum of |d| (l1) or d^2 (l2), sums[1] = sum of d^2, sums[2] = 0: the layout tvae_nll_fwd produces; the
-// per-(tile, warp) fp32 partials are added in fixed order in fp64
-__global__ void __launch_bounds__(1024) conv_nll_final_kernel(const float* __restrict__ part, long long n,
-                                                              double* __restrict__ sums) {
+// per-(tile, warp) fp32 partials are added in a fixed order in fp64, in two stages (128 slices, then the slices): one
+// block walking all 327,680 pairs of the B=256 step took 60 us on the critical path.
+constexpr int NLL_SLICES = 128;
+__global__ void __launch_bounds__(256) conv_nll_slice_kernel(const float* __restrict__ part, long long n,
+                                                             double* __restrict__ slices) {
   __shared__ double red[32];
+  const long long per = (n + NLL_SLICES - 1) / NLL_SLICES;
+  const long long i0 = blockIdx.x * per, i1 = min(i0 + per, n);
   double a = 0.0, b = 0.0;
-  for (long long i = threadIdx.x; i < n; i += blockDim.x) { a += (double)part[2 * i]; b += (double)part[2 * i + 1]; }
+  for (long long i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+    const float2 v = *reinterpret_cast<const float2*>(part + 2 * i);
+    a += (double)v.x; b += (double)v.y;
+  }
   const double t1 = block_sum(a, red);
   const double t2 = block_sum(b, red);
+  if (threadIdx.x == 0) { slices[2 * blockIdx.x] = t1; slices[2 * blockIdx.x + 1] = t2; }
+}
+__global__ void __launch_bounds__(NLL_SLICES) conv_nll_final_kernel(const double* __restrict__ slices,
+                                                                    double* __restrict__ sums) {
+  __shared__ double red[32];
+  const double t1 = block_sum(slices[2 * threadIdx.x], red);
+  const double t2 = block_sum(slices[2 * threadIdx.x + 1], red);
   if (threadIdx.x == 0) { sums[0] = t1; sums[1] = t2; sums[2] = 0.0; }
 }
 
@@ -776,7 +790,10 @@ extern "C" int32_t tvae_conv_gemm(const tvae_conv_args* a, cudaStream_t stream) 
   }
   TVAE_CUDA(cudaGetLastError());
   if (p.nll_x) {
-    conv_nll_final_kernel<<<1, 1024, 0, stream>>>(p.nll_part, (long long)p.m_tiles * p.n_tiles * 8, a->nll_sums);
+    const long long npairs = (long long)p.m_tiles * p.n_tiles * 8;
+    double* slices = reinterpret_cast<double*>(p.nll_part + ((2 * npairs + 3) & ~3ll));   // 16-byte aligned tail
+    conv_nll_slice_kernel<<<NLL_SLICES, 256, 0, stream>>>(p.nll_part, npairs, slices);
+    conv_nll_final_kernel<<<1, NLL_SLICES, 0, stream>>>(slices, a->nll_sums);
     TVAE_CUDA(cudaGetLastError());
   }
   return 0;
@@ -784,7 +801,8 @@ extern "C" int32_t tvae_conv_gemm(const tvae_conv_args* a, cudaStream_t stream) 
 
 // upper bound for any N-tile choice: n_tiles <= ceil(Cout / 16)
 extern "C" int64_t tvae_conv_nll_workspace_bytes(int64_t pixels, int32_t Cout) {
-  return ((pixels + BM - 1) / BM) * (int64_t)((Cout + 15) / 16) * 8 * 2 * (int64_t)sizeof(float);
+  return ((pixels + BM - 1) / BM) * (int64_t)((Cout + 15) / 16) * 8 * 2 * (int64_t)sizeof(float) + 16 +
+         2 * NLL_SLICES * (int64_t)sizeof(double);
 }
 
 extern "C" int32_t tvae_conv_set_trace(void* device_buffer, int32_t tiles_per_unit) {
