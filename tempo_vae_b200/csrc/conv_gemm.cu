@@ -305,13 +305,6 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
         bias_sm[as * 256 + e] = (e < p.bn && col0 + e < p.n_valid) ? __ldg(p.bias + col0 + e) : 0.f;
         asm volatile("bar.sync 2, 256;" ::: "memory");   // the 8 epilogue warps only
       }
-      mbar_wait(&tfull_bar[as], aphase, 4);
-      tc_fence_after();
-      const bool etr = TRACE && p.trace != nullptr && rank == 0 && warp == 2 && lane == 0;
-      if (etr) {
-        const int ti = (t - unit0) / nunits;
-        if (ti < p.trace_cap) p.trace[((long long)unit0 * p.trace_cap + ti) * 8 + 5] = (unsigned long long)clock64();
-      }
       const long long pix = (long long)mt * BM + row;
       const bool row_ok = pix < p.m_total;
       long long opix = pix;
@@ -321,6 +314,13 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
         const int rem = (int)(pix - (long long)n * hw);
         const int h = rem / p.up_W, w = rem - h * p.up_W;
         opix = ((long long)n * (2 * p.up_H) + (2 * h + (tap >> 1))) * (2 * p.up_W) + (2 * w + (tap & 1));
+      }
+      mbar_wait(&tfull_bar[as], aphase, 4);
+      tc_fence_after();
+      const bool etr = TRACE && p.trace != nullptr && rank == 0 && warp == 2 && lane == 0;
+      if (etr) {
+        const int ti = (t - unit0) / nunits;
+        if (ti < p.trace_cap) p.trace[((long long)unit0 * p.trace_cap + ti) * 8 + 5] = (unsigned long long)clock64();
       }
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * 256u;
       const bool do_stats = !LEAN && p.stats_part != nullptr;
@@ -334,6 +334,7 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
       const bool do_nll = !LEAN && p.nll_x != nullptr;
       const __nv_bfloat16* x_row = do_nll ? p.nll_x + opix * p.nll_x_pitch : nullptr;
       const float ngs = do_nll ? expf(-__ldg(p.nll_logvar)) / (float)p.nll_batch : 0.f;
+      const uint32_t ngs_pair = pack_bf16(ngs, ngs);
       float nrec = 0.f, nsq = 0.f;
 
       uint32_t r[16];
@@ -350,19 +351,21 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
           }
         }
       };
+      uint4 xn0 = make_uint4(0u, 0u, 0u, 0u), xn1 = xn0;
+      auto load_target = [&](int col) {
+        xn0 = __ldg(reinterpret_cast<const uint4*>(x_row + col));
+        xn1 = __ldg(reinterpret_cast<const uint4*>(x_row + col + 8));
+      };
       if (cbeg < cend) {                                    // prologue: first chunk in flight
         tmem_ld16(taddr + (uint32_t)(cbeg << 4), r);
         const int col = col0 + (cbeg << 4);
         if (res_row && row_ok && col + 16 <= p.n_valid) load_res(col);
+        if (do_nll && row_ok && col + 16 <= p.n_valid) load_target(col);
       }
       for (int ch = cbeg; ch < cend; ++ch) {
         const int c = ch << 4;
         const int col = col0 + c;
-        uint4 xq0 = make_uint4(0u, 0u, 0u, 0u), xq1 = xq0;
-        if (do_nll && row_ok && col + 16 <= p.n_valid) {      // the target's 16 values: in flight during the TMEM wait
-          xq0 = __ldg(reinterpret_cast<const uint4*>(x_row + col));
-          xq1 = __ldg(reinterpret_cast<const uint4*>(x_row + col + 8));
-        }
+        const uint4 xq0 = xn0, xq1 = xn1;      // the loss target's 16 values of this chunk (loaded one chunk ahead)
         tmem_ld_wait();
         float v[16];
 #pragma unroll
@@ -374,6 +377,7 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
           tmem_ld16(taddr + (uint32_t)(c + 16), r);
           const int ncol = col + 16;
           if (res_row && row_ok && ncol + 16 <= p.n_valid) load_res(ncol);
+          if (do_nll && row_ok && ncol + 16 <= p.n_valid) load_target(ncol);
         }
         if (row_ok && col < p.n_valid) {
           const bool full = (col + 16 <= p.n_valid);
@@ -395,29 +399,62 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
             }
           }
           if (do_nll) {
-            // d = reconstruction - target; v becomes the loss gradient wrt the reconstruction (src/model.py:656-663)
-            float xv[16];
+            // d = reconstruction - target; the bf16 output is the loss gradient wrt the reconstruction
+            // (src/model.py:656-663), written right here. Kept lean on purpose: in the first version this block doubled
+            // the epilogue's instruction count (both loss types evaluated and selected per element, a bounds predicate
+            // per element, a two-compare sign) and the tensor pipe of decoder.conv_out dropped from 90 % to 83 %.
+            __nv_bfloat16* op = p.out_bf16 + opix * p.ld_bf16 + col;
             if (full) {
               const uint32_t xw[8] = {xq0.x, xq0.y, xq0.z, xq0.w, xq1.x, xq1.y, xq1.z, xq1.w};
+              uint32_t w8[8];
+              if (!p.nll_l2) {
+                // l1: the gradient is +-g or 0, g = exp(-logvar) / batch. The packed bf16 pair is |g| with the sign bits
+                // of the two differences OR'ed in (one PRMT + one LOP3 per pair, no float->bf16 conversion); an exact
+                // zero difference (gradient 0, as torch.sign gives) is patched on a rarely taken path.
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                xv[2 * j] = bf16_bits_to_f(xw[j] & 0xffffu);
-                xv[2 * j + 1] = bf16_bits_to_f(xw[j] >> 16);
-              }
-            } else {
-              for (int j = 0; j < 16; ++j) xv[j] = (col + j < p.n_valid) ? __bfloat162float(x_row[col + j]) : 0.f;
-            }
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float d = (full || col + j < p.n_valid) ? v[j] - xv[j] : 0.f;
-              const float sq = d * d;
-              nsq += sq;
-              if (p.nll_l2) {
-                nrec += sq;
-                v[j] = 2.0f * d * ngs;
+                for (int j = 0; j < 8; ++j) {
+                  const float d0 = v[2 * j] - bf16_bits_to_f(xw[j] & 0xffffu);
+                  const float d1 = v[2 * j + 1] - bf16_bits_to_f(xw[j] >> 16);
+                  nsq = fmaf(d0, d0, nsq);
+                  nsq = fmaf(d1, d1, nsq);
+                  nrec += fabsf(d0);
+                  nrec += fabsf(d1);
+                  uint32_t w = (__byte_perm(__float_as_uint(d0), __float_as_uint(d1), 0x7030) & 0x80008000u) | ngs_pair;
+                  if (d0 * d1 == 0.f) {
+                    if (d0 == 0.f) w &= 0xffff0000u;
+                    if (d1 == 0.f) w &= 0x0000ffffu;
+                  }
+                  w8[j] = w;
+                }
               } else {
-                nrec += fabsf(d);
-                v[j] = (d > 0.f) ? ngs : ((d < 0.f) ? -ngs : 0.f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float d0 = v[2 * j] - bf16_bits_to_f(xw[j] & 0xffffu);
+                  const float d1 = v[2 * j + 1] - bf16_bits_to_f(xw[j] >> 16);
+                  const float q0 = d0 * d0, q1 = d1 * d1;
+                  nsq += q0; nsq += q1;
+                  nrec += q0; nrec += q1;
+                  w8[j] = pack_bf16(2.0f * d0 * ngs, 2.0f * d1 * ngs);
+                }
+              }
+              if (p.wide & 2) {
+                st_global_v8_b32(op, w8);
+              } else {
+                *reinterpret_cast<uint4*>(op) = make_uint4(w8[0], w8[1], w8[2], w8[3]);
+                *reinterpret_cast<uint4*>(op + 8) = make_uint4(w8[4], w8[5], w8[6], w8[7]);
+              }
+            } else {                          // the ragged last chunk of the channel range (1028 = 64 x 16 + 4)
+              for (int j = 0; j < 16; ++j) {
+                if (col + j < p.n_valid) {
+                  const float d = v[j] - __bfloat162float(x_row[col + j]);
+                  const float sq = d * d;
+                  nsq += sq;
+                  nrec += p.nll_l2 ? sq : fabsf(d);
+                  const float gj = p.nll_l2 ? 2.0f * d * ngs : ((d > 0.f) ? ngs : ((d < 0.f) ? -ngs : 0.f));
+                  op[j] = __float2bfloat16(gj);
+                } else if (col + j < p.ld_bf16) {
+                  op[j] = __float2bfloat16(0.f);            // pad lanes of the gradient rows
+                }
               }
             }
           }
@@ -442,7 +479,7 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
                 if (col + j < p.n_valid) op[j] = v[j];
             }
           }
-          if (LEAN || p.out_bf16) {
+          if (LEAN || (p.out_bf16 && !do_nll)) {
             __nv_bfloat16* op = p.out_bf16 + opix * p.ld_bf16 + col;
             if (full) {
               uint32_t w8[8];
@@ -455,10 +492,8 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
                 *reinterpret_cast<uint4*>(op + 8) = make_uint4(w8[4], w8[5], w8[6], w8[7]);
               }
             } else {
-              for (int j = 0; j < 16; ++j) {
+              for (int j = 0; j < 16; ++j)
                 if (col + j < p.n_valid) op[j] = __float2bfloat16(v[j]);
-                else if (do_nll && col + j < p.ld_bf16) op[j] = __float2bfloat16(0.f);   // pad lanes of the gradient rows
-              }
             }
             if (!LEAN && p.out_bf16_lo) {     // residual of the bf16 rounding, for split-bf16 consumers
               __nv_bfloat16* ol = p.out_bf16_lo + opix * p.ld_bf16 + col;

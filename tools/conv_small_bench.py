@@ -59,3 +59,22 @@ if which in ("all", "1x1"):
           fl, B * 4096 * 512 * 4)
     timed("1x1 256->512 @64, bf16", lambda: o.conv_gemm(x, 256, wp, kind=0, R=1, Cout=512, bias=bias, want_f32=False,
                                                        want_bf16=True), fl, B * 4096 * 512 * 2)
+if which in ("all", "nll"):
+    # decoder.conv_out: 512 -> 1028 3x3 @64, fp32 output vs the fused reconstruction-loss epilogue (bf16 gradient out)
+    x = torch.randn((B, 64, 64, 512), device="cuda", generator=g).to(torch.bfloat16)
+    w = torch.randn((1028, 512, 3, 3), device="cuda", generator=g) / math.sqrt(4608)
+    bias = torch.randn((1028,), device="cuda", generator=g)
+    wp = o.pack_weight(w, "fwd")
+    target = torch.randn((B, 64, 64, 1032), device="cuda", generator=g).to(torch.bfloat16)
+    logvar = torch.zeros((1,), device="cuda")
+    out = torch.empty((B, 64, 64, 1032), device="cuda", dtype=torch.bfloat16)
+    of32 = torch.empty((B, 64, 64, 1028), device="cuda", dtype=torch.float32)
+    fl = 2.0 * B * 4096 * 1028 * 4608
+    for rep in range(2):
+        timed("conv_out 512->1028, f32", lambda: o.conv_gemm(x, 512, wp, kind=0, R=3, Cout=1028, bias=bias, want_f32=True,
+                                                             out_f32=of32), fl, B * 4096 * 1028 * 4)
+        timed("conv_out 512->1028, bf16", lambda: o.conv_gemm(x, 512, wp, kind=0, R=3, Cout=1028, bias=bias, want_f32=False,
+                                                              want_bf16=True, out_bf16=out), fl, B * 4096 * 1028 * 2)
+        timed("conv_out 512->1028, fused loss", lambda: o.conv_gemm(
+            x, 512, wp, kind=0, R=3, Cout=1028, bias=bias, want_f32=False, want_bf16=True, out_bf16=out,
+            nll={"x": target[..., :1028], "loss_type": 0, "logvar": logvar, "batch": B}), fl, B * 4096 * 1028 * 4)
