@@ -58,10 +58,10 @@ TINY_MODEL = dict(
 )
 FWD_GF, BWD_GF = 165.776, 292.746          # algorithmic conv GFLOP / sample
 REF_BATCH = 8                              # BASELINE config 1: the reference's CPU-runnable case
-# dram bytes of one 512->512 3x3 @64x64 launch at B=256 from the committed ncu capture (profiles/ncu_gemm_r1.md,
-# launch 1: 1.084 GB read + 2.104 GB written; the launch reads a 1.07 GB bf16 activation + 4.7 MB of weights and
+# dram bytes of one 512->512 3x3 @64x64 launch at B=256 from the committed ncu capture (profiles/ncu_gemm_r2.md, end of
+# round 2, launch 1: 1.089 GB read + 2.105 GB written; the launch reads a 1.07 GB bf16 activation + 4.7 MB of weights and
 # writes a 2.15 GB fp32 tensor)
-NCU_CONV_TRAFFIC_BYTES = 3.188e9
+NCU_CONV_TRAFFIC_BYTES = 3.194e9
 WORKLOAD = ("default TEMPO-VAE train step (configs/training/train_vae_default.yaml model), synthetic patches "
             "[1028,64,64] clamp(N(0,1),-10,10), random-init weights")
 
@@ -628,7 +628,7 @@ def run_ours(args):
                      "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
                      "traffic": NCU_CONV_TRAFFIC_BYTES if B == 256 else None,
                      "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch "
-                                       "(profiles/ncu_gemm_r1.md); algorithmic bytes per launch 3.22e9",
+                                       "(profiles/ncu_gemm_r2.md, end-of-round capture); algorithmic bytes per launch 3.22e9",
                      "peak_source": pk["source"] + ", bf16_tflops_sustained (cuBLAS back to back for 4 s: the figure "
                                     "for a kernel timed inside a long step)",
                      "frac_of_burst_peak": achieved / pk["burst"], "burst_peak": pk["burst"],
