@@ -78,3 +78,18 @@ if which in ("all", "nll"):
         timed("conv_out 512->1028, fused loss", lambda: o.conv_gemm(
             x, 512, wp, kind=0, R=3, Cout=1028, bias=bias, want_f32=False, want_bf16=True, out_bf16=out,
             nll={"x": target[..., :1028], "loss_type": 0, "logvar": logvar, "batch": B}), fl, B * 4096 * 1028 * 4)
+if which in ("nll1024",):
+    # what would decoder.conv_out cost with whole 256-column tiles only (1024 of the 1028 output channels)?
+    x = torch.randn((B, 64, 64, 512), device="cuda", generator=g).to(torch.bfloat16)
+    w = torch.randn((1028, 512, 3, 3), device="cuda", generator=g) / math.sqrt(4608)
+    bias = torch.randn((1028,), device="cuda", generator=g)
+    wp = o.pack_weight(w, "fwd")
+    target = torch.randn((B, 64, 64, 1032), device="cuda", generator=g).to(torch.bfloat16)
+    logvar = torch.zeros((1,), device="cuda")
+    out = torch.empty((B, 64, 64, 1032), device="cuda", dtype=torch.bfloat16)
+    for rep in range(3):
+        for Cout in (1028, 1024):
+            fl = 2.0 * B * 4096 * Cout * 4608
+            timed(f"conv_out 512->{Cout}, fused loss", lambda: o.conv_gemm(
+                x, 512, wp, kind=0, R=3, Cout=Cout, bias=bias, want_f32=False, want_bf16=True, out_bf16=out,
+                nll={"x": target[..., :Cout], "loss_type": 0, "logvar": logvar, "batch": B}), fl, B * 4096 * Cout * 4)
