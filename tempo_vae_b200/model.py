@@ -1083,6 +1083,15 @@ class _VAELossFn(torch.autograd.Function):
             nll = {"x": xb, "loss_type": loss_type, "logvar": vae.logvar.detach(), "batch": B}
             xhat, dec_saved = dec.program_fwd(z_bf16, train, nll=nll)
             sums, dxhat = nll["sums"], nll["dxhat"]
+            # conv_out's bias gradient = column sums of the gradient just written. The l1 gradient is +-g with g =
+            # exp(-logvar) / B ROUNDED TO BF16 in every element, so its column sums carry that one rounding as a common
+            # factor (up to 2^-9): divide it out (tvae_nll_fwd sums the fp32 values; l2 gradients round independently).
+            cs = torch.empty((C,), dtype=torch.float32, device=dxhat.device)
+            ops.colsum_bf16(dxhat, C, cs)
+            if loss_type == 0:
+                gsc = torch.exp(-vae.logvar.detach().float().reshape(-1)[:1]) / B
+                cs.mul_(gsc / gsc.to(torch.bfloat16).float())
+            dxhat.tvae_colsum = cs
         else:
             xhat, dec_saved = dec.program_fwd(z_bf16, train)
             sums, dxhat = ops.nll_fwd(xb, xhat.f32, C, loss_type, vae.logvar.detach(), B, train)

@@ -434,6 +434,36 @@ def test_wgrad_skinny_tail_channels(N, H, W, Cn, tail, accumulate):
     assert (untouched == base).all() if accumulate else torch.isnan(untouched).all()
 
 
+def test_new_entry_points_refuse_bad_arguments():
+    """tvae_wgrad_skinny / the fused-loss mode of tvae_conv_gemm / tvae_attn_*_tc fail with a message instead of launching
+    when their preconditions do not hold (error behaviour of the C ABI: negative return code + tvae_last_error)."""
+    o = ops()
+    from tempo_vae_b200._lib import TvaeError
+    wide = torch.zeros((1, 8, 8, 96), device="cuda", dtype=torch.bfloat16)
+    skinny = torch.zeros((1, 8, 8, 8), device="cuda", dtype=torch.bfloat16)
+    grad = torch.zeros((96 * 9 * 8,), device="cuda")
+    with pytest.raises(TvaeError, match="multiple of 64"):
+        o.wgrad_skinny(wide, 96, skinny[..., :4], 4, sign=+1, grad=grad, stride_c=9, stride_n=9 * 8)
+    wide = torch.zeros((1, 8, 8, 64), device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(TvaeError, match="1..4 skinny"):
+        o.wgrad_skinny(wide, 64, skinny[..., :5], 5, sign=+1, grad=grad, stride_c=9, stride_n=9 * 8)
+    with pytest.raises(TvaeError, match="shift_sign"):
+        o.wgrad_skinny(wide, 64, skinny[..., :4], 4, sign=0, grad=grad, stride_c=9, stride_n=9 * 8)
+    # fused loss: only a stride-1 forward conv with the bf16 output alone may carry it
+    x = torch.zeros((1, 8, 8, 64), device="cuda", dtype=torch.bfloat16)
+    w = torch.zeros((64, 64, 2, 2), device="cuda")
+    nll = {"x": x, "loss_type": 0, "logvar": torch.zeros(1, device="cuda"), "batch": 1}
+    with pytest.raises((TvaeError, AssertionError)):
+        o.conv_gemm(x, 64, o.pack_weight(w, "fwd"), kind=1, R=2, Cout=64, want_f32=False, want_bf16=True, nll=nll)
+    # attention: the tensor-core entry points are for head dimension 32 only
+    q = torch.zeros((16, 3 * 64), device="cuda")
+    out = torch.zeros((16, 64), device="cuda")
+    lse = torch.zeros((1, 4, 16), device="cuda")
+    rc = o.lib.tvae_attn_fwd_tc(q.data_ptr(), q.data_ptr() + 256, q.data_ptr() + 512, 192, 1, 16, 64, 4, 0, out.data_ptr(),
+                                lse.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    assert rc != 0 and b"head dimension must be 32" in o.lib.tvae_last_error()
+
+
 @pytest.mark.parametrize("N,H,W,C,act,x_bf16", [(3, 16, 16, 128, 1, False), (2, 64, 64, 512, 1, True), (2, 8, 8, 256, 3, False),
                                                  (2, 16, 16, 128, 2, False)])
 def test_groupnorm_saved_activation_gradient(N, H, W, C, act, x_bf16):

@@ -567,6 +567,46 @@ def test_wgrad_stream_overlap_gives_identical_gradients():
         assert torch.equal(grads[1][k], grads[2][k]), k
 
 
+@pytest.mark.parametrize("loss_type", ["l1", "l2"])
+def test_loss_fused_into_conv_out_gives_identical_gradients(loss_type):
+    """ENGINE.fuse_nll: decoder.conv_out's epilogue forms the reconstruction loss and writes its gradient instead of the
+    fp32 reconstruction. The gradient it writes is bit-identical to what conv -> tvae_nll_fwd produces, so every
+    parameter gradient must be bit-identical too -- except conv_out's own bias gradient, which the two-kernel path sums
+    from the fp32 gradient values and the fused path from their bf16 roundings (with the common rounding factor of the
+    l1 gradient divided out): equal to fp32 summation accuracy. The loss scalars differ by the summation order."""
+    from tempo_vae_b200.model import ENGINE
+    cfg = dict(orc.TINY_CFG, nll_loss_type=loss_type)
+    x = orc.structured_batch(6, cfg, seed=8).cuda()
+    eps = torch.randn((6, cfg["embed_dim"], cfg["shape"][1] // 4, cfg["shape"][2] // 4),
+                      generator=torch.Generator().manual_seed(4)).cuda()
+    out = []
+    prev = ENGINE.fuse_nll
+    try:
+        for mode in (False, True):
+            ENGINE.fuse_nll = mode
+            model = build(cfg, seed=7)
+            sd = orc.rerandomize_zero_init({k: v.detach().cpu().clone() for k, v in model.state_dict().items()})
+            model.load_state_dict(sd)
+            loss, metrics = model.vae.get_loss(x, eps=eps)
+            loss.backward()
+            torch.cuda.synchronize()
+            out.append((float(loss.detach()), {k: float(v.detach() if torch.is_tensor(v) else v) for k, v in metrics.items()},
+                        {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}))
+    finally:
+        ENGINE.fuse_nll = prev
+    (l0, m0, g0), (l1, m1, g1) = out
+    assert abs(l0 - l1) <= 1e-6 * abs(l0)
+    for k in m0:
+        assert abs(m0[k] - m1[k]) <= 1e-5 * max(abs(m0[k]), 1e-12), k
+    assert g0.keys() == g1.keys() and len(g0) > 20
+    for k in g0:
+        if k.endswith("decoder.conv_out.bias"):
+            tol = 1e-5 if loss_type == "l1" else 2e-3      # l2: independent bf16 roundings of 6 x 256 values per channel
+            assert rel(g1[k], g0[k]) < tol, (k, rel(g1[k], g0[k]))
+        else:
+            assert torch.equal(g0[k], g1[k]), k
+
+
 def test_channels_last_inputs_are_consumed_without_the_nchw_detour(tmp_path):
     """"accept channels_last strides without copying". The same values fed as (a) NCHW fp32, (b) fp32
     with channels-last strides, (c) a permuted view of [N, H, W, C] tiles and (d) the bf16 channels-last view that
