@@ -491,6 +491,10 @@ VARIANTS = {
     "no_mid_attn_wide": dict(mid_attn=False, chs=[64, 32, 32], shape=(12, 32, 32)),
     "no_affine": dict(norm_affine=False),
     "two_levels_odd_batch": dict(chs=[32, 32], shape=(20, 16, 16)),
+    # 260 = 2 x 128 + 4 spectral channels: the 1028-channel code paths of the default model at test size -- weight
+    # gradients of conv_in / conv_out as whole-tile GEMM + tvae_wgrad_skinny, the fused loss epilogue with a ragged
+    # last channel chunk and pad lanes
+    "tail_channels_260": dict(chs=[64, 32, 32], shape=(260, 16, 16)),
 }
 
 
@@ -565,6 +569,50 @@ def test_wgrad_stream_overlap_gives_identical_gradients():
     for k in grads[0]:
         assert torch.equal(grads[0][k], grads[1][k]), k
         assert torch.equal(grads[1][k], grads[2][k]), k
+
+
+def test_wide_wgrad_split_and_attention_switches_leave_the_step_unchanged():
+    """260 = 2 x 128 + 4 channels (the default model's 1028 at test size). ENGINE.split_wide_wgrad computes the weight
+    gradients of conv_in / conv_out as a whole-tile tcgen05 GEMM + tvae_wgrad_skinny instead of one padded GEMM: those two
+    tensors agree to fp32 summation accuracy, every other gradient is bit-identical. tvae_attn_set_tcgen05 swaps the
+    tcgen05 kind::tf32 attention for the mma.sync kernels: same TF32 operands, another summation order -- gradients
+    agree to 2e-3 of each tensor's norm (they pass through bf16 roundings downstream)."""
+    from tempo_vae_b200.model import ENGINE
+    from tempo_vae_b200._lib import lib
+    cfg = dict(orc.TINY_CFG, chs=[64, 32, 32], shape=(260, 16, 16))
+    x = orc.structured_batch(4, cfg, seed=9).cuda()
+    eps = torch.randn((4, cfg["embed_dim"], 4, 4), generator=torch.Generator().manual_seed(6)).cuda()
+
+    def run():
+        model = build(cfg, seed=7)
+        sd = orc.rerandomize_zero_init({k: v.detach().cpu().clone() for k, v in model.state_dict().items()})
+        model.load_state_dict(sd)
+        loss, _ = model.vae.get_loss(x, eps=eps)
+        loss.backward()
+        torch.cuda.synchronize()
+        return float(loss.detach()), {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
+    prev = ENGINE.split_wide_wgrad
+    try:
+        ENGINE.split_wide_wgrad = True
+        l_split, g_split = run()
+        ENGINE.split_wide_wgrad = False
+        l_one, g_one = run()
+        ENGINE.split_wide_wgrad = True
+        lib.tvae_attn_set_tcgen05(0)
+        l_mma, g_mma = run()
+    finally:
+        ENGINE.split_wide_wgrad = prev
+        lib.tvae_attn_set_tcgen05(1)
+    assert l_split == l_one
+    wide = ("vae.encoder.conv_in.weight", "vae.decoder.conv_out.weight")
+    for k in g_split:
+        if k in wide:
+            assert rel(g_split[k], g_one[k]) < 1e-5, (k, rel(g_split[k], g_one[k]))
+        else:
+            assert torch.equal(g_split[k], g_one[k]), k
+    assert abs(l_mma - l_split) <= 1e-5 * abs(l_split)
+    worst = max(rel(g_mma[k], g_split[k]) for k in g_split)
+    assert worst < 2e-2, worst           # per-tensor; typically 1e-3
 
 
 @pytest.mark.parametrize("loss_type", ["l1", "l2"])
