@@ -552,10 +552,12 @@ def test_wgrad_stream_overlap_gives_identical_gradients():
     eps = torch.randn((6, cfg["embed_dim"], cfg["shape"][1] // 4, cfg["shape"][2] // 4),
                       generator=torch.Generator().manual_seed(3)).cuda()
     grads = []
-    prev = ENGINE.wgrad_overlap
+    prev = ENGINE.wgrad_overlap, ENGINE.wgrad_overlap_max_pixels
     try:
-        for mode in (False, True, True):
-            ENGINE.wgrad_overlap = mode
+        # the last mode overlaps only the layers of at most 400 pixels (the 8x8 and 4x4 levels at B=6): main-stream and
+        # side-stream weight gradients then run concurrently and must not share a split-K workspace
+        for mode, max_px in ((False, 0), (True, 0), (True, 0), (False, 400)):
+            ENGINE.wgrad_overlap, ENGINE.wgrad_overlap_max_pixels = mode, max_px
             model = build(cfg, seed=7)
             sd = orc.rerandomize_zero_init({k: v.detach().cpu().clone() for k, v in model.state_dict().items()})
             model.load_state_dict(sd)
@@ -564,11 +566,12 @@ def test_wgrad_stream_overlap_gives_identical_gradients():
             torch.cuda.synchronize()
             grads.append({k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None})
     finally:
-        ENGINE.wgrad_overlap = prev
+        ENGINE.wgrad_overlap, ENGINE.wgrad_overlap_max_pixels = prev
     assert grads[0].keys() == grads[1].keys() and len(grads[0]) > 20
     for k in grads[0]:
         assert torch.equal(grads[0][k], grads[1][k]), k
         assert torch.equal(grads[1][k], grads[2][k]), k
+        assert torch.equal(grads[2][k], grads[3][k]), k
 
 
 def test_wide_wgrad_split_and_attention_switches_leave_the_step_unchanged():
