@@ -205,8 +205,8 @@ attn_fwd_sm100_kernel(const float* __restrict__ q, const float* __restrict__ k, 
   uint8_t* sK = sQ + ROW_TILE_BYTES;
   uint8_t* sV = sK + COL_TILE_BYTES;
   const int warp = threadIdx.x >> 5;
-  const int b = blockIdx.y / heads, h = blockIdx.y % heads;
-  const int row0 = blockIdx.x * RT;
+  const int b = blockIdx.x / heads, h = blockIdx.x % heads;   // (sample, head) on x: no 65,535 limit on B * heads
+  const int row0 = blockIdx.y * RT;
   const int rvalid = min(RT, T - row0);
   const long long base = (long long)b * T;
   const int C = HD * heads;
@@ -340,8 +340,8 @@ attn_bwd_dq_sm100_kernel(const float* __restrict__ q, const float* __restrict__ 
   uint8_t* sV = sK + COL_TILE_BYTES;
   uint8_t* sKmn = sV + COL_TILE_BYTES;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.y / heads, h = blockIdx.y % heads;
-  const int row0 = blockIdx.x * RT;
+  const int b = blockIdx.x / heads, h = blockIdx.x % heads;   // (sample, head) on x: no 65,535 limit on B * heads
+  const int row0 = blockIdx.y * RT;
   const int rvalid = min(RT, T - row0);
   const long long base = (long long)b * T;
   const int C = HD * heads;
@@ -477,8 +477,8 @@ attn_bwd_dkv_sm100_kernel(const float* __restrict__ q, const float* __restrict__
   float* sL = reinterpret_cast<float*>(sm.tmem_ptr + 4);
   float* sD = sL + CT;
   const int warp = threadIdx.x >> 5;
-  const int b = blockIdx.y / heads, h = blockIdx.y % heads;
-  const int row0 = blockIdx.x * RT;
+  const int b = blockIdx.x / heads, h = blockIdx.x % heads;   // (sample, head) on x: no 65,535 limit on B * heads
+  const int row0 = blockIdx.y * RT;
   const int rvalid = min(RT, T - row0);
   const long long base = (long long)b * T;
   const int C = HD * heads;
@@ -621,8 +621,9 @@ int set_attrs() {
 int attn_fwd_sm100(const float* q, const float* k, const float* v, int pitch, int B, int T, int heads, void* out_bf16,
                    float* out_f32, float* lse, cudaStream_t stream) {
   if (int rc = set_attrs()) return rc;
+  TVAE_CHECK(B > 0 && T > 0 && (T + RT - 1) / RT <= 65535, "tvae_attn_fwd_tc: bad batch / sequence length (B = %d, T = %d)", B, T);
   const float scale = 1.0f / sqrtf((float)HD);
-  dim3 grid((T + RT - 1) / RT, B * heads);
+  dim3 grid(B * heads, (T + RT - 1) / RT);
   attn_fwd_sm100_kernel<<<grid, NT, SMEM_FWD, stream>>>(q, k, v, pitch, T, heads, scale,
                                                         reinterpret_cast<__nv_bfloat16*>(out_bf16), out_f32, lse);
   TVAE_CUDA(cudaGetLastError());
@@ -632,9 +633,10 @@ int attn_fwd_sm100(const float* q, const float* k, const float* v, int pitch, in
 int attn_bwd_sm100(const float* q, const float* k, const float* v, int pitch, const float* o, const float* d_out,
                    const float* lse, int B, int T, int heads, void* dqkv_bf16, float* workspace, cudaStream_t stream) {
   if (int rc = set_attrs()) return rc;
+  TVAE_CHECK(B > 0 && T > 0 && (T + RT - 1) / RT <= 65535, "tvae_attn_bwd_tc: bad batch / sequence length (B = %d, T = %d)", B, T);
   const float scale = 1.0f / sqrtf((float)HD);
   __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(dqkv_bf16);
-  dim3 grid((T + RT - 1) / RT, B * heads);
+  dim3 grid(B * heads, (T + RT - 1) / RT);
   attn_bwd_dq_sm100_kernel<<<grid, NT, SMEM_BWD, stream>>>(q, k, v, pitch, o, d_out, lse, T, heads, scale, dp, workspace);
   TVAE_CUDA(cudaGetLastError());
   attn_bwd_dkv_sm100_kernel<<<grid, NT, SMEM_BWD, stream>>>(q, k, v, pitch, d_out, lse, workspace, T, heads, scale, dp);
