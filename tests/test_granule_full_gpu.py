@@ -54,6 +54,8 @@ def test_whole_granule_encode_at_full_size_vs_oracle_on_gpu(capsys):
         assert z.shape == (131, 2048, 1028) and float(z.abs().max()) <= 10.0
         lat = t.encode_granule_whole(model, z)
         assert lat.shape == (1, 32, 32, 512)
+        for _ in range(12):       # bring the clocks up: three 8 ms calls straight after an idle GPU once measured 38 ms each
+            t.encode_granule_whole(model, z)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize(); e0.record()
         for _ in range(3):
