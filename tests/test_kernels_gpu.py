@@ -644,6 +644,40 @@ def _attention_case(o, B, T, C, heads, tol):
     assert rel_err(dqkv.float(), qkv.grad) < 1e-2  # bf16 output
 
 
+@pytest.mark.parametrize("B,T,heads", [(2, 200, 4), (1, 129, 3), (3, 64, 1)])
+def test_attention_tcgen05_writes_stay_in_bounds(B, T, heads):
+    """Every output of the tcgen05 attention kernels (o_bf16, o_f32, lse, dqkv, the D workspace) is allocated inside a
+    NaN-filled arena at ragged token counts; the bands around each of them must stay untouched and the payload finite."""
+    o = ops()
+    C = 32 * heads
+    g = torch.Generator(device="cuda").manual_seed(17)
+    qkv = torch.randn((B * T, 3 * C), device="cuda", generator=g)
+    d_out = torch.randn((B * T, C), device="cuda", generator=g)
+    band = 4096
+
+    def arena(numel, dtype):
+        a = torch.full((numel + 2 * band,), float("nan"), device="cuda", dtype=dtype)
+        return a, a[band:band + numel]
+    a_ob, ob = arena(B * T * C, torch.bfloat16)
+    a_of, of = arena(B * T * C, torch.float32)
+    a_lse, lse = arena(B * heads * T, torch.float32)
+    a_dq, dqkv = arena(B * T * 3 * C, torch.bfloat16)
+    a_ws, ws = arena(B * heads * T, torch.float32)
+    st = torch.cuda.current_stream().cuda_stream
+    base = qkv.data_ptr()
+    assert o.lib.tvae_attn_set_tcgen05(-1) == 1
+    rc = o.lib.tvae_attn_fwd_tc(base, base + 4 * C, base + 8 * C, 3 * C, B, T, C, heads, ob.data_ptr(), of.data_ptr(),
+                                lse.data_ptr(), st)
+    assert rc == 0, o.lib.tvae_last_error()
+    rc = o.lib.tvae_attn_bwd_tc(base, base + 4 * C, base + 8 * C, 3 * C, of.data_ptr(), d_out.data_ptr(), lse.data_ptr(), B, T,
+                                C, heads, dqkv.data_ptr(), ws.data_ptr(), st)
+    assert rc == 0, o.lib.tvae_last_error()
+    torch.cuda.synchronize()
+    for a, payload in ((a_ob, ob), (a_of, of), (a_lse, lse), (a_dq, dqkv), (a_ws, ws)):
+        assert torch.isnan(a[:band].float()).all() and torch.isnan(a[-band:].float()).all()
+        assert torch.isfinite(payload.float()).all()
+
+
 def test_reparam_kl_fwd_bwd():
     o = ops()
     B, h, w, Z = 3, 16, 16, 32
