@@ -306,7 +306,7 @@ def conv_gemm(x, C_in, wp, *, kind, R, Cout, flip=False, bias=None, residual=Non
         a.nll_x, a.nll_x_pitch = tgt.data_ptr(), pitch_of(tgt)
         a.nll_loss_type, a.nll_logvar, a.nll_batch = int(nll["loss_type"]), nll["logvar"].data_ptr(), int(nll["batch"])
         a.nll_workspace, a.nll_sums = nws.data_ptr(), nll["sums"].data_ptr()
-        KERNEL_LAUNCHES[0] += 1
+        KERNEL_LAUNCHES[0] += 2       # the two-stage reduction of the loss partials
     part = None
     if stats is not None and fused_stats_ok(N, oH, oW, Cout, stats[0], kind, H, W):
         grid_px = (H * W) if kind == 2 else (oH * oW)
