@@ -41,10 +41,10 @@ __device__ __forceinline__ void store8_bf16(__nv_bfloat16* p, const float (&v)[8
 // value and derivative of the activation in one evaluation (GELU: both come out of the same Phi / phi pair)
 __device__ __forceinline__ void act_and_grad_fast(float y, int act, float& a, float& g) {
   if (act == 1) {
-    float Phi, pe;
-    gelu_phi(y, Phi, pe);
-    a = y * Phi;
-    g = fmaf(y, pe, Phi);
+    float q, pe;
+    gelu_q(y, q, pe);
+    a = gelu_from_q(y, q);                                    // the same value gelu_fast produces, bit for bit
+    g = fmaf(y, pe, (y >= 0.f) ? 1.0f - q : q);
   } else {
     a = act_f(y, act);
     g = act_grad_f(y, act);
