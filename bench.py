@@ -58,6 +58,7 @@ TINY_MODEL = dict(
 )
 FWD_GF, BWD_GF = 165.776, 292.746          # algorithmic conv GFLOP / sample
 REF_BATCH = 8                              # BASELINE config 1: the reference's CPU-runnable case
+ENCODE_GRANULES = 49                       # config 5: the Jan-2025-LA set size (3,136 patches), SURVEY.md 8(d)
 # dram bytes of one 512->512 3x3 @64x64 launch at B=256 from the committed ncu capture (profiles/ncu_gemm_r2.md, end of
 # round 2, launch 1: 1.089 GB read + 2.105 GB written; the launch reads a 1.07 GB bf16 activation + 4.7 MB of weights and
 # writes a 2.15 GB fp32 tensor)
@@ -400,12 +401,11 @@ def measure_encode(torch, t, model, dev, B, steps, warmup, rank=0, n_gran=4):
     g = torch.Generator(device=dev).manual_seed(100 + rank)
     mean_s = torch.full((1028,), 3.0, device=dev)
     std_s = torch.full((1028,), 0.5, device=dev)
-    patches = []
-    for _ in range(n_gran):
+    patches = torch.empty((64 * n_gran, 1028, 64, 64), device=dev)     # per rank, the reference's fp32 NCHW patches
+    for i in range(n_gran):
         rad = torch.exp(torch.randn((131, 2048, 1028), device=dev, generator=g) * 0.5 + 3.0)
-        patches.append(t.granule_to_patches(t.normalize_radiance(rad, mean_s, std_s)))
+        patches[64 * i:64 * (i + 1)] = t.granule_to_patches(t.normalize_radiance(rad, mean_s, std_s))
         del rad
-    patches = torch.cat(patches)                    # [64 * n_gran, 1028, 64, 64] per rank
     for _ in range(warmup):
         t.encode_patches(model, patches, batch_size=B)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -417,8 +417,8 @@ def measure_encode(torch, t, model, dev, B, steps, warmup, rank=0, n_gran=4):
     n = patches.shape[0]
     return {"workload": "encode-only patch sweep (BASELINE config 5): posterior means of the 64x64 patches of synthetic "
                         "granules [131,2048,1028]", "metric": "encoded patches/sec", "value": n / ms * 1e3,
-            "unit": "patches/s", "ms_per_sweep": ms, "patches_per_gpu": n, "sweeps": steps,
-            "latent_shape": list(lat.shape[1:]), "encoder_tflops": n / ms * 1e3 * 84.248 / 1e3}
+            "unit": "patches/s", "ms_per_sweep": ms, "granules_per_gpu": n_gran, "patches_per_gpu": n, "sweeps": steps,
+            "batch_per_call": B, "latent_shape": list(lat.shape[1:]), "encoder_tflops": n / ms * 1e3 * 84.248 / 1e3}
 
 
 def run_ours(args):
@@ -600,7 +600,9 @@ def run_ours(args):
         # path); the aggregate is world x the SLOWEST rank's rate
         barrier()
         try:
-            secondary["encode"] = measure_encode(torch, t, model, dev, B, ksteps, kwarm, rank)
+            # the 49-granule set (3,136 patches) sharded across the ranks
+            secondary["encode"] = measure_encode(torch, t, model, dev, B, ksteps, kwarm, rank,
+                                                 n_gran=max(1, -(-ENCODE_GRANULES // world)))
         except Exception as e:  # noqa: BLE001
             secondary["encode"] = {"error": repr(e)[:300]}
         if world > 1:
