@@ -298,7 +298,7 @@ def run_reference_gpu(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": args.ref_precision, "data": "synthetic",
         "config": {"workload": WORKLOAD, "batch_per_gpu": B},
-        "peak_hbm_gb": peak_hbm_gb, "final_loss": float(loss),
+        "peak_hbm_gb": torch.cuda.max_memory_allocated(dev) / 1e9, "final_loss": float(loss),
     }), flush=True)
 
 
