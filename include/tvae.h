@@ -405,6 +405,30 @@ int32_t tvae_act_dropout_bwd(const float* x, int32_t x_pitch, const void* da_bf1
 int32_t tvae_probe_mse(const float* pred, int32_t pred_pitch, const float* target, int64_t target_pitch, int64_t n_valid,
                        int64_t rows_padded, double* sums, void* dpred_bf16, int32_t dp_pitch, tvae_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Probe TARGETS (the data side of the probes): the L2 component fields a probe regresses on are
+ * normalised per component and averaged over 4x4 pixel blocks down to the latent grid
+ * (src/scripts/linear_probe_analysis.py:60-110 normalize_component, :180-190 reshape + np.nanmean). NaN = invalid pixel.
+ *
+ * tvae_nan_moments: out5 (fp64) = count, sum (x - center), sum (x - center)^2, min x, max x over the non-NaN elements of
+ *  x[0..n) (mean / std / min / max of the "zscore" and "minmax" statistics; a second call with center = mean gives the
+ *  centred second moment). min / max are +inf / -inf when nothing is valid.
+ * tvae_select_hist: one 8-bit pass of an exact radix select (np.median of the "asinh" statistics: median, then the
+ *  median of |x - median|). Keys are the order-preserving uint32 image of v = x (use_abs = 0) or |x - center|
+ *  (use_abs = 1), NaN skipped; hist256[b] = number of elements whose key equals `prefix` on the bits of `prefix_mask`
+ *  and whose byte (key >> shift) & 255 is b. Four calls (shift 24, 16, 8, 0), the caller narrowing prefix between them,
+ *  pin the k-th smallest value exactly. key(v) = ~bits(v) for negative v, bits(v) | 0x80000000 otherwise.
+ * tvae_component_pool: f(x) per pixel, mode 0: (x - a) / b; mode 1: asinh(x / b); mode 2: logit(a + (1 - 2a) x); NaN stays
+ *  NaN. `normalized` (optional, fp32 [H][W] dense) receives f; pooled[H / pool][W / pool] = mean of the valid f in each
+ *  pool x pool block, NaN where a block has none. x is fp32 [H][pitch]. Rows / columns beyond the last whole block are
+ *  dropped from `pooled` (the reference crops the field to a multiple of 64 first) and kept in `normalized`.
+ */
+int32_t tvae_nan_moments(const float* x, int64_t n, float center, double* out5, tvae_stream_t stream);
+int32_t tvae_select_hist(const float* x, int64_t n, float center, int32_t use_abs, uint32_t prefix, uint32_t prefix_mask,
+                         int32_t shift, uint64_t* hist256, tvae_stream_t stream);
+int32_t tvae_component_pool(const float* x, int32_t H, int32_t W, int32_t pitch, int32_t pool, int32_t mode, float a,
+                            float b, float* normalized, float* pooled, tvae_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,7 +6,7 @@ source is located with `ast`, never written anywhere -- and executed with numpy/
 stores input, seed and output, and pins oracle.extract_tiles (tests/test_oracle_cpu.py) and, through it, the CUDA
 kernel tvae_extract_tiles (tests/test_data_gpu.py).
 
-  python oracle/make_golden_data.py
+  python oracle/make_golden_data.py [tiles] [probes] [probe_targets]
 """
 import ast
 import os
@@ -44,9 +44,6 @@ def main():
     torch.save(dict(cases=cases, source="src/scripts/prepare_tempo_tiles.py:21-58 executed from /root/reference"), out)
     print("wrote", out, os.path.getsize(out), "bytes")
 
-
-if __name__ == "__main__":
-    main()
 
 
 def probe_fixture():
@@ -90,5 +87,50 @@ def probe_fixture():
     print("wrote", out, os.path.getsize(out), "bytes")
 
 
+
+def probe_target_fixture():
+    """tests/golden/probe_targets.pt: the reference's own `normalize_component` (compiled on its own from
+    src/scripts/linear_probe_analysis.py:60-110; scipy is in this image) on synthetic component fields with NaN blobs,
+    followed by the pooling statement of `process_file` (:183-190: reshape(h//4, 4, w//4, 4) + np.nanmean over axes
+    (1, 3)), which cannot run as a function (the rest of process_file reads NetCDF files)."""
+    import warnings
+    normalize_component = reference_function(os.path.join(REF, "src/scripts/linear_probe_analysis.py"), "normalize_component")
+    rs = np.random.RandomState(23)
+    cases = []
+    for name, norm_type, (H, W), make in [
+        ("no2_like", "asinh", (64, 192), lambda s: (rs.standard_t(3, size=s) * 2e15 + 1e15)),
+        ("o3_like", "zscore", (64, 192), lambda s: rs.normal(300.0, 25.0, size=s)),
+        ("hcho_like", "asinh", (32, 100), lambda s: rs.standard_t(4, size=s) * 8e15),
+        ("cloud_like", "logit", (64, 192), lambda s: rs.beta(0.6, 1.5, size=s)),
+        ("minmax_odd", "minmax", (36, 52), lambda s: rs.normal(0.0, 1.0, size=s)),
+    ]:
+        field = make((H, W)).astype(np.float32)
+        blob = np.kron(rs.rand(H // 4, W // 4) < 0.12, np.ones((4, 4), dtype=bool))          # whole 4x4 blocks invalid
+        field[blob] = np.nan
+        field[rs.rand(H, W) < 0.08] = np.nan                                                  # and scattered pixels
+        normalized, stats = normalize_component(field.copy(), norm_type)
+        h, w = normalized.shape
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            pooled = np.nanmean(normalized.reshape(h // 4, 4, w // 4, 4), axis=(1, 3))
+        again, _ = normalize_component(field.copy(), norm_type, stats)                        # the `stats` given path
+        assert np.array_equal(again, normalized, equal_nan=True)
+        cases.append(dict(name=name, norm_type=norm_type, field=torch.from_numpy(field),
+                          normalized=torch.from_numpy(np.asarray(normalized, dtype=np.float32)),
+                          pooled=torch.from_numpy(np.asarray(pooled, dtype=np.float32)),
+                          stats={k: float(v) for k, v in stats.items()},
+                          stats_dtype={k: str(np.asarray(v).dtype) for k, v in stats.items()},
+                          normalized_dtype=str(normalized.dtype)))
+        print(name, norm_type, {k: float(v) for k, v in stats.items()}, normalized.dtype,
+              "valid pooled:", int((~np.isnan(pooled)).sum()), "of", pooled.size)
+    out = os.path.join(ROOT, "tests", "golden", "probe_targets.pt")
+    torch.save(dict(cases=cases, source="src/scripts/linear_probe_analysis.py:60-110 executed from /root/reference; "
+                                        ":183-190 restated in oracle/make_golden_data.py"), out)
+    print("wrote", out, os.path.getsize(out), "bytes")
+
+
 if __name__ == "__main__":
-    probe_fixture()
+    # python oracle/make_golden_data.py [tiles] [probes] [probe_targets]   (no argument: all three)
+    todo = sys.argv[1:] or ["tiles", "probes", "probe_targets"]
+    for what in todo:
+        {"tiles": main, "probes": probe_fixture, "probe_targets": probe_target_fixture}[what]()

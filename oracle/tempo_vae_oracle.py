@@ -471,3 +471,56 @@ def r2_score(y, pred):
     """sklearn.metrics.r2_score for 1-D arrays (src/scripts/linear_probe_analysis.py:680)."""
     y, pred = torch.as_tensor(y).double().reshape(-1), torch.as_tensor(pred).double().reshape(-1)
     return float(1.0 - ((y - pred) ** 2).sum() / ((y - y.mean()) ** 2).sum())
+
+
+# ------------------------------------------------------------------------------------------------ probe targets
+def component_statistics(field, norm_type):
+    """The statistics src/scripts/linear_probe_analysis.py:62-100 derives from the valid (non-NaN) pixels of a float32
+    component field (numpy float32 arithmetic, as the reference's `np.mean / np.std / np.median` give on float32)."""
+    import numpy as np
+    field = np.asarray(field, dtype=np.float32)
+    good = field[np.isfinite(field) | np.isinf(field)]            # everything that is not NaN
+    if norm_type == "zscore":
+        return {"mean": good.mean(), "std": good.std()}
+    if norm_type == "minmax":
+        return {"min": good.min(), "max": good.max()}
+    if norm_type == "asinh":
+        centre = np.median(good)
+        return {"scale": 1.4826 * np.median(np.abs(good - centre)), "median": centre}
+    if norm_type == "logit":
+        return {"eps": 0.01}
+    raise ValueError(f"Unknown normalization type: {norm_type}")
+
+
+def normalize_component(field, norm_type, stats=None):
+    """(normalised field, stats) of src/scripts/linear_probe_analysis.py:60-110; NaN pixels stay NaN."""
+    import numpy as np
+    field = np.asarray(field, dtype=np.float32)
+    stats = component_statistics(field, norm_type) if stats is None else stats
+    if norm_type == "zscore":
+        out = (field - stats["mean"]) / (stats["std"] + 1e-8)
+    elif norm_type == "minmax":
+        out = (field - stats["min"]) / (stats["max"] - stats["min"] + 1e-8)
+    elif norm_type == "asinh":
+        out = np.arcsinh(field / (stats["scale"] + 1e-8))
+    elif norm_type == "logit":
+        p = stats["eps"] + (1 - 2 * stats["eps"]) * field
+        with np.errstate(divide="ignore", invalid="ignore"):
+            out = np.log(p / (1 - p)).astype(np.float32)          # scipy.special.logit
+    else:
+        raise ValueError(f"Unknown normalization type: {norm_type}")
+    return out, stats
+
+
+def nanmean_pool(field, pool=4):
+    """[H, W] -> [H // pool, W // pool] block means over the valid pixels, NaN for an all-NaN block
+    (src/scripts/linear_probe_analysis.py:183-190)."""
+    import numpy as np
+    field = np.asarray(field, dtype=np.float32)
+    h, w = field.shape[0] // pool, field.shape[1] // pool
+    blocks = field[:h * pool, :w * pool].reshape(h, pool, w, pool).transpose(0, 2, 1, 3).reshape(h, w, pool * pool)
+    ok = ~np.isnan(blocks)
+    total = np.where(ok, blocks, np.float32(0)).sum(axis=2, dtype=np.float32)
+    count = ok.sum(axis=2)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return (total / count.astype(np.float32)).astype(np.float32)

@@ -19,6 +19,8 @@ from .inference import (encode_granule_whole, encode_patches, evaluate_reconstru
 from .model_with_l2 import L2PredictionHead, VAEWithL2Supervision  # noqa: F401
 from .optim import FusedAdamW  # noqa: F401
 from .probes import LinearProbe, MLPProbe, probe_metrics, train_probe  # noqa: F401
+from .probe_targets import (component_stats, component_targets, nan_median, normalize_component,  # noqa: F401
+                            pool_component, sample_probe_pairs)
 from .tempo_data import (DevicePrefetcher, DeviceTileCache, HostTileStore, RandomBuffer, TEMPODataLoader,  # noqa: F401
                          TEMPODataset, load_normalization_stats)
 from .tile_prep import SpectrumStats, draw_tile_specs, extract_tiles, granule_statistics, process_granule  # noqa: F401

@@ -69,6 +69,7 @@ def _load():
             "(or `make -C tempo_vae_b200/csrc`). There is no CPU/PyTorch fallback for this path.")
     lib = C.CDLL(LIB_PATH)
     vp, i32, i64, u64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_float
+    u32 = C.c_uint32
     sigs = {
         "tvae_last_error": (C.c_char_p, []),
         "tvae_abi_version": (i32, []),
@@ -129,6 +130,9 @@ def _load():
         "tvae_act_dropout_fwd": (i32, [vp, i32, i64, i32, i32, f32, u64, u64, vp, i32, vp]),
         "tvae_act_dropout_bwd": (i32, [vp, i32, vp, i32, i64, i32, i32, f32, u64, u64, vp, i32, vp]),
         "tvae_probe_mse": (i32, [vp, i32, vp, i64, i64, i64, vp, vp, i32, vp]),
+        "tvae_nan_moments": (i32, [vp, i64, f32, vp, vp]),
+        "tvae_select_hist": (i32, [vp, i64, f32, i32, u32, u32, i32, vp, vp]),
+        "tvae_component_pool": (i32, [vp, i32, i32, i32, i32, i32, f32, f32, vp, vp, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol

@@ -142,6 +142,121 @@ inline int pw_grid(long long work) {
   return (int)g;
 }
 
+// ---------------------------------------------------------------------------------------------- probe targets
+// The component fields the probes regress on (src/scripts/linear_probe_analysis.py:60-110 normalize_component, :180-190
+// 4x4 nanmean pooling to the latent grid). NaN marks an invalid pixel everywhere below.
+
+// order-preserving map float -> uint32 (negative values reversed); every non-NaN float has a distinct key
+__device__ __forceinline__ uint32_t float_key(float v) {
+  const uint32_t b = __float_as_uint(v);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+// out[0..4] = count, sum (x - c), sum (x - c)^2, min x, max x over the non-NaN elements (fp64, fixed order)
+__global__ void __launch_bounds__(1024)
+nan_moments_kernel(const float* __restrict__ x, long long n, float center, double* __restrict__ out) {
+  double cnt = 0.0, s1 = 0.0, s2 = 0.0;
+  float mn = INFINITY, mx = -INFINITY;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    const float v = x[i];
+    if (v == v) {
+      const double d = (double)v - (double)center;
+      cnt += 1.0; s1 += d; s2 += d * d;
+      mn = fminf(mn, v); mx = fmaxf(mx, v);
+    }
+  }
+  __shared__ double sh[3][32];
+  __shared__ float shm[2][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+    s1 += __shfl_down_sync(0xffffffffu, s1, o);
+    s2 += __shfl_down_sync(0xffffffffu, s2, o);
+    mn = fminf(mn, __shfl_down_sync(0xffffffffu, mn, o));
+    mx = fmaxf(mx, __shfl_down_sync(0xffffffffu, mx, o));
+  }
+  if (lane == 0) { sh[0][warp] = cnt; sh[1][warp] = s1; sh[2][warp] = s2; shm[0][warp] = mn; shm[1][warp] = mx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0, c = 0.0;
+    float lo = INFINITY, hi = -INFINITY;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+      a += sh[0][w]; b += sh[1][w]; c += sh[2][w];
+      lo = fminf(lo, shm[0][w]); hi = fmaxf(hi, shm[1][w]);
+    }
+    out[0] = a; out[1] = b; out[2] = c; out[3] = (double)lo; out[4] = (double)hi;
+  }
+}
+
+// One pass of an exact radix select over v = x (use_abs = 0) or |x - center| (use_abs = 1), NaN skipped: hist[b] +=
+// number of elements whose key agrees with `prefix` on `prefix_mask` and whose byte (key >> shift) & 255 is b.
+__global__ void __launch_bounds__(256)
+select_hist_kernel(const float* __restrict__ x, long long n, float center, int use_abs, uint32_t prefix,
+                   uint32_t prefix_mask, int shift, unsigned long long* __restrict__ hist) {
+  __shared__ unsigned int sh[256];
+  sh[threadIdx.x] = 0u;
+  __syncthreads();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float xv = x[i];
+    if (xv == xv) {
+      const float v = use_abs ? fabsf(__fsub_rn(xv, center)) : xv;
+      const uint32_t k = float_key(v);
+      if ((k & prefix_mask) == prefix) atomicAdd(&sh[(k >> shift) & 255u], 1u);
+    }
+  }
+  __syncthreads();
+  if (sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], (unsigned long long)sh[threadIdx.x]);
+}
+
+// mode 0: (x - a) / b   (zscore: a = mean, b = std + 1e-8; minmax: a = min, b = max - min + 1e-8)
+// mode 1: asinh(x / b)  (b = scale + 1e-8)
+// mode 2: logit(a + (1 - 2a) x) = log(p / (1 - p))
+__device__ __forceinline__ float component_f(float x, int mode, float a, float b, float one_minus_2a) {
+  if (mode == 0) return __fdiv_rn(__fsub_rn(x, a), b);
+  if (mode == 1) return asinhf(__fdiv_rn(x, b));
+  const float p = __fadd_rn(a, __fmul_rn(one_minus_2a, x));
+  return logf(__fdiv_rn(p, __fsub_rn(1.0f, p)));
+}
+
+// One thread per pooled pixel: normalises its pool x pool block (optionally writing the normalised field) and takes
+// the mean of the valid values (NaN when the block has none).
+__global__ void __launch_bounds__(256)
+component_pool_kernel(const float* __restrict__ x, int H, int W, int pitch, int pool, int mode, float a, float b,
+                      float one_minus_2a, float* __restrict__ normalized, float* __restrict__ pooled) {
+  const int hp = H / pool, wp = W / pool;
+  const long long total = (long long)hp * wp;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / wp), c = (int)(i - (long long)r * wp);
+    float s = 0.f;
+    int cnt = 0;
+    for (int dr = 0; dr < pool; ++dr) {
+      const long long off = (long long)(r * pool + dr) * pitch + (long long)c * pool;
+      for (int dc = 0; dc < pool; ++dc) {
+        const float v = x[off + dc];
+        const float f = (v == v) ? component_f(v, mode, a, b, one_minus_2a) : v;
+        if (normalized) normalized[(long long)(r * pool + dr) * W + (long long)c * pool + dc] = f;
+        if (f == f) { s += f; ++cnt; }
+      }
+    }
+    pooled[i] = cnt ? __fdiv_rn(s, (float)cnt) : __int_as_float(0x7fc00000);
+  }
+}
+
+// rows / columns beyond the last whole pool block only exist in the normalised field
+__global__ void __launch_bounds__(256)
+component_edge_kernel(const float* __restrict__ x, int H, int W, int pitch, int pool, int mode, float a, float b,
+                      float one_minus_2a, float* __restrict__ normalized) {
+  const int h0 = (H / pool) * pool, w0 = (W / pool) * pool;
+  const long long total = (long long)H * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / W), c = (int)(i - (long long)r * W);
+    if (r < h0 && c < w0) continue;
+    const float v = x[(long long)r * pitch + c];
+    normalized[i] = (v == v) ? component_f(v, mode, a, b, one_minus_2a) : v;
+  }
+}
+
 }  // namespace
 }  // namespace tvae
 
@@ -183,5 +298,43 @@ extern "C" int32_t tvae_probe_mse(const float* pred, int32_t pred_pitch, const f
   probe_mse_kernel<<<1, 1024, 0, stream>>>(pred, pred_pitch, target, target_pitch, n_valid, rows_padded, sums,
                                            reinterpret_cast<__nv_bfloat16*>(dpred_bf16), dp_pitch);
   TVAE_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int32_t tvae_nan_moments(const float* x, int64_t n, float center, double* out5, cudaStream_t stream) {
+  TVAE_ENTER(x);
+  TVAE_CHECK(x && out5 && n > 0, "tvae_nan_moments: bad arguments");
+  nan_moments_kernel<<<1, 1024, 0, stream>>>(x, n, center, out5);
+  TVAE_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int32_t tvae_select_hist(const float* x, int64_t n, float center, int32_t use_abs, uint32_t prefix,
+                                    uint32_t prefix_mask, int32_t shift, uint64_t* hist256, cudaStream_t stream) {
+  TVAE_ENTER(x);
+  TVAE_CHECK(x && hist256 && n > 0, "tvae_select_hist: bad arguments");
+  TVAE_CHECK(shift >= 0 && shift <= 24 && (shift & 7) == 0 && (prefix & ~prefix_mask) == 0u,
+             "tvae_select_hist: shift must be 0, 8, 16 or 24 and prefix must lie inside prefix_mask");
+  TVAE_CUDA(cudaMemsetAsync(hist256, 0, 256 * sizeof(uint64_t), stream));
+  select_hist_kernel<<<pw_grid(n), 256, 0, stream>>>(x, n, center, use_abs, prefix, prefix_mask, shift,
+                                                     reinterpret_cast<unsigned long long*>(hist256));
+  TVAE_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int32_t tvae_component_pool(const float* x, int32_t H, int32_t W, int32_t pitch, int32_t pool, int32_t mode,
+                                       float a, float b, float* normalized, float* pooled, cudaStream_t stream) {
+  TVAE_ENTER(x);
+  TVAE_CHECK(x && pooled && H > 0 && W > 0 && pitch >= W && pool >= 1 && H >= pool && W >= pool,
+             "tvae_component_pool: bad arguments");
+  TVAE_CHECK(mode >= 0 && mode <= 2, "tvae_component_pool: mode must be 0 (affine), 1 (asinh) or 2 (logit)");
+  const float om2a = 1.0f - 2.0f * a;
+  component_pool_kernel<<<pw_grid((long long)(H / pool) * (W / pool)), 256, 0, stream>>>(x, H, W, pitch, pool, mode, a, b,
+                                                                                       om2a, normalized, pooled);
+  TVAE_CUDA(cudaGetLastError());
+  if (normalized && (H % pool || W % pool)) {
+    component_edge_kernel<<<pw_grid((long long)H * W), 256, 0, stream>>>(x, H, W, pitch, pool, mode, a, b, om2a, normalized);
+    TVAE_CUDA(cudaGetLastError());
+  }
   return 0;
 }

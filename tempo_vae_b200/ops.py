@@ -82,6 +82,7 @@ _KERNELS_PER_CALL = {
     "tvae_l2head_loss_fwd": 1, "tvae_l2head_loss_bwd": 1, "tvae_l2head_finalize": 1, "tvae_sumsq": 2, "tvae_adamw": 1,
     "tvae_gather_rows": 1, "tvae_extract_tiles": 1, "tvae_spectrum_stats_accum": 2, "tvae_spectrum_stats_finalize": 1,
     "tvae_batch_stats": 2, "tvae_act_dropout_fwd": 1, "tvae_act_dropout_bwd": 1, "tvae_probe_mse": 1,
+    "tvae_nan_moments": 1, "tvae_select_hist": 1, "tvae_component_pool": 1,
 }
 
 
@@ -864,3 +865,42 @@ def probe_mse(pred, y, n_valid, rows_padded, sums, dpred=None):
                              int(n_valid), int(rows_padded), sums.data_ptr(), _ptr(dpred),
                              dpred.stride(0) if dpred is not None else 0, _stream()), "tvae_probe_mse")
     return sums
+
+
+# ----------------------------------------------------------------------------------------------- probe targets
+@_on_device
+def nan_moments(x, center=0.0):
+    """fp64 [5] on the device: count, sum (x - c), sum (x - c)^2, min, max over the non-NaN elements (tvae_nan_moments)."""
+    require_cuda(x, "component field")
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.numel() > 0
+    out = torch.empty(5, dtype=torch.float64, device=x.device)
+    check(lib.tvae_nan_moments(x.data_ptr(), x.numel(), float(center), out.data_ptr(), _stream()), "tvae_nan_moments")
+    return out
+
+
+@_on_device
+def select_hist(x, center, use_abs, prefix, prefix_mask, shift, hist=None):
+    """One 8-bit pass of the exact radix select (tvae_select_hist): uint64-as-int64 [256] counts on the device."""
+    require_cuda(x, "component field")
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.numel() > 0
+    if hist is None:
+        hist = torch.empty(256, dtype=torch.int64, device=x.device)
+    check(lib.tvae_select_hist(x.data_ptr(), x.numel(), float(center), int(bool(use_abs)), int(prefix), int(prefix_mask),
+                               int(shift), hist.data_ptr(), _stream()), "tvae_select_hist")
+    return hist
+
+
+@_on_device
+def component_pool(x, mode, a, b, pool=4, want_normalized=False):
+    """x fp32 [H, W] (row pitch = x.stride(0)) -> (normalised [H, W] or None, pooled [H // pool, W // pool])
+    (tvae_component_pool: normalisation and the nanmean pooling in one pass)."""
+    require_cuda(x, "component field")
+    assert x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
+    H, W = x.shape
+    norm = torch.empty((H, W), dtype=torch.float32, device=x.device) if want_normalized else None
+    pooled = torch.empty((H // pool, W // pool), dtype=torch.float32, device=x.device)
+    check(lib.tvae_component_pool(x.data_ptr(), H, W, x.stride(0), int(pool), int(mode), float(a), float(b), _ptr(norm),
+                                  pooled.data_ptr(), _stream()), "tvae_component_pool")
+    if want_normalized and (H % pool or W % pool):
+        KERNEL_LAUNCHES[0] += 1
+    return norm, pooled

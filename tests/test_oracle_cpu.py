@@ -377,6 +377,31 @@ def test_oracle_probe_training_matches_the_reference_run():
         assert 0.0 < orc.r2_score(fx["y_val"], pred) < 1.0
 
 
+def test_oracle_probe_targets_match_the_reference_function():
+    """oracle.normalize_component / nanmean_pool against tests/golden/probe_targets.pt (the reference's own
+    normalize_component, src/scripts/linear_probe_analysis.py:60-110, and its pooling statement :183-190)."""
+    import numpy as np
+    fx = gold("probe_targets.pt")
+    assert {c["norm_type"] for c in fx["cases"]} == {"zscore", "minmax", "asinh", "logit"}
+    for c in fx["cases"]:
+        field = c["field"].numpy()
+        normalized, stats = orc.normalize_component(field, c["norm_type"])
+        assert {k: float(v) for k, v in stats.items()} == c["stats"], c["name"]
+        assert normalized.dtype == np.float32 == np.dtype(c["normalized_dtype"])
+        want = c["normalized"].numpy()
+        assert np.array_equal(np.isnan(normalized), np.isnan(want)) and np.array_equal(np.isnan(want), np.isnan(field))
+        if c["norm_type"] == "logit":      # scipy's logit against log(p / (1 - p)) in float32
+            assert np.allclose(normalized, want, rtol=2e-6, atol=2e-6, equal_nan=True)
+        else:
+            assert np.array_equal(normalized, want, equal_nan=True), c["name"]
+        again, _ = orc.normalize_component(field, c["norm_type"], stats=c["stats"])
+        assert np.allclose(again, want, rtol=2e-6, atol=2e-6, equal_nan=True)
+        pooled = orc.nanmean_pool(want)
+        assert pooled.shape == tuple(c["pooled"].shape) == (field.shape[0] // 4, field.shape[1] // 4)
+        assert np.array_equal(np.isnan(pooled), np.isnan(c["pooled"].numpy())) and np.isnan(pooled).any()
+        assert np.allclose(pooled, c["pooled"].numpy(), rtol=1e-6, atol=1e-7, equal_nan=True)
+
+
 def test_epoch_shard_gives_every_rank_the_same_number_of_batches():
     """ADVICE r1: with n % world != 0, perm[rank::world] alone can hand rank 0 one batch more than the others (n=4089,
     world=8, B=256: 2 vs 1) and the ranks would issue different numbers of all-reduces."""
