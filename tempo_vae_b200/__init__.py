@@ -15,7 +15,7 @@ from .model import (ENGINE, AttnBlock, AutoencoderKL, Conv2d, ConvTranspose2d, D
                     DiagonalGaussianDistribution, Encoder, GroupNorm, ResNetBlock, ResNetDown, ResNetUp, SpectralVAE,
                     get_conv, get_model, get_precision, set_precision, zero_init)
 from .inference import (encode_granule_whole, encode_patches, evaluate_reconstruction, granule_to_patches,  # noqa: F401
-                        normalize_radiance)
+                        normalize_radiance, reconstruct_granule_whole)
 from .model_with_l2 import L2PredictionHead, VAEWithL2Supervision  # noqa: F401
 from .optim import FusedAdamW  # noqa: F401
 from .probes import LinearProbe, MLPProbe, probe_metrics, train_probe  # noqa: F401

@@ -270,6 +270,32 @@ __global__ void gn_stats_finalize_kernel(const float* __restrict__ part, int spi
   stats[2 * i + 1] = (float)(1.0 / sqrt(var + (double)eps));
 }
 
+// The same for FEW samples with MANY tiles each (whole-granule inference: one sample, 2,048 tile slots per group at
+// 128 x 2048; one thread per (sample, group) walked them serially, 67 us per call): one block per (sample, group), the
+// slots strided over the threads, fixed-order fp64 block reduction.
+__global__ void __launch_bounds__(256)
+gn_stats_finalize_wide_kernel(const float* __restrict__ part, int spi, int G, double count, float eps,
+                              float* __restrict__ stats) {
+  __shared__ double red1[32], red2[32];
+  const int i = blockIdx.x;
+  const int n = i / G, g = i - n * G;
+  double s1 = 0.0, s2 = 0.0;
+  for (int k = threadIdx.x; k < spi; k += blockDim.x) {
+    const float* p = part + (((long long)n * spi + k) * G + g) * 2;
+    s1 += (double)p[0];
+    s2 += (double)p[1];
+  }
+  s1 = block_sum(s1, red1);
+  s2 = block_sum(s2, red2);
+  if (threadIdx.x == 0) {
+    const double mean = s1 / count;
+    double var = s2 / count - mean * mean;
+    if (var < 0) var = 0;
+    stats[2 * i] = (float)mean;
+    stats[2 * i + 1] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- GN apply (+GELU)
 template <int VEC>
 __global__ void gn_act_fwd_kernel(const float* __restrict__ x, const float* __restrict__ stats,
@@ -745,7 +771,10 @@ extern "C" int32_t tvae_gn_stats_finalize(const float* part, int32_t spi, int32_
   TVAE_ENTER(part);
   TVAE_CHECK(part && stats && spi > 0 && N > 0 && G > 0, "tvae_gn_stats_finalize: bad arguments");
   const int NG = N * G;
-  gn_stats_finalize_kernel<<<(NG + 127) / 128, 128, 0, stream>>>(part, spi, NG, G, count, eps, stats);
+  if (spi >= 256 && NG <= 1024)    // few samples, many tile slots each: a block per (sample, group)
+    gn_stats_finalize_wide_kernel<<<NG, 256, 0, stream>>>(part, spi, G, count, eps, stats);
+  else
+    gn_stats_finalize_kernel<<<(NG + 127) / 128, 128, 0, stream>>>(part, spi, NG, G, count, eps, stats);
   TVAE_CUDA(cudaGetLastError());
   return 0;
 }

@@ -35,16 +35,22 @@ __device__ __forceinline__ float philox_normal(uint64_t seed, uint64_t sample, u
 }
 
 // ---------------------------------------------------------------------------------------------- reparam + KL
-// one block per sample
+// CL = 1: one block per sample (the training shapes: 8 K latent elements per sample, hundreds of samples).
+// CL = 8: a cluster of eight 1024-thread blocks per sample for the whole-granule passes (ONE sample of 524 K latent
+// elements: a single 256-thread block took 1.2 ms); the eight KL partials meet in rank 0 through distributed shared
+// memory and are added in rank order, so the result does not depend on scheduling.
+template <int CL>
 __global__ void reparam_fwd_kernel(const float* __restrict__ moments, const float* __restrict__ eps, uint64_t seed,
                                    uint64_t sample_offset, int HW, int Z, __nv_bfloat16* __restrict__ z_bf16,
                                    __nv_bfloat16* __restrict__ z_lo, int z_pitch, float* __restrict__ z_nchw,
                                    float* __restrict__ eps_out, float* __restrict__ kl) {
   __shared__ double red[32];
-  const int b = blockIdx.x;
+  __shared__ double cl_part;
+  const int b = blockIdx.x / CL;
+  const int rank = CL > 1 ? (int)cluster_ctarank() : 0;
   const int total = HW * Z;
   double acc = 0.0;
-  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+  for (int e = rank * blockDim.x + threadIdx.x; e < total; e += CL * blockDim.x) {
     const int p = e / Z, c = e - p * Z;
     const long long row = (long long)b * HW + p;
     const float mean = moments[row * 2 * Z + c];
@@ -61,7 +67,22 @@ __global__ void reparam_fwd_kernel(const float* __restrict__ moments, const floa
     acc += (double)(0.5f * (mean * mean + expf(lv) - 1.0f - lv));
   }
   const double t = block_sum(acc, red);
-  if (threadIdx.x == 0 && kl) kl[b] = (float)t;
+  if (CL == 1) {
+    if (threadIdx.x == 0 && kl) kl[b] = (float)t;
+    return;
+  }
+  if (threadIdx.x == 0) cl_part = t;
+  cluster_sync_all();
+  if (rank == 0 && threadIdx.x == 0 && kl) {
+    double sum = 0.0;
+    for (int r = 0; r < CL; ++r) {
+      double v;
+      asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(mapa_u32(smem_u32(&cl_part), (uint32_t)r)) : "memory");
+      sum += v;
+    }
+    kl[b] = (float)sum;
+  }
+  cluster_sync_all();      // nobody leaves while rank 0 may still be reading its shared memory
 }
 
 __global__ void reparam_bwd_kernel(const float* __restrict__ moments, const float* __restrict__ dz1,
@@ -469,9 +490,25 @@ extern "C" int32_t tvae_reparam_fwd(const float* moments, const float* eps, uint
   TVAE_ENTER(moments);
   TVAE_CHECK(moments, "tvae_reparam_fwd: null moments");
   TVAE_CHECK(B > 0 && HW > 0 && Z > 0, "tvae_reparam_fwd: bad shape");
-  reparam_fwd_kernel<<<B, 256, 0, stream>>>(moments, eps, seed, sample_offset, HW, Z,
-                                            reinterpret_cast<__nv_bfloat16*>(z_bf16),
-                                            reinterpret_cast<__nv_bfloat16*>(z_lo), z_pitch, z_nchw, eps_out, kl);
+  __nv_bfloat16* zb = reinterpret_cast<__nv_bfloat16*>(z_bf16);
+  __nv_bfloat16* zl = reinterpret_cast<__nv_bfloat16*>(z_lo);
+  if ((long long)HW * Z >= 65536 && B <= 64) {     // few, large samples (whole-granule inference): 8 blocks per sample
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)B * 8u);
+    cfg.blockDim = dim3(1024);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 8;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    TVAE_CUDA(cudaLaunchKernelEx(&cfg, reparam_fwd_kernel<8>, moments, eps, seed, sample_offset, (int)HW, (int)Z, zb, zl,
+                                 (int)z_pitch, z_nchw, eps_out, kl));
+    return 0;
+  }
+  reparam_fwd_kernel<1><<<B, 256, 0, stream>>>(moments, eps, seed, sample_offset, HW, Z, zb, zl, z_pitch, z_nchw, eps_out, kl);
   TVAE_CUDA(cudaGetLastError());
   return 0;
 }

@@ -4,6 +4,7 @@ Callers this serves in the reference (they stay the reference's scripts; these a
   * patch-batched evaluation ........ src/scripts/evaluate_reconstruction.py:70-90  (`model(batch)` on [B,1028,64,64])
   * whole-granule latent extraction .. src/scripts/linear_probe_analysis.py:113-140  (`model.get_latent(x).mean` on
                                        [1,1028,128,2048]; fully convolutional, attention over 16,384 tokens)
+  * whole-granule reconstruction ..... src/scripts/analyze_reconstruction.py:111-127  (`model(x)` on the same crop)
   * normalisation .................... src/scripts/prepare_tempo_tiles.py:69-83 / linear_probe_analysis.py:121-124:
                                        log(clamp(rad, min_radiance)) -> z-score with the per-channel spectrum
                                        statistics -> clip to [-10, 10]
@@ -78,6 +79,21 @@ def encode_granule_whole(model, z_rad: torch.Tensor, tile: int = 64) -> torch.Te
     M, T, C = z_rad.shape
     x = z_rad[:(M // tile) * tile, :(T // tile) * tile, :].permute(2, 0, 1).unsqueeze(0)
     return vae.encode(x.to(dev, dtype=torch.float32)).mean
+
+
+@torch.no_grad()
+def reconstruct_granule_whole(model, z_rad: torch.Tensor, tile: int = 64, sample_posterior: bool = True,
+                              eps: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """The reference's whole-granule reconstruction (src/scripts/analyze_reconstruction.py:111-127: `recon = model(x)` on
+    the [1, C, H, W] crop, converted back to [H, W, C]): one fully convolutional encode -> sample -> decode pass; the
+    result stays on the device. `sample_posterior=False` decodes the posterior mode, `eps` ([1, Z, H/4, W/4]) injects the
+    noise (by default it is drawn on the device, as `model(x)` draws it)."""
+    vae = model.vae if hasattr(model, "vae") else model
+    dev = next(vae.parameters()).device
+    M, T, C = z_rad.shape
+    x = z_rad[:(M // tile) * tile, :(T // tile) * tile, :].permute(2, 0, 1).unsqueeze(0)
+    rec, _ = vae(x.to(dev, dtype=torch.float32), sample_posterior=sample_posterior, eps=eps)
+    return rec[0].permute(1, 2, 0)
 
 
 @torch.no_grad()

@@ -24,34 +24,40 @@ def rel(a, b):
     return float((a.float() - b.float()).norm() / b.float().norm())
 
 
+def model_and_granule(t, dev):
+    """Default model (zero-initialised convolutions re-randomised: the latents would be 0 otherwise) and one normalised
+    radiance-like granule [131, 2048, 1028]: smooth spatial fields x a smooth spectrum + noise, then the reference's
+    normalisation (fused kernel) -> z in [-10, 10]."""
+    from bench import DEFAULT_MODEL
+    t.seed_all(42)
+    model = t.get_model(DEFAULT_MODEL, dev)
+    sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    orc.rerandomize_zero_init(sd, seed=1234)
+    model.load_state_dict(sd)
+    sd = {k: v.to(dev) for k, v in sd.items()}
+    g = torch.Generator(device=dev).manual_seed(11)
+    rad = torch.exp(0.5 * torch.randn((131, 2048, 1028), device=dev, generator=g) + 3.0)
+    coarse = torch.randn((1, 8, 9, 128), device=dev, generator=g)
+    field = torch.nn.functional.interpolate(coarse, size=(131, 2048), mode="bilinear")[0]          # [8, 131, 2048]
+    basis = torch.cos(torch.linspace(0, 3.14159, 1028, device=dev)[None, :] * torch.arange(1, 9, device=dev)[:, None])
+    rad = rad * torch.exp(0.4 * torch.einsum("rhw,rc->hwc", field, basis))
+    del coarse, field
+    mean_s, std_s = t.granule_statistics(rad)
+    z = t.normalize_radiance(rad, mean_s, std_s)
+    del rad
+    assert z.shape == (131, 2048, 1028) and float(z.abs().max()) <= 10.0
+    return model, sd, z
+
+
 def test_whole_granule_encode_at_full_size_vs_oracle_on_gpu(capsys):
     import tempo_vae_b200 as t
-    from bench import DEFAULT_MODEL
     dev = torch.device("cuda")
     cfg = orc.DEFAULT_CFG
     tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     try:
-        t.seed_all(42)
-        model = t.get_model(DEFAULT_MODEL, dev)
-        sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
-        orc.rerandomize_zero_init(sd, seed=1234)              # conv_out of the encoder is zero at init: latents would be 0
-        model.load_state_dict(sd)
-        sd = {k: v.to(dev) for k, v in sd.items()}
-        g = torch.Generator(device=dev).manual_seed(11)
-        # radiance-like granule [131, 2048, 1028]: smooth spatial fields x a smooth spectrum + noise, then the reference's
-        # normalisation (fused kernel) -> z in [-10, 10]
-        rad = torch.exp(0.5 * torch.randn((131, 2048, 1028), device=dev, generator=g) + 3.0)
-        coarse = torch.randn((1, 8, 9, 128), device=dev, generator=g)
-        field = torch.nn.functional.interpolate(coarse, size=(131, 2048), mode="bilinear")[0]          # [8, 131, 2048]
-        basis = torch.cos(torch.linspace(0, 3.14159, 1028, device=dev)[None, :] * torch.arange(1, 9, device=dev)[:, None])
-        rad = rad * torch.exp(0.4 * torch.einsum("rhw,rc->hwc", field, basis))
-        del coarse, field
-        mean_s, std_s = t.granule_statistics(rad)
-        z = t.normalize_radiance(rad, mean_s, std_s)
-        del rad
-        assert z.shape == (131, 2048, 1028) and float(z.abs().max()) <= 10.0
+        model, sd, z = model_and_granule(t, dev)
         lat = t.encode_granule_whole(model, z)
         assert lat.shape == (1, 32, 32, 512)
         for _ in range(12):       # bring the clocks up: three 8 ms calls straight after an idle GPU once measured 38 ms each
@@ -90,3 +96,55 @@ def test_whole_granule_encode_at_full_size_vs_oracle_on_gpu(capsys):
               f"differs from whole-granule by {diff:.2f} (a different function, by design)")
     assert err < max(1e-2, 1.1 * floor), (err, floor)
     assert diff > 10 * err
+
+
+def test_whole_granule_reconstruction_at_full_size_vs_oracle_on_gpu(capsys):
+    """The other whole-granule caller (src/scripts/analyze_reconstruction.py:111-127): `recon = model(x)` on the
+    [1, 1028, 128, 2048] crop -- encoder, one posterior sample, decoder (a second 16,384-token attention, transposed
+    convolutions up to 128 x 2048, GroupNorm groups of 16.8 M elements) -- against the fp32 oracle on the same GPU with the
+    same noise, and the posterior-mode variant. Bound: rel-L2 of the reconstruction <= max(1e-2, 1.1 x the ideal
+    bf16-operand floor of the same variant)."""
+    import tempo_vae_b200 as t
+    dev = torch.device("cuda")
+    cfg = orc.DEFAULT_CFG
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        model, sd, z = model_and_granule(t, dev)
+        eps = torch.randn((1, 32, 32, 512), device=dev, generator=torch.Generator(device=dev).manual_seed(5))
+        rec = t.reconstruct_granule_whole(model, z, eps=eps)
+        assert rec.shape == (128, 2048, 1028) and bool(torch.isfinite(rec).all())
+        for _ in range(12):      # clocks up after the idle set-up phase (see the encode test)
+            t.reconstruct_granule_whole(model, z, eps=eps)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); e0.record()
+        for _ in range(3):
+            rec2 = t.reconstruct_granule_whole(model, z, eps=eps)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        assert torch.equal(rec, rec2)
+        mode = t.reconstruct_granule_whole(model, z, sample_posterior=False)
+        x = z[:128, :2048].permute(2, 0, 1).unsqueeze(0).contiguous()
+
+        def oracle_forward(noise):
+            mean, logvar, _ = orc.encode(sd, x, cfg)
+            return orc.decode(sd, mean + torch.exp(0.5 * logvar) * noise, cfg)[0].permute(1, 2, 0)
+
+        with torch.no_grad():
+            ref = oracle_forward(eps)
+            ref_mode = oracle_forward(torch.zeros_like(eps))
+            with orc.bf16_operands():
+                ideal = oracle_forward(eps)
+                ideal_mode = oracle_forward(torch.zeros_like(eps))
+        # two floors: with the noise injected exactly on both sides the latent's own error is diluted by std * eps; the
+        # posterior mode feeds the decoder the bare mean
+        err, err_mode, floor, floor_mode = rel(rec, ref), rel(mode, ref_mode), rel(ideal, ref), rel(ideal_mode, ref_mode)
+        gt_err = rel(rec, z[:128, :2048])            # random weights: the reconstruction is nowhere near the input
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    with capsys.disabled():
+        print(f"\n[whole-granule reconstruction 128x2048x1028] rel-L2 vs fp32 oracle on the GPU {err:.3e} (ideal-bf16 floor "
+              f"{floor:.3e}), posterior mode {err_mode:.3e} (floor {floor_mode:.3e}); engine {ms:.1f} ms per granule = {64e3 / ms:.0f} "
+              f"patch-equivalents/s; |recon - input| / |input| = {gt_err:.2f} (random weights)")
+    assert err < max(1e-2, 1.1 * floor) and err_mode < max(1e-2, 1.1 * floor_mode), (err, floor, err_mode, floor_mode)

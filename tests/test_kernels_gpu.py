@@ -711,6 +711,42 @@ def test_reparam_kl_fwd_bwd():
     assert abs(e1.mean().item()) < 0.02 and abs(e1.std().item() - 1.0) < 0.02
 
 
+def test_few_large_samples_take_the_wide_reparam_and_statistics_kernels():
+    """Whole-granule inference is ONE sample with 524 K latent elements and 2,048 tile slots per GroupNorm group. Both
+    per-sample kernels have a variant for that shape (reparam: a cluster of 8 blocks per sample, KL partials combined
+    through distributed shared memory in rank order; statistics finalize: a block per (sample, group)); they must
+    agree with the per-sample kernels on the same data -- draws and samples bit for bit -- and with torch."""
+    o = ops()
+    from tempo_vae_b200._lib import lib
+    g = torch.Generator(device="cuda").manual_seed(21)
+    Z, h, w = 32, 64, 32                                        # 65,536 latent elements per sample
+    many = torch.randn((65, h, w, 2 * Z), device="cuda", generator=g) * 2       # 65 samples: the per-sample kernel
+    few = many[:3].contiguous()                                                  # <= 64 samples: the clustered one
+    eps = torch.randn((65, Z, h, w), device="cuda", generator=g)
+    _, z_many, _, kl_many = o.reparam_fwd(many, Z, eps=eps, want_z_nchw=True)
+    zb_few, z_few, _, kl_few = o.reparam_fwd(few, Z, eps=eps[:3].contiguous(), want_z_nchw=True)
+    mean, logvar = few[..., :Z].permute(0, 3, 1, 2), few[..., Z:].permute(0, 3, 1, 2).clamp(-30.0, 20.0)
+    assert torch.equal(z_few, z_many[:3]) and rel_err(z_few, mean + torch.exp(0.5 * logvar) * eps[:3]) < 1e-6
+    assert rel_err(zb_few.float().permute(0, 3, 1, 2), z_few) < 4e-3
+    kl_ref = 0.5 * torch.sum(mean.double() ** 2 + torch.exp(logvar.double()) - 1.0 - logvar.double(), dim=[1, 2, 3])
+    assert rel_err(kl_few.double(), kl_ref) < 1e-6 and rel_err(kl_few, kl_many[:3]) < 1e-6
+    _, _, e_many, _ = o.reparam_fwd(many, Z, seed=77, sample_offset=5)
+    _, _, e_few, _ = o.reparam_fwd(few, Z, seed=77, sample_offset=5)
+    assert torch.equal(e_few, e_many[:3]) and abs(e_few.mean().item()) < 0.01 and abs(e_few.std().item() - 1.0) < 0.01
+    # statistics finalize: 300 tile slots per sample; 2 samples (wide kernel) against the same rows inside 129 samples
+    spi, G, count, eps_gn = 300, 8, 300.0 * 128 * 16, 1e-6
+    part = torch.randn((129, spi, G, 2), device="cuda", generator=g)
+    part[..., 1] = part[..., 1].abs() * 40 + 30                  # sums of squares: positive, variance > 0
+    st_many = torch.empty((129, G, 2), device="cuda")
+    st_few = torch.empty((2, G, 2), device="cuda")
+    assert lib.tvae_gn_stats_finalize(part.data_ptr(), spi, 129, G, count, eps_gn, st_many.data_ptr(), None) == 0
+    assert lib.tvae_gn_stats_finalize(part.data_ptr(), spi, 2, G, count, eps_gn, st_few.data_ptr(), None) == 0
+    s = part[:2].double().sum(dim=1)
+    m = s[..., 0] / count
+    want = torch.stack([m, 1.0 / torch.sqrt(s[..., 1] / count - m * m + eps_gn)], dim=-1)
+    assert rel_err(st_few.double(), want) < 1e-6 and rel_err(st_few, st_many[:2]) < 1e-6
+
+
 @pytest.mark.parametrize("HW,C", [(16, 1028), (32, 1028), (32, 20), (40, 7)])
 @pytest.mark.parametrize("loss_type", [0, 1])
 def test_nll(loss_type, HW, C):
