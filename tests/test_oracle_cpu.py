@@ -402,6 +402,50 @@ def test_oracle_probe_targets_match_the_reference_function():
         assert np.allclose(pooled, c["pooled"].numpy(), rtol=1e-6, atol=1e-7, equal_nan=True)
 
 
+def test_radix_select_host_logic_with_an_emulated_histogram_pass(monkeypatch):
+    """Host side of the exact median (tempo_vae_b200/probe_targets.py: order_statistics / nan_median) with
+    tvae_select_hist emulated in numpy from its documented contract (include/tvae.h): prefix narrowing over four 8-bit
+    passes, two ranks sharing a pass while they share a bucket, the even-count average, NaN holes, negative keys."""
+    import numpy as np
+    from tempo_vae_b200 import ops, probe_targets as pt
+    calls = []
+
+    def fake_select_hist(x, center, use_abs, prefix, prefix_mask, shift, hist=None):
+        v = x.numpy().astype(np.float32)
+        v = v[~np.isnan(v)]
+        if use_abs:
+            v = np.abs(v - np.float32(center))
+        bits = v.view(np.uint32)
+        keys = np.where(bits >> 31 == 1, ~bits, bits | np.uint32(0x80000000)).astype(np.uint32)
+        keys = keys[(keys & np.uint32(prefix_mask)) == np.uint32(prefix)]
+        calls.append(shift)
+        return torch.from_numpy(np.bincount((keys >> np.uint32(shift)) & np.uint32(255), minlength=256).astype(np.int64))
+
+    monkeypatch.setattr(ops, "select_hist", fake_select_hist)
+    rs = np.random.RandomState(6)
+    for a in (rs.standard_normal(501), rs.standard_normal(500), np.array([1.5, -2.5]), np.array([-4.0]),
+              np.concatenate([np.zeros(9), rs.standard_normal(8)]), rs.standard_t(2, size=4000) * 1e15,
+              rs.randint(-2, 3, size=300).astype(np.float64)):
+        a = a.astype(np.float32)
+        holes = a.copy()
+        if a.size > 4:
+            holes[rs.rand(a.size) < 0.25] = np.nan
+        for v in (a, holes):
+            good = v[~np.isnan(v)]
+            del calls[:]
+            med = pt.nan_median(torch.from_numpy(v))
+            assert med.dtype == np.float32 and med == np.median(good)
+            assert 4 <= len(calls) <= 7 and calls[0] == 24            # two ranks: at most one split on the way down
+            mad = pt.nan_median(torch.from_numpy(v), center=float(med), use_abs=True)
+            assert mad == np.median(np.abs(good - med))
+    n, vals = pt.order_statistics(torch.from_numpy(a), lambda n: range(n))
+    assert n == a.size and [vals[i] for i in range(n)] == sorted(a.tolist())
+    assert np.isnan(pt.nan_median(torch.full((3,), float("nan"))))
+    assert pt._transform("zscore", {"mean": 1.0, "std": 2.0})[:2] == (0, 1.0) and pt._transform("asinh", {"scale": 3.0})[0] == 1
+    with pytest.raises(ValueError):
+        pt._transform("boxcox", {})
+
+
 def test_epoch_shard_gives_every_rank_the_same_number_of_batches():
     """ADVICE r1: with n % world != 0, perm[rank::world] alone can hand rank 0 one batch more than the others (n=4089,
     world=8, B=256: 2 vs 1) and the ranks would issue different numbers of all-reduces."""
