@@ -14,7 +14,7 @@ from ._lib import EXPORTED, LIB_PATH, TvaeError, lib  # noqa: F401  (loads the s
 from .model import (ENGINE, AttnBlock, AutoencoderKL, Conv2d, ConvTranspose2d, Decoder,  # noqa: F401
                     DiagonalGaussianDistribution, Encoder, GroupNorm, ResNetBlock, ResNetDown, ResNetUp, SpectralVAE,
                     get_conv, get_model, get_precision, set_precision, zero_init)
-from .inference import (encode_granule_whole, encode_patches, evaluate_reconstruction, granule_to_patches,  # noqa: F401
+from .inference import (GranuleGraph, encode_granule_whole, encode_patches, evaluate_reconstruction, granule_to_patches,  # noqa: F401
                         normalize_radiance, reconstruct_granule_whole)
 from .model_with_l2 import L2PredictionHead, VAEWithL2Supervision  # noqa: F401
 from .optim import FusedAdamW  # noqa: F401

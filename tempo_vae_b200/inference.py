@@ -96,6 +96,64 @@ def reconstruct_granule_whole(model, z_rad: torch.Tensor, tile: int = 64, sample
     return rec[0].permute(1, 2, 0)
 
 
+class GranuleGraph:
+    """CUDA-graph replay of a whole-granule pass for ONE granule shape (opt-in).
+
+    A [1, C, 128, 2048] pass is a chain of 50-100 short launches on an otherwise idle GPU, so the host's launch cost shows
+    up as gaps between kernels (1.3-1.5 ms of a 6.7 / 12.5 ms pass, `tools/granule_timeline.py`). Here the chain is
+    captured once (`torch.cuda.graph`: the C ABI launches on torch's current stream, which is the capturing stream;
+    every buffer comes from torch's allocator, whose graph pool keeps the addresses -- and with them the TMA descriptors
+    baked into the launches -- valid) and replayed per granule: `g = GranuleGraph(model, z.shape); lat = g(z)`.
+
+      * `reconstruct=False`: `encode_granule_whole` -> latent means [1, Z, H/4, W/4];
+      * `reconstruct=True`: `reconstruct_granule_whole` -> [H, W, C]; the noise is injected through a static buffer that
+        is refilled per call (`eps=` or, by default, `torch.randn` on the device; the eager path draws Philox noise).
+
+    The weight packs are rebuilt inside the graph from the LIVE parameters (one launch), so optimiser steps or
+    `load_state_dict` between calls are picked up as long as the parameters stay where they are (capture after the
+    optimiser has been built: FusedAdamW moves them into its flat buffer). The returned tensor is the graph's static
+    output: it is overwritten by the next call (`.clone()` it to keep it)."""
+
+    def __init__(self, model, shape, tile: int = 64, reconstruct: bool = False, warmup: int = 3):
+        vae = model.vae if hasattr(model, "vae") else model
+        dev = next(vae.parameters()).device
+        M, T, C = (int(v) for v in shape)
+        if M < tile or T < tile:
+            raise TvaeError(f"granule {tuple(shape)} is smaller than one {tile}x{tile} patch")
+        self.model, self.reconstruct, self.shape = model, reconstruct, (M, T, C)
+        self.z = torch.zeros((M, T, C), dtype=torch.float32, device=dev)
+        self.eps = torch.zeros((1, vae.embed_dim, (M // tile) * tile // 4, (T // tile) * tile // 4), device=dev) \
+            if reconstruct else None
+        run = (lambda: reconstruct_granule_whole(model, self.z, tile, eps=self.eps)) if reconstruct else \
+            (lambda: encode_granule_whole(model, self.z, tile))
+        with torch.cuda.device(dev):
+            # warm-up AND capture on one stream of our own: the engine's scratch buffers are keyed by stream, so the ones
+            # the captured launches use are the ones allocated (outside the capture) during the warm-up
+            self._stream = torch.cuda.Stream()
+            self._stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self._stream):
+                for _ in range(max(1, warmup)):
+                    run()
+            torch.cuda.current_stream().wait_stream(self._stream)
+            torch.cuda.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, stream=self._stream):
+                self.out = run()
+
+    @torch.no_grad()
+    def __call__(self, z_rad: torch.Tensor, eps: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if tuple(z_rad.shape) != self.shape:
+            raise TvaeError(f"this graph was captured for granules of shape {self.shape}, got {tuple(z_rad.shape)}")
+        self.z.copy_(z_rad, non_blocking=True)
+        if self.reconstruct:
+            if eps is None:
+                self.eps.normal_()
+            else:
+                self.eps.copy_(eps, non_blocking=True)
+        self.graph.replay()
+        return self.out
+
+
 @torch.no_grad()
 def evaluate_reconstruction(model, x: torch.Tensor, eps: Optional[torch.Tensor] = None,
                             sample_posterior: bool = True, max_val: float = 20.0) -> dict:

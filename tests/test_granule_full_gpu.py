@@ -148,3 +148,43 @@ def test_whole_granule_reconstruction_at_full_size_vs_oracle_on_gpu(capsys):
               f"{floor:.3e}), posterior mode {err_mode:.3e} (floor {floor_mode:.3e}); engine {ms:.1f} ms per granule = {64e3 / ms:.0f} "
               f"patch-equivalents/s; |recon - input| / |input| = {gt_err:.2f} (random weights)")
     assert err < max(1e-2, 1.1 * floor) and err_mode < max(1e-2, 1.1 * floor_mode), (err, floor, err_mode, floor_mode)
+
+
+def test_granule_graph_replays_the_eager_pass_bit_for_bit(capsys):
+    """`GranuleGraph`: the whole-granule launch chain captured into a CUDA graph. Replays must equal the eager calls bit
+    for bit (same kernels, same order), follow new inputs, new noise and NEW WEIGHTS (the pack launch is inside the
+    graph), and refuse another shape. Reports the time the host's launch gaps cost."""
+    import tempo_vae_b200 as t
+    dev = torch.device("cuda")
+    model, _, z = model_and_granule(t, dev)
+    z2 = torch.roll(z, shifts=(5, 100), dims=(0, 1)).contiguous()
+
+    def timed(fn, n=5):
+        for _ in range(12):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); e0.record()
+        for _ in range(n):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    enc = t.GranuleGraph(model, z.shape)
+    assert torch.equal(enc(z), t.encode_granule_whole(model, z))
+    lat1 = enc(z).clone()                                       # the graph's output buffer is reused by the next call
+    assert torch.equal(enc(z2), t.encode_granule_whole(model, z2)) and not torch.equal(lat1, enc(z2))
+    rec = t.GranuleGraph(model, z.shape, reconstruct=True)
+    eps = torch.randn((1, 32, 32, 512), device=dev, generator=torch.Generator(device=dev).manual_seed(8))
+    assert torch.equal(rec(z, eps=eps), t.reconstruct_granule_whole(model, z, eps=eps))
+    a = rec(z).clone()
+    assert not torch.equal(a, rec(z))                          # fresh noise per call when none is given
+    with torch.no_grad():                                      # weights changed behind the graph's back
+        model.vae.encoder.conv_in.weight.data.mul_(1.5)
+    assert torch.equal(enc(z), t.encode_granule_whole(model, z))
+    with pytest.raises(t.TvaeError):
+        enc(z[:, :1024])
+    ms = {"encode eager": timed(lambda: t.encode_granule_whole(model, z)), "encode graph": timed(lambda: enc(z)),
+          "reconstruct eager": timed(lambda: t.reconstruct_granule_whole(model, z, eps=eps)),
+          "reconstruct graph": timed(lambda: rec(z, eps=eps))}
+    with capsys.disabled():
+        print("\n[granule graph] ms per granule: " + ", ".join(f"{k} {v:.2f}" for k, v in ms.items()))
